@@ -1,0 +1,412 @@
+"""pbf-cuda_b200 — Python host-side mirror of the reference's Simulator interface over the C-ABI.
+
+The product is `libpbf_b200.so` (hand-written sm_100a kernels behind include/pbf.h). This module
+is a thin ctypes binding used by tests/, bench.py and __graft_entry__.py; it mirrors the
+reference's `Simulator` (fluids/Simulator.h:10,37-42), `GUIParams` (fluids/GUIParams.h:7-17) and
+`ParticleSource` scenes (fluids/ParticleSource.h:11-13). There is no CPU fallback: if the shared
+library is missing, importing this module fails; if no sm_100 GPU is present, every compute call
+raises PbfError.
+
+The directory name has a hyphen (the project's name), so import it with
+    pbf = importlib.import_module("pbf-cuda_b200")
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpbf_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, 1, 2, 3, 4
+
+READ_KEY, READ_SRC_INDEX, READ_IID, READ_CELL_START, READ_CELL_END, READ_NPOS, READ_LAMBDA, READ_RHO, \
+    READ_POS0, READ_VEL, READ_NEIGHBOR_COUNT = range(11)
+
+STAGE_NAMES = ("ADVECT", "GRID", "DENSITY", "VELOCITY_UPDATE", "VELOCITY_CORRECT")  # reference Logger.h:7-23
+
+# every symbol include/pbf.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "pbf_default_params", "pbf_create", "pbf_destroy", "pbf_set_params", "pbf_get_params", "pbf_set_lim",
+    "pbf_get_lim", "pbf_set_option_exact_pow", "pbf_get_grid_dim", "pbf_step", "pbf_step_host",
+    "pbf_stage_begin", "pbf_stage_advect", "pbf_stage_build_grid", "pbf_stage_correct_density",
+    "pbf_stage_update_velocity", "pbf_stage_correct_velocity", "pbf_stage_end", "pbf_read", "pbf_get_stats",
+    "pbf_enable_stage_timing", "pbf_get_stage_ms", "pbf_launch_count", "pbf_device_alloc", "pbf_device_free",
+    "pbf_copy_h2d", "pbf_copy_d2h", "pbf_device_sync", "pbf_scene_cube", "pbf_scene_double_dam_reference",
+    "pbf_scene_block_device", "pbf_scene_block_host", "pbf_last_error", "pbf_version",
+)
+
+
+class PbfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pbf error %d: %s" % (code, msg))
+        self.code = code
+
+
+class GUIParams(C.Structure):
+    """Fluid half of the reference's GUIParams (fluids/GUIParams.h:7-17); layout == pbf_params."""
+    _fields_ = [("niter", C.c_int32), ("pho0", C.c_float), ("g", C.c_float), ("h", C.c_float),
+                ("dt", C.c_float), ("lambda_eps", C.c_float), ("delta_q", C.c_float),
+                ("k_corr", C.c_float), ("n_corr", C.c_float), ("k_boundaryDensity", C.c_float),
+                ("c_XSPH", C.c_float)]
+
+    def copy(self):
+        q = GUIParams()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(GUIParams))
+        return q
+
+
+class Stats(C.Structure):
+    _fields_ = [("density_err_mean", C.c_double), ("density_err_max", C.c_double),
+                ("kinetic_energy", C.c_double), ("max_speed", C.c_double), ("mean_z", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("%s is missing: run `make -C pbf-cuda_b200` (or __graft_entry__.build()); "
+                      "there is no CPU fallback" % LIB_PATH)
+
+_lib = C.CDLL(LIB_PATH)
+_vp, _i64, _f3 = C.c_void_p, C.c_int64, C.POINTER(C.c_float)
+_lib.pbf_default_params.argtypes = [C.POINTER(GUIParams)]
+_lib.pbf_create.argtypes = [C.POINTER(GUIParams), _f3, _f3, _i64, C.c_int, C.POINTER(_vp)]
+_lib.pbf_destroy.argtypes = [_vp]
+_lib.pbf_set_params.argtypes = [_vp, C.POINTER(GUIParams)]
+_lib.pbf_get_params.argtypes = [_vp, C.POINTER(GUIParams)]
+_lib.pbf_set_lim.argtypes = [_vp, _f3, _f3]
+_lib.pbf_get_lim.argtypes = [_vp, _f3, _f3]
+_lib.pbf_set_option_exact_pow.argtypes = [_vp, C.c_int]
+_lib.pbf_get_grid_dim.argtypes = [_vp, C.POINTER(C.c_int32)]
+_lib.pbf_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.pbf_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64]
+_lib.pbf_stage_begin.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+for _n in ("advect", "build_grid", "correct_density", "update_velocity", "correct_velocity", "end"):
+    getattr(_lib, "pbf_stage_" + _n).argtypes = [_vp]
+_lib.pbf_read.argtypes = [_vp, C.c_int, _vp, _i64]
+_lib.pbf_get_stats.argtypes = [_vp, _vp, _vp, _i64, C.POINTER(Stats)]
+_lib.pbf_enable_stage_timing.argtypes = [_vp, C.c_int]
+_lib.pbf_get_stage_ms.argtypes = [_vp, _f3]
+_lib.pbf_launch_count.argtypes = [_vp]
+_lib.pbf_launch_count.restype = _i64
+_lib.pbf_device_alloc.argtypes = [C.c_int, _i64, C.POINTER(_vp)]
+_lib.pbf_device_free.argtypes = [C.c_int, _vp]
+_lib.pbf_copy_h2d.argtypes = [_vp, _vp, _i64]
+_lib.pbf_copy_d2h.argtypes = [_vp, _vp, _i64]
+_lib.pbf_device_sync.argtypes = [C.c_int]
+_lib.pbf_scene_cube.argtypes = [_f3, _f3, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_uint32, _vp, _vp, _vp,
+                                _i64, C.POINTER(_i64)]
+_lib.pbf_scene_double_dam_reference.argtypes = [_vp, _vp, _vp, _i64, C.POINTER(_i64), _f3, _f3]
+_lib.pbf_scene_block_device.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]
+_lib.pbf_scene_block_host.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, _vp, _vp, _vp]
+_lib.pbf_last_error.restype = C.c_char_p
+_lib.pbf_version.restype = C.c_char_p
+
+
+def lib():
+    return _lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise PbfError(rc, _lib.pbf_last_error().decode())
+
+
+def _f3arr(v):
+    a = np.ascontiguousarray(np.asarray(v, np.float32).reshape(3))
+    return a, a.ctypes.data_as(_f3)
+
+
+def _ptr(x):
+    """Device pointer of a torch tensor / DeviceBuffer / int; host pointer of a numpy array."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        assert x.flags.c_contiguous
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ptr"):
+        return x.ptr
+    raise TypeError(type(x))
+
+
+def version():
+    return _lib.pbf_version().decode()
+
+
+def default_params():
+    """Defaults the reference writes at FluidSystem.cpp:15-25."""
+    p = GUIParams()
+    _check(_lib.pbf_default_params(C.byref(p)))
+    return p
+
+
+class DeviceBuffer:
+    """cudaMalloc'ed buffer through the C-ABI helpers (for callers that do not use torch)."""
+
+    def __init__(self, nbytes, device=0):
+        self.device, self.nbytes = device, int(nbytes)
+        p = _vp()
+        _check(_lib.pbf_device_alloc(device, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _check(_lib.pbf_copy_h2d(self.ptr, arr.ctypes.data, arr.nbytes))
+        return self
+
+    def download(self, dtype, shape):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        _check(_lib.pbf_copy_d2h(out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            _lib.pbf_device_free(self.device, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Simulator:
+    """Mirror of the reference's `Simulator` (fluids/Simulator.h:7-61).
+
+    Simulator(params, ulim, llim)   <- Simulator(const GUIParams&, float3 ulim, float3 llim)
+    step(pos, npos, vel, nvel, iid, n) <- step(uint d_pos, ..., int nparticle), on device buffers
+    loadParams(params) / saveParams()  <- loadParams() / saveParams() without the singleton
+    setLim(ulim, llim)                 <- setLim(const float3&, const float3&)
+    """
+
+    def __init__(self, params, ulim, llim, max_particles, device=0):
+        self._h = None
+        u, up = _f3arr(ulim)
+        l, lp = _f3arr(llim)
+        h = _vp()
+        _check(_lib.pbf_create(C.byref(params), up, lp, int(max_particles), device, C.byref(h)))
+        self._h = h.value
+        self.device = device
+        self.max_particles = int(max_particles)
+        self.n = 0
+
+    def close(self):
+        if self._h:
+            _lib.pbf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters / box
+    def loadParams(self, params):
+        _check(_lib.pbf_set_params(self._h, C.byref(params)))
+
+    def saveParams(self):
+        p = GUIParams()
+        _check(_lib.pbf_get_params(self._h, C.byref(p)))
+        return p
+
+    def setLim(self, ulim, llim):
+        u, up = _f3arr(ulim)
+        l, lp = _f3arr(llim)
+        _check(_lib.pbf_set_lim(self._h, up, lp))
+
+    def getLim(self):
+        u = np.zeros(3, np.float32)
+        l = np.zeros(3, np.float32)
+        _check(_lib.pbf_get_lim(self._h, u.ctypes.data_as(_f3), l.ctypes.data_as(_f3)))
+        return u, l
+
+    def set_exact_pow(self, on):
+        _check(_lib.pbf_set_option_exact_pow(self._h, int(bool(on))))
+
+    def grid_dim(self):
+        d = (C.c_int32 * 3)()
+        _check(_lib.pbf_get_grid_dim(self._h, d))
+        return tuple(d)
+
+    # -- the hot path
+    def step(self, pos, npos, vel, nvel, iid, n, stream=None):
+        self.n = int(n)
+        _check(_lib.pbf_step(self._h, _ptr(pos), _ptr(npos), _ptr(vel), _ptr(nvel), _ptr(iid), int(n), stream))
+
+    def step_host(self, pos, npos, vel, nvel, iid):
+        n = len(iid)
+        self.n = n
+        for a in (pos, npos, vel, nvel):
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.size == 3 * n
+        assert iid.dtype == np.uint32 and iid.flags.c_contiguous
+        _check(_lib.pbf_step_host(self._h, _ptr(pos), _ptr(npos), _ptr(vel), _ptr(nvel), _ptr(iid), n))
+
+    # -- stages (reference Simulator.h:44-48)
+    def begin(self, pos, npos, vel, nvel, iid, n, stream=None):
+        self.n = int(n)
+        _check(_lib.pbf_stage_begin(self._h, _ptr(pos), _ptr(npos), _ptr(vel), _ptr(nvel), _ptr(iid), int(n), stream))
+
+    def advect(self): _check(_lib.pbf_stage_advect(self._h))
+    def buildGridHash(self): _check(_lib.pbf_stage_build_grid(self._h))
+    def correctDensity(self): _check(_lib.pbf_stage_correct_density(self._h))
+    def updateVelocity(self): _check(_lib.pbf_stage_update_velocity(self._h))
+    def correctVelocity(self): _check(_lib.pbf_stage_correct_velocity(self._h))
+    def end(self): _check(_lib.pbf_stage_end(self._h))
+
+    # -- read-backs
+    def read(self, what, count=None):
+        if what in (READ_CELL_START, READ_CELL_END):
+            d = self.grid_dim()
+            count = d[0] * d[1] * d[2] if count is None else count
+            out = np.empty(count, np.uint32)
+        elif what in (READ_NPOS, READ_POS0, READ_VEL):
+            count = self.n if count is None else count
+            out = np.empty((count, 3), np.float32)
+        elif what in (READ_LAMBDA, READ_RHO):
+            count = self.n if count is None else count
+            out = np.empty(count, np.float32)
+        else:
+            count = self.n if count is None else count
+            out = np.empty(count, np.uint32)
+        _check(_lib.pbf_read(self._h, what, out.ctypes.data, count))
+        return out
+
+    def stats(self, npos, nvel, n):
+        st = Stats()
+        _check(_lib.pbf_get_stats(self._h, _ptr(npos), _ptr(nvel), int(n), C.byref(st)))
+        return st.as_dict()
+
+    def enable_stage_timing(self, on=True):
+        _check(_lib.pbf_enable_stage_timing(self._h, int(on)))
+
+    def stage_ms(self):
+        ms = (C.c_float * 5)()
+        _check(_lib.pbf_get_stage_ms(self._h, ms))
+        return dict(zip(STAGE_NAMES, list(ms)))
+
+    def launch_count(self):
+        return int(_lib.pbf_launch_count(self._h))
+
+
+# ---- ParticleSource scenes (fluids/ParticleSource.h, DoubleDamSource.*, FixedCubeSource.*) ----
+
+class ParticleSource:
+    """initialize() returns host arrays (pos[n,3], vel[n,3], iid[n]); update()/reset() follow the
+    reference: update returns the count unchanged, reset == initialize (DoubleDamSource.cpp:43-49)."""
+
+    def initialize(self):
+        raise NotImplementedError
+
+    def update(self):
+        return self.count
+
+    def reset(self):
+        return self.initialize()
+
+
+class FixedCubeSource(ParticleSource):
+    """FixedCubeSource(ulim, llim, ns) (fluids/FixedCubeSource.h:12-20)."""
+
+    def __init__(self, ulim, llim, ns, seed=27):
+        self.ulim, self.llim, self.ns, self.seed = ulim, llim, ns, seed
+        self.count = 0
+
+    def initialize(self):
+        pos, vel, iid, _ = _scene_cubes([(self.ulim, self.llim, self.ns)], self.seed)
+        self.count = len(iid)
+        return pos, vel, iid
+
+
+class DoubleDamSource(ParticleSource):
+    """DoubleDamSource(ulim1, llim1, ns1, ulim2, llim2, ns2) (fluids/DoubleDamSource.h:11-23)."""
+
+    def __init__(self, ulim1, llim1, ns1, ulim2, llim2, ns2, seed=27):
+        self.blocks = [(ulim1, llim1, ns1), (ulim2, llim2, ns2)]
+        self.seed = seed
+        self.count = 0
+
+    def initialize(self):
+        pos, vel, iid, _ = _scene_cubes(self.blocks, self.seed)
+        self.count = len(iid)
+        return pos, vel, iid
+
+
+def _scene_cubes(blocks, seed):
+    total = sum(int(np.prod(b[2])) for b in blocks)
+    pos = np.zeros((total, 3), np.float32)
+    vel = np.zeros((total, 3), np.float32)
+    iid = np.zeros(total, np.uint32)
+    rng = C.c_uint32(seed)
+    off = 0
+    for ulim, llim, ns in blocks:
+        u, up = _f3arr(ulim)
+        l, lp = _f3arr(llim)
+        nsa = (C.c_int32 * 3)(*[int(v) for v in ns])
+        cnt = _i64()
+        _check(_lib.pbf_scene_cube(up, lp, nsa, C.byref(rng), off, pos[off:].ctypes.data, vel[off:].ctypes.data,
+                                   iid[off:].ctypes.data, total - off, C.byref(cnt)))
+        off += cnt.value
+    return pos, vel, iid, rng.value
+
+
+def scene_double_dam_reference():
+    """The reference's shipped scene (FluidSystem.cpp:34-35,55-61): returns pos, vel, iid, ulim, llim."""
+    pos = np.zeros((32000, 3), np.float32)
+    vel = np.zeros((32000, 3), np.float32)
+    iid = np.zeros(32000, np.uint32)
+    ulim = np.zeros(3, np.float32)
+    llim = np.zeros(3, np.float32)
+    cnt = _i64()
+    _check(_lib.pbf_scene_double_dam_reference(pos.ctypes.data, vel.ctypes.data, iid.ctypes.data, 32000, C.byref(cnt),
+                                               ulim.ctypes.data_as(_f3), llim.ctypes.data_as(_f3)))
+    assert cnt.value == 32000
+    return pos, vel, iid, ulim, llim
+
+
+def scene_block_host(origin, n3, spacing=0.05, seed=27, first_iid=0):
+    o, op = _f3arr(origin)
+    n3a = (C.c_int32 * 3)(*[int(v) for v in n3])
+    total = int(n3[0]) * int(n3[1]) * int(n3[2])
+    pos = np.zeros((total, 3), np.float32)
+    vel = np.zeros((total, 3), np.float32)
+    iid = np.zeros(total, np.uint32)
+    _check(_lib.pbf_scene_block_host(op, n3a, spacing, seed, first_iid, pos.ctypes.data, vel.ctypes.data, iid.ctypes.data))
+    return pos, vel, iid
+
+
+def scene_block_device(origin, n3, d_pos, d_vel, d_iid, spacing=0.05, seed=27, first_iid=0, stream=None):
+    o, op = _f3arr(origin)
+    n3a = (C.c_int32 * 3)(*[int(v) for v in n3])
+    _check(_lib.pbf_scene_block_device(op, n3a, spacing, seed, first_iid, _ptr(d_pos), _ptr(d_vel), _ptr(d_iid), stream))
+    return int(n3[0]) * int(n3[1]) * int(n3[2])
+
+
+def wall_lim(ulim0, llim0, a_ulim, a_llim, w, frame, start_frame=0):
+    """Moving-wall schedule of FluidSystem::stepSimulate (FluidSystem.cpp:104-110):
+    float t = w*(frame-start); float phi = sin(t); lim = lim0 + A*phi (all float)."""
+    t = np.float32(np.float32(w) * np.float32(frame - start_frame))
+    phi = np.float32(np.sin(np.float64(t)))
+    u = np.asarray(ulim0, np.float32) + np.asarray(a_ulim, np.float32) * phi
+    l = np.asarray(llim0, np.float32) + np.asarray(a_llim, np.float32) * phi
+    return u.astype(np.float32), l.astype(np.float32)
+
+
+# The named benchmark scenes (BASELINE.md section 3 / SURVEY.md 8d).
+SCENES = {
+    "double_dam_32k": dict(ulim=(2.0, 2.0, 4.0), llim=(-2.0, -2.0, 0.0), n=32000),
+    "dam_1m": dict(ulim=(16.0, 3.6, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (128, 64, 128))]),
+    "sweep_4m": dict(ulim=(19.2, 6.8, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (256, 128, 128))],
+                     wall=dict(a_ulim=(4.8, 0.0, 0.0), a_llim=(0.0, 0.0, 0.0), w=0.05), ulim_max=(24.0, 6.8, 9.6)),
+    "double_dam_16m": dict(ulim=(38.4, 38.4, 9.6), llim=(0.0, 0.0, 0.0),
+                           blocks=[((0.2, 25.4, 0.2), (256, 256, 128)), ((25.4, 0.2, 0.2), (256, 256, 128))]),
+    "dam_64m": dict(ulim=(76.8, 26.0, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (1024, 512, 128))]),
+}

@@ -1,0 +1,572 @@
+// pbf_capi.cu — the C-ABI of include/pbf.h: handle lifetime, parameters, the step and its stages.
+//
+// Host-side mirror of the reference's Simulator (fluids/Simulator.h, Simulator.cpp): same five
+// stages in the same order; GL interop replaced by raw device pointers; the process-wide
+// GUIParams singleton replaced by a parameter block in the handle; checkCudaErrors' print+exit
+// replaced by status codes.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "pbf_internal.h"
+
+using namespace pbf;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(PBF_ERR_CUDA, "CUDA error at %s:%d code=%d(%s) \"%s\"", __FILE__, __LINE__, \
+                        (int)e__, cudaGetErrorName(e__), #expr);                                 \
+    } while (0)
+
+// dst[i*width + k] = src[i*stride + offset + k]: de-interleaves one field of an internal
+// SoA-of-struct array into a tight array for the parity read-backs.
+__global__ void extract_words_kernel(const uint32_t* __restrict__ src, int stride, int offset, int width,
+                                     uint32_t* __restrict__ dst, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t i = t / width;
+    const int k = (int)(t % width);
+    dst[t] = src[i * stride + offset + k];
+}
+
+enum Stage { ST_IDLE = 0, ST_BOUND, ST_ADVECTED, ST_GRID, ST_DENSITY, ST_VELOCITY, ST_XSPH };
+
+}  // namespace
+
+struct pbf_sim {
+    int device = 0;
+    pbf_params p{};
+    float ulim[3]{}, llim[3]{};
+    int64_t max_particles = 0;
+    int64_t cell_capacity = 0;
+    int exact_pow = 0;
+
+    // scratch (device)
+    uint32_t* keys = nullptr;
+    uint32_t* sort_zero = nullptr;  // [hist | tile counters | tile descriptors], zeroed per step
+    size_t sort_zero_capacity = 0;
+    KeyIdx* pairs[2] = {nullptr, nullptr};
+    float4* x[2] = {nullptr, nullptr};
+    float4* xl = nullptr;   // (x, y, z, lambda); reused as (vx, vy, vz, rho) after the last delta-p pass
+    float* rho = nullptr;
+    uint32_t* iid_sorted = nullptr;
+    uint2* cell_range = nullptr;
+    uint32_t* count_scratch = nullptr;
+    uint32_t* read_scratch = nullptr;
+    double* stats_partial = nullptr;
+    double* stats_host = nullptr;
+    // staging for pbf_step_host
+    float* h_pos = nullptr; float* h_npos = nullptr; float* h_vel = nullptr; float* h_nvel = nullptr;
+    uint32_t* h_iid = nullptr;
+
+    // bound state of the step in flight
+    Stage stage = ST_IDLE;
+    float *pos = nullptr, *npos = nullptr, *vel = nullptr, *nvel = nullptr;
+    uint32_t* iid = nullptr;
+    int64_t n = 0;
+    cudaStream_t stream = nullptr;
+    GridConsts g{};
+    SolverConsts c{};
+    int npass = 1;
+    int sorted_buf = 0;
+    int cur = 0;         // x[cur] holds the current iterate
+    int iters_done = 0;
+    bool pos0_in_npos = false;
+
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[6] = {};
+    bool ev_valid = false;
+};
+
+namespace {
+
+int key_bits(int64_t ncell) {
+    int b = 0;
+    while (((int64_t)1 << b) < ncell) b++;
+    return b < 1 ? 1 : b;
+}
+
+// Grid dims as the reference recomputes them every step (Simulator.cu:187-188).
+void compute_dim(const float ulim[3], const float llim[3], float h, int32_t dim[3]) {
+    for (int a = 0; a < 3; a++) {
+        float diff = ulim[a] - llim[a];
+        dim[a] = (int32_t)ceilf(diff / h);
+    }
+}
+
+int refresh_consts(pbf_sim* s) {
+    GridConsts& g = s->g;
+    SolverConsts& c = s->c;
+    const pbf_params& p = s->p;
+    if (!(p.h > 0.f) || !(p.dt > 0.f) || p.niter < 0) return fail(PBF_ERR_INVALID, "bad parameters (h, dt, niter)");
+    for (int a = 0; a < 3; a++) { g.llim[a] = s->llim[a]; g.ulim[a] = s->ulim[a]; }
+    g.h = p.h;
+    compute_dim(s->ulim, s->llim, p.h, g.dim);
+    if (g.dim[0] < 1 || g.dim[1] < 1 || g.dim[2] < 1) return fail(PBF_ERR_INVALID, "empty box");
+    const int64_t ncell = (int64_t)g.dim[0] * g.dim[1] * g.dim[2];
+    if (ncell > s->cell_capacity || ncell >= ((int64_t)1 << 30))
+        return fail(PBF_ERR_CAPACITY, "box has %lld cells, handle holds %lld", (long long)ncell, (long long)s->cell_capacity);
+    g.ncell = (int32_t)ncell;
+    g.dyz = g.dim[1] * g.dim[2];
+    s->npass = (key_bits(ncell) + RADIX_BITS - 1) / RADIX_BITS;
+
+    // getPoly6 / getSpikyGrad constructors and h_updateVelocity, host arithmetic as in the
+    // reference (Simulator.cu:77-83, 94-98, 129); M_PI there is the double literal 3.14159265359.
+    const double ref_pi = 3.14159265359;
+    const float h = p.h;
+    c.h = h;
+    c.h2 = h * h;
+    c.h2_cull = c.h2 * 1.000001f;
+    const float ih = 1.f / h;
+    const float ih3 = ih * ih * ih;
+    const float ih9 = ih3 * ih3 * ih3;
+    c.poly6_coef = (float)((double)(315.f * ih9) / ((double)64.f * ref_pi));
+    float h6 = h * h;
+    h6 = h6 * h6 * h6;
+    c.spiky_coef = (float)((double)-45.f / (ref_pi * (double)h6));
+    c.pho0 = p.pho0;
+    c.lambda_eps = p.lambda_eps;
+    c.k_boundary = p.k_boundaryDensity;
+    // m_coef_corr = -k_corr / powf(poly6(dq*dq), n_corr), host powf (Simulator.cu:235)
+    {
+        const float r2 = p.delta_q * p.delta_q;
+        float w = 0.f;
+        if (!(r2 >= c.h2)) {
+            const float d = c.h2 - r2;
+            w = c.poly6_coef * d * d * d;
+        }
+        c.coef_corr = -p.k_corr / powf(w, p.n_corr);
+    }
+    c.n_corr = p.n_corr;
+    c.c_xsph = p.c_XSPH;
+    c.dt = p.dt;
+    c.inv_dt = 1.f / p.dt;
+    c.gravity = p.g;
+    for (int a = 0; a < 3; a++) {
+        c.lim_hi[a] = (double)s->ulim[a] - 1e-3;  // LIM_EPS, helper.h:5
+        c.lim_lo[a] = (double)s->llim[a] + 1e-3;
+    }
+    c.exact_pow = s->exact_pow;
+    return PBF_OK;
+}
+
+void free_all(pbf_sim* s) {
+    cudaFree(s->keys); cudaFree(s->sort_zero); cudaFree(s->pairs[0]); cudaFree(s->pairs[1]);
+    cudaFree(s->x[0]); cudaFree(s->x[1]); cudaFree(s->xl); cudaFree(s->rho); cudaFree(s->iid_sorted);
+    cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
+    cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
+    if (s->stats_host) cudaFreeHost(s->stats_host);
+    if (s->ev_valid) for (auto& e : s->ev) cudaEventDestroy(e);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pbf_last_error(void) { return g_err; }
+const char* pbf_version(void) { return "pbf-cuda_b200 0.1 (sm_100a)"; }
+
+int pbf_default_params(pbf_params* p) {
+    if (!p) return fail(PBF_ERR_INVALID, "null params");
+    // FluidSystem.cpp:15-25
+    p->g = 9.8f;
+    p->h = .1f;
+    p->dt = 0.0083f;
+    p->pho0 = 8000.f;
+    p->lambda_eps = 1000.f;
+    p->delta_q = (float)(0.3 * (double)p->h);
+    p->k_corr = 0.001f;
+    p->n_corr = 4;
+    p->k_boundaryDensity = 0.f;
+    p->c_XSPH = 0.5f;
+    p->niter = 4;
+    return PBF_OK;
+}
+
+int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3], int64_t max_particles,
+               int device, pbf_sim** out) {
+    if (!params || !ulim || !llim || !out) return fail(PBF_ERR_INVALID, "null argument");
+    if (max_particles <= 0 || max_particles >= ((int64_t)1 << 30)) return fail(PBF_ERR_INVALID, "max_particles out of range");
+    *out = nullptr;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PBF_ERR_CUDA, "no CUDA device %d (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(PBF_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+
+    pbf_sim* s = new (std::nothrow) pbf_sim;
+    if (!s) return fail(PBF_ERR_INVALID, "out of host memory");
+    s->device = device;
+    s->p = *params;
+    memcpy(s->ulim, ulim, sizeof(float) * 3);
+    memcpy(s->llim, llim, sizeof(float) * 3);
+    s->max_particles = max_particles;
+    // cell capacity: the reference's 4*(int)(dx*dy*dz) with d = (ulim-llim)/0.1 (Simulator.h:13-14),
+    // but never less than twice the cells of this box at the actual h (the sweep widens it 1.5x).
+    int32_t dim[3];
+    compute_dim(ulim, llim, params->h, dim);
+    const int64_t cells = (int64_t)dim[0] * dim[1] * dim[2];
+    const double dx = (ulim[0] - llim[0]) / 0.1, dy = (ulim[1] - llim[1]) / 0.1, dz = (ulim[2] - llim[2]) / 0.1;
+    int64_t cap = 4 * (int64_t)(dx * dy * dz);
+    if (cap < 2 * cells) cap = 2 * cells;
+    if (cap < 1) cap = 1;
+    if (cap >= ((int64_t)1 << 30)) cap = ((int64_t)1 << 30) - 1;
+    s->cell_capacity = cap;
+    const char* ep = getenv("PBF_EXACT_POW");
+    s->exact_pow = (ep && ep[0] == '1') ? 1 : 0;
+
+    const size_t n = (size_t)max_particles;
+    s->sort_zero_capacity = sort_scratch_zero_bytes(max_particles, MAX_PASSES);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&s->keys, n * 4);
+    A((void**)&s->sort_zero, s->sort_zero_capacity);
+    A((void**)&s->pairs[0], n * sizeof(KeyIdx));
+    A((void**)&s->pairs[1], n * sizeof(KeyIdx));
+    A((void**)&s->x[0], n * sizeof(float4));
+    A((void**)&s->x[1], n * sizeof(float4));
+    A((void**)&s->xl, n * sizeof(float4));
+    A((void**)&s->rho, n * 4);
+    A((void**)&s->iid_sorted, n * 4);
+    A((void**)&s->cell_range, (size_t)cap * sizeof(uint2));
+    A((void**)&s->stats_partial, 1024 * 5 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->stats_host, 1024 * 5 * sizeof(double));
+    if (e != cudaSuccess) {
+        free_all(s);
+        delete s;
+        return fail(PBF_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    }
+    int rc = refresh_consts(s);
+    if (rc != PBF_OK) { free_all(s); delete s; return rc; }
+    *out = s;
+    return PBF_OK;
+}
+
+int pbf_destroy(pbf_sim* s) {
+    if (!s) return PBF_OK;
+    cudaSetDevice(s->device);
+    free_all(s);
+    delete s;
+    return PBF_OK;
+}
+
+int pbf_set_params(pbf_sim* s, const pbf_params* p) {
+    if (!s || !p) return fail(PBF_ERR_INVALID, "null argument");
+    pbf_params old = s->p;
+    s->p = *p;
+    int rc = refresh_consts(s);
+    if (rc != PBF_OK) { s->p = old; refresh_consts(s); }
+    return rc;
+}
+int pbf_get_params(const pbf_sim* s, pbf_params* out) {
+    if (!s || !out) return fail(PBF_ERR_INVALID, "null argument");
+    *out = s->p;
+    return PBF_OK;
+}
+int pbf_set_option_exact_pow(pbf_sim* s, int on) {
+    if (!s) return fail(PBF_ERR_INVALID, "null argument");
+    s->exact_pow = on ? 1 : 0;
+    return refresh_consts(s);
+}
+int pbf_set_lim(pbf_sim* s, const float ulim[3], const float llim[3]) {
+    if (!s || !ulim || !llim) return fail(PBF_ERR_INVALID, "null argument");
+    float ou[3], ol[3];
+    memcpy(ou, s->ulim, sizeof(ou)); memcpy(ol, s->llim, sizeof(ol));
+    memcpy(s->ulim, ulim, sizeof(float) * 3);
+    memcpy(s->llim, llim, sizeof(float) * 3);
+    int rc = refresh_consts(s);
+    if (rc != PBF_OK) { memcpy(s->ulim, ou, sizeof(ou)); memcpy(s->llim, ol, sizeof(ol)); refresh_consts(s); }
+    return rc;
+}
+int pbf_get_lim(const pbf_sim* s, float ulim[3], float llim[3]) {
+    if (!s || !ulim || !llim) return fail(PBF_ERR_INVALID, "null argument");
+    memcpy(ulim, s->ulim, sizeof(float) * 3);
+    memcpy(llim, s->llim, sizeof(float) * 3);
+    return PBF_OK;
+}
+int pbf_get_grid_dim(const pbf_sim* s, int32_t dim[3]) {
+    if (!s || !dim) return fail(PBF_ERR_INVALID, "null argument");
+    dim[0] = s->g.dim[0]; dim[1] = s->g.dim[1]; dim[2] = s->g.dim[2];
+    return PBF_OK;
+}
+int64_t pbf_launch_count(const pbf_sim* s) { return s ? s->launches : 0; }
+
+/* ---- stages ------------------------------------------------------------------------------- */
+
+static int stage_event(pbf_sim* s, int k) {
+    if (s->timing) CUDA_TRY(cudaEventRecord(s->ev[k], s->stream));
+    return PBF_OK;
+}
+
+int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n,
+                    void* stream) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    if (n < 0 || n > s->max_particles) return fail(PBF_ERR_CAPACITY, "n=%lld exceeds max_particles=%lld", (long long)n, (long long)s->max_particles);
+    if (n > 0 && (!pos || !npos || !vel || !nvel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
+    CUDA_TRY(cudaSetDevice(s->device));
+    s->pos = pos; s->npos = npos; s->vel = vel; s->nvel = nvel; s->iid = iid; s->n = n;
+    s->stream = (cudaStream_t)stream;
+    s->cur = 0;
+    s->iters_done = 0;
+    s->pos0_in_npos = false;
+    s->stage = ST_BOUND;
+    return PBF_OK;
+}
+
+int pbf_stage_advect(pbf_sim* s) {
+    if (!s || s->stage != ST_BOUND) return fail(PBF_ERR_STATE, "advect: call pbf_stage_begin first");
+    int rc = stage_event(s, 0);
+    if (rc) return rc;
+    const size_t zero_bytes = sort_scratch_zero_bytes(s->n, s->npass);
+    CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, zero_bytes, s->stream));
+    s->launches++;
+    CUDA_TRY(launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->g, s->c, s->stream, &s->launches));
+    s->stage = ST_ADVECTED;
+    return stage_event(s, 1);
+}
+
+int pbf_stage_build_grid(pbf_sim* s) {
+    if (!s || s->stage != ST_ADVECTED) return fail(PBF_ERR_STATE, "build_grid: advect first");
+    SortScratch sc;
+    sc.hist = s->sort_zero;
+    sc.tile_counter = s->sort_zero + MAX_PASSES * RADIX;
+    sc.tile_desc = s->sort_zero + MAX_PASSES * RADIX + MAX_PASSES;
+    sc.bufs[0] = s->pairs[0];
+    sc.bufs[1] = s->pairs[1];
+    sc.tile_desc_words = 0;
+    CUDA_TRY(launch_sort(s->keys, sc, s->n, s->npass, &s->sorted_buf, s->stream, &s->launches));
+    CUDA_TRY(launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->npos, s->iid_sorted,
+                            s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+    s->cur = 0;
+    s->pos0_in_npos = true;
+    s->stage = ST_GRID;
+    return stage_event(s, 2);
+}
+
+int pbf_stage_correct_density(pbf_sim* s) {
+    if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "correct_density: build_grid first");
+    CUDA_TRY(launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+    CUDA_TRY(launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+    s->cur ^= 1;
+    s->iters_done++;
+    s->stage = ST_DENSITY;
+    return PBF_OK;
+}
+
+int pbf_stage_update_velocity(pbf_sim* s) {
+    if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "update_velocity: build_grid first");
+    int rc = stage_event(s, 3);
+    if (rc) return rc;
+    // xl is dead after the last delta-p pass: reuse it for (velocity, rho)
+    CUDA_TRY(launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->n, s->c, s->stream, &s->launches));
+    s->pos0_in_npos = false;
+    s->stage = ST_VELOCITY;
+    return stage_event(s, 4);
+}
+
+int pbf_stage_correct_velocity(pbf_sim* s) {
+    if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
+    CUDA_TRY(launch_xsph(s->x[s->cur], s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->n, s->g, s->c, s->stream, &s->launches));
+    s->stage = ST_XSPH;
+    return stage_event(s, 5);
+}
+
+int pbf_stage_end(pbf_sim* s) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    s->stage = ST_IDLE;
+    return PBF_OK;
+}
+
+int pbf_step(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
+    int rc = pbf_stage_begin(s, pos, npos, vel, nvel, iid, n, stream);
+    if (rc) return rc;
+    if ((rc = pbf_stage_advect(s))) return rc;
+    if ((rc = pbf_stage_build_grid(s))) return rc;
+    for (int i = 0; i < s->p.niter; i++)
+        if ((rc = pbf_stage_correct_density(s))) return rc;
+    if ((rc = pbf_stage_update_velocity(s))) return rc;
+    if ((rc = pbf_stage_correct_velocity(s))) return rc;
+    return pbf_stage_end(s);
+}
+
+int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    if (n < 0 || n > s->max_particles) return fail(PBF_ERR_CAPACITY, "n exceeds max_particles");
+    if (!pos || !npos || !vel || !nvel || !iid) return fail(PBF_ERR_INVALID, "null particle buffer");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t m = (size_t)s->max_particles;
+    if (!s->h_pos) {
+        CUDA_TRY(cudaMalloc((void**)&s->h_pos, m * 12));
+        CUDA_TRY(cudaMalloc((void**)&s->h_npos, m * 12));
+        CUDA_TRY(cudaMalloc((void**)&s->h_vel, m * 12));
+        CUDA_TRY(cudaMalloc((void**)&s->h_nvel, m * 12));
+        CUDA_TRY(cudaMalloc((void**)&s->h_iid, m * 4));
+    }
+    cudaStream_t st = nullptr;
+    CUDA_TRY(cudaMemcpyAsync(s->h_pos, pos, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->h_vel, vel, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->h_iid, iid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    int rc = pbf_step(s, s->h_pos, s->h_npos, s->h_vel, s->h_nvel, s->h_iid, n, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(npos, s->h_npos, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nvel, s->h_nvel, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(iid, s->h_iid, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(pos, s->h_pos, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(vel, s->h_vel, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PBF_OK;
+}
+
+/* ---- read-backs --------------------------------------------------------------------------- */
+
+int pbf_read(pbf_sim* s, int what, void* dst, int64_t count) {
+    if (!s || !dst) return fail(PBF_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (count < 0) return fail(PBF_ERR_INVALID, "negative count");
+    const bool per_particle = what != PBF_READ_CELL_START && what != PBF_READ_CELL_END;
+    if (per_particle && count > s->n) return fail(PBF_ERR_INVALID, "count exceeds the bound particle count");
+    if (!per_particle && count > s->g.ncell) return fail(PBF_ERR_INVALID, "count exceeds the cell count");
+    if (count == 0) return PBF_OK;
+    const KeyIdx* sorted = s->pairs[s->sorted_buf];
+    if (!s->read_scratch) {
+        size_t bytes = (size_t)s->max_particles * 12;
+        if (bytes < (size_t)s->cell_capacity * 4) bytes = (size_t)s->cell_capacity * 4;
+        CUDA_TRY(cudaMalloc((void**)&s->read_scratch, bytes));
+    }
+    // extract one field (stride/offset/width in 32-bit words) into tight host memory
+    auto extract = [&](const void* src, int stride, int offset, int width) -> int {
+        const int64_t total = count * width;
+        extract_words_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>((const uint32_t*)src, stride, offset, width, s->read_scratch, count);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(dst, s->read_scratch, (size_t)total * 4, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return PBF_OK;
+    };
+    switch (what) {
+        case PBF_READ_KEY: return extract(sorted, 2, 0, 1);
+        case PBF_READ_SRC_INDEX: return extract(sorted, 2, 1, 1);
+        case PBF_READ_IID: return extract(s->iid_sorted, 1, 0, 1);
+        case PBF_READ_CELL_START: return extract(s->cell_range, 2, 0, 1);
+        case PBF_READ_CELL_END: return extract(s->cell_range, 2, 1, 1);
+        case PBF_READ_NPOS: return extract(s->x[s->cur], 4, 0, 3);
+        case PBF_READ_LAMBDA:
+            if (s->stage != ST_DENSITY) return fail(PBF_ERR_STATE, "lambda is only valid between correct_density and update_velocity");
+            return extract(s->xl, 4, 3, 1);
+        case PBF_READ_RHO: return extract(s->rho, 1, 0, 1);
+        case PBF_READ_POS0: return extract(s->pos0_in_npos ? s->npos : s->pos, 3, 0, 3);
+        case PBF_READ_VEL:
+            if (s->stage != ST_VELOCITY && s->stage != ST_XSPH) return fail(PBF_ERR_STATE, "velocity not computed yet");
+            return extract(s->xl, 4, 0, 3);
+        case PBF_READ_NEIGHBOR_COUNT: {
+            if (!s->count_scratch) CUDA_TRY(cudaMalloc((void**)&s->count_scratch, (size_t)s->max_particles * 4));
+            CUDA_TRY(launch_neighbor_count(s->x[s->cur], s->cell_range, s->count_scratch, s->n, s->g, s->c, s->stream));
+            return extract(s->count_scratch, 1, 0, 1);
+        }
+        default:
+            return fail(PBF_ERR_INVALID, "unknown read selector %d", what);
+    }
+}
+
+int pbf_get_stats(pbf_sim* s, const float* npos, const float* nvel, int64_t n, pbf_stats* out) {
+    if (!s || !npos || !nvel || !out) return fail(PBF_ERR_INVALID, "null argument");
+    if (n <= 0 || n > s->max_particles) return fail(PBF_ERR_INVALID, "bad n");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int nb = (int)((n + 255) / 256);
+    if (nb > 1024) nb = 1024;
+    CUDA_TRY(launch_stats(s->rho, npos, nvel, n, s->p.pho0, s->stats_partial, nb, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->stats_host, s->stats_partial, (size_t)nb * 5 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    double e_sum = 0, e_max = -1e300, ke = 0, v_max = 0, z_sum = 0;
+    for (int b = 0; b < nb; b++) {
+        const double* q = s->stats_host + b * 5;
+        e_sum += q[0];
+        if (q[1] > e_max) e_max = q[1];
+        ke += q[2];
+        if (q[3] > v_max) v_max = q[3];
+        z_sum += q[4];
+    }
+    out->density_err_mean = e_sum / (double)n;
+    out->density_err_max = e_max;
+    out->kinetic_energy = ke;
+    out->max_speed = sqrt(v_max);
+    out->mean_z = z_sum / (double)n;
+    return PBF_OK;
+}
+
+int pbf_enable_stage_timing(pbf_sim* s, int enable) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (enable && !s->ev_valid) {
+        for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+        s->ev_valid = true;
+    }
+    s->timing = enable != 0;
+    return PBF_OK;
+}
+
+int pbf_get_stage_ms(pbf_sim* s, float ms[5]) {
+    if (!s || !ms) return fail(PBF_ERR_INVALID, "null argument");
+    if (!s->timing || !s->ev_valid) return fail(PBF_ERR_STATE, "stage timing is not enabled");
+    CUDA_TRY(cudaEventSynchronize(s->ev[5]));
+    for (int k = 0; k < 5; k++) CUDA_TRY(cudaEventElapsedTime(&ms[k], s->ev[k], s->ev[k + 1]));
+    return PBF_OK;
+}
+
+/* ---- device memory helpers ---------------------------------------------------------------- */
+
+int pbf_device_alloc(int device, int64_t bytes, void** out) {
+    if (!out || bytes < 0) return fail(PBF_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(out, (size_t)(bytes ? bytes : 1)));
+    return PBF_OK;
+}
+int pbf_device_free(int device, void* ptr) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(ptr));
+    return PBF_OK;
+}
+int pbf_copy_h2d(void* dst, const void* src, int64_t bytes) {
+    CUDA_TRY(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return PBF_OK;
+}
+int pbf_copy_d2h(void* dst, const void* src, int64_t bytes) {
+    CUDA_TRY(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return PBF_OK;
+}
+int pbf_device_sync(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return PBF_OK;
+}
+
+int pbf_scene_block_device(const float origin[3], const int32_t n[3], float spacing, uint32_t seed,
+                           uint32_t first_iid, float* d_pos, float* d_vel, uint32_t* d_iid, void* stream) {
+    if (!origin || !n || !d_pos || !d_vel || !d_iid) return fail(PBF_ERR_INVALID, "null argument");
+    CUDA_TRY(launch_scene_block(origin, n, spacing, seed, first_iid, d_pos, d_vel, d_iid, (cudaStream_t)stream));
+    return PBF_OK;
+}
+
+}  // extern "C"

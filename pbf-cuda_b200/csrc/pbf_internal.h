@@ -1,0 +1,105 @@
+// pbf_internal.h — types shared by the kernels and the C-ABI layer (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pbf.h"
+
+namespace pbf {
+
+// Everything a kernel needs to know about the box and the grid for one step.
+// Recomputed on the host whenever the box or h changes (reference: Simulator.cu:187-188
+// recomputes m_gridHashDim every step from the current m_ulim/m_llim).
+struct GridConsts {
+    float llim[3];
+    float ulim[3];
+    float h;
+    int32_t dim[3];
+    int32_t ncell;
+    int32_t dyz;  // dim[1]*dim[2]
+};
+
+// Per-launch constants of the solver kernels. Host-side values are computed exactly the way
+// the reference's functor constructors compute them (Simulator.cu:77-83, 94-98, 129, 235).
+struct SolverConsts {
+    float h;
+    float h2;          // h*h in float                      (getPoly6::h2)
+    float h2_cull;     // slightly above h2: pairs below go to the exact range tests
+    float poly6_coef;  // 315/(64 pi h^9)                   (getPoly6::coef)
+    float spiky_coef;  // -45/(pi h^6)                      (getSpikyGrad::coef)
+    float pho0;
+    float lambda_eps;
+    float k_boundary;
+    float coef_corr;   // -k_corr / powf(poly6(dq^2), n_corr)   (Simulator.cu:235)
+    float n_corr;
+    float c_xsph;
+    float dt;
+    float inv_dt;      // 1.f/dt                            (h_updateVelocity)
+    float gravity;     // g, applied as (0,0,-g)
+    double lim_hi[3];  // (double)ulim - LIM_EPS            (Simulator_kernel.cuh:190-192)
+    double lim_lo[3];  // (double)llim + LIM_EPS
+    int32_t exact_pow; // 1: powf(w, n_corr) like the reference; 0: (w*w)^2 when n_corr == 4
+};
+
+// (key, source index) pair the radix sort moves; one 8-byte transaction per element.
+struct __align__(8) KeyIdx {
+    uint32_t key;
+    uint32_t idx;
+};
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 4;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+// ---- launchers (each returns the CUDA error of its launches) ---------------------------
+
+// advect + cell key + per-pass digit histograms, in input order (advect_key.cu)
+cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist,
+                              int64_t n, int npass, const GridConsts& g, const SolverConsts& c,
+                              cudaStream_t st, int64_t* launches);
+
+// onesweep LSD radix sort of (key, idx) (radix_sort.cu). `keys` is consumed by pass 0 with the
+// implicit index; result ends in bufs[result_buf].
+struct SortScratch {
+    uint32_t* hist;          // [MAX_PASSES][RADIX] digit counts -> exclusive prefix in place
+    uint32_t* tile_counter;  // [MAX_PASSES]
+    uint32_t* tile_desc;     // [npass][ntiles][RADIX] decoupled look-back state
+    KeyIdx* bufs[2];
+    int64_t tile_desc_words; // capacity per pass
+};
+cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, int* result_buf,
+                        cudaStream_t st, int64_t* launches);
+size_t sort_scratch_zero_bytes(int64_t n, int npass);
+
+// gather the payload into sorted SoA + cell ranges (reorder.cu)
+cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
+                           float4* x0, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
+                           int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                           int64_t* launches);
+
+// solver passes (solver.cu)
+cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t n,
+                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t n,
+                           const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
+                                   float* vel_out, float4* v4, int64_t n, const SolverConsts& c,
+                                   cudaStream_t st, int64_t* launches);
+cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,
+                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t n, const GridConsts& g,
+                        const SolverConsts& c, cudaStream_t st, int64_t* launches);
+cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
+                                  const GridConsts& g, const SolverConsts& c, cudaStream_t st);
+
+// scene + stats (scene.cu, stats.cu)
+cudaError_t launch_scene_block(const float origin[3], const int32_t n3[3], float spacing, uint32_t seed,
+                               uint32_t first_iid, float* pos, float* vel, uint32_t* iid, cudaStream_t st);
+void scene_block_host(const float origin[3], const int32_t n3[3], float spacing, uint32_t seed,
+                      uint32_t first_iid, float* pos, float* vel, uint32_t* iid);
+cudaError_t launch_stats(const float* rho, const float* npos, const float* nvel, int64_t n, float pho0,
+                         double* partial, int nblocks, cudaStream_t st);
+
+}  // namespace pbf

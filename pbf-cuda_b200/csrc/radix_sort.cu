@@ -1,0 +1,223 @@
+// radix_sort.cu — hand-written onesweep LSD radix sort of (cell key, source index) pairs.
+//
+// Replaces the reference's thrust::sort_by_key over a 5-way zip of float3 payloads
+// (Simulator.cu:196-198), which moves 56 B per particle per pass plus a pack and an unpack
+// (~0.66 KB/particle). Here only 8 B pairs move; the payload is gathered once
+// afterwards (reorder.cu).
+//
+// Algorithm (Adinets & Merrill "Onesweep", restated from the paper, not from CUB's sources):
+//   - digit histograms of ALL passes are produced up front by advect_key.cu;
+//   - one kernel per 8-bit digit: each CTA takes a tile through an atomic ticket (so that every
+//     tile it may wait on is already resident), ranks its keys with warp-level match_any
+//     (stable: items are visited in memory order), publishes its per-digit counts, resolves its
+//     per-digit exclusive prefix by decoupled look-back over the preceding tiles, reorders the
+//     tile through shared memory and writes coalesced runs.
+//   - stable, deterministic, no temporary allocation.
+//
+// HBM traffic per pass: R 8 B + W 8 B per particle (pass 0 reads the 4 B key only).
+#include "pbf_internal.h"
+
+namespace pbf {
+
+namespace {
+
+constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr uint32_t FLAG_AGGREGATE = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+static_assert(SORT_THREADS == RADIX, "one thread per digit in the look-back phase");
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// counts -> exclusive prefix, one CTA of RADIX threads per pass.
+__global__ void __launch_bounds__(RADIX) hist_scan_kernel(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_wsum[RADIX / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* h = hist + blockIdx.x * RADIX;
+    const uint32_t cnt = h[tid];
+    uint32_t v = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v += t;
+    }
+    if (lane == 31) s_wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < RADIX / 32 ? s_wsum[lane] : 0, iw = w;
+#pragma unroll
+        for (int off = 1; off < RADIX / 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, iw, off);
+            if (lane >= off) iw += t;
+        }
+        if (lane < RADIX / 32) s_wsum[lane] = iw - w;
+    }
+    __syncthreads();
+    h[tid] = v - cnt + s_wsum[warp];
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__ pairs_in,
+                KeyIdx* __restrict__ out, const uint32_t* __restrict__ hist_excl,
+                uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ tile_desc, int64_t n,
+                int shift) {
+    __shared__ KeyIdx s_pairs[SORT_TILE];
+    __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];
+    __shared__ uint32_t s_digit_start[RADIX];
+    __shared__ uint32_t s_global_base[RADIX];
+    __shared__ uint32_t s_wsum[SORT_WARPS];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) s_warp_hist[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t tile_base = (int64_t)tile * SORT_TILE;
+    const int tile_n = (int)min((int64_t)SORT_TILE, n - tile_base);
+
+    // ---- load, warp-striped so that (item k, lane l) is memory order within the warp's chunk
+    KeyIdx item[SORT_ITEMS];
+    const int warp_base = warp * 32 * SORT_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        const int local = warp_base + k * 32 + lane;
+        if (local < tile_n) {
+            if (FIRST) {
+                item[k].key = keys_in[tile_base + local];
+                item[k].idx = (uint32_t)(tile_base + local);
+            } else {
+                item[k] = pairs_in[tile_base + local];
+            }
+        } else {
+            item[k].key = 0xffffffffu;
+            item[k].idx = 0xffffffffu;
+        }
+    }
+
+    // ---- rank within the warp (stable)
+    uint32_t rank[SORT_ITEMS];
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        const bool valid = (warp_base + k * 32 + lane) < tile_n;
+        const uint32_t d = valid ? ((item[k].key >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        uint32_t old = 0;
+        if (valid) old = s_warp_hist[warp][d];
+        __syncwarp();
+        if (valid && lane == (__ffs(peers) - 1)) s_warp_hist[warp][d] = old + __popc(peers);
+        __syncwarp();
+        rank[k] = old + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+
+    // ---- per digit (thread == digit): exclusive scan over the warps, tile count
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+        uint32_t t = s_warp_hist[w][tid];
+        s_warp_hist[w][tid] = count;
+        count += t;
+    }
+
+    // ---- publish, then decoupled look-back for the exclusive prefix over preceding tiles
+    uint32_t* my_desc = tile_desc + (size_t)tile * RADIX;
+    uint32_t excl = 0;
+    if (tile == 0) {
+        st_volatile(my_desc + tid, count | FLAG_PREFIX);
+    } else {
+        st_volatile(my_desc + tid, count | FLAG_AGGREGATE);
+        int64_t t = (int64_t)tile - 1;
+        while (true) {
+            uint32_t v = ld_volatile(tile_desc + (size_t)t * RADIX + tid);
+            if ((v & FLAG_MASK) == 0) {
+                __nanosleep(32);
+                continue;
+            }
+            excl += v & VALUE_MASK;
+            if (v & FLAG_PREFIX) break;
+            t--;
+        }
+        st_volatile(my_desc + tid, (excl + count) | FLAG_PREFIX);
+    }
+
+    // ---- exclusive scan of the tile counts over the digits -> position in the tile-sorted order
+    uint32_t v = count;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v += t;
+    }
+    if (lane == 31) s_wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SORT_WARPS ? s_wsum[lane] : 0, iw = w;
+#pragma unroll
+        for (int off = 1; off < SORT_WARPS; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, iw, off);
+            if (lane >= off) iw += t;
+        }
+        if (lane < SORT_WARPS) s_wsum[lane] = iw - w;
+    }
+    __syncthreads();
+    const uint32_t dstart = v - count + s_wsum[warp];
+    s_digit_start[tid] = dstart;
+    s_global_base[tid] = hist_excl[tid] + excl - dstart;  // + position in tile order = global slot
+    __syncthreads();
+
+    // ---- reorder the tile through shared memory
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        if ((warp_base + k * 32 + lane) < tile_n) {
+            const uint32_t d = (item[k].key >> shift) & (RADIX - 1);
+            s_pairs[s_digit_start[d] + s_warp_hist[warp][d] + rank[k]] = item[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- coalesced runs out
+    for (int p = tid; p < tile_n; p += SORT_THREADS) {
+        const KeyIdx e = s_pairs[p];
+        const uint32_t d = (e.key >> shift) & (RADIX - 1);
+        out[s_global_base[d] + (uint32_t)p] = e;
+    }
+}
+
+}  // namespace
+
+size_t sort_scratch_zero_bytes(int64_t n, int npass) {
+    int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    return sizeof(uint32_t) * ((size_t)MAX_PASSES * RADIX + MAX_PASSES + (size_t)npass * tiles * RADIX);
+}
+
+cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, int* result_buf,
+                        cudaStream_t st, int64_t* launches) {
+    if (n <= 0) { *result_buf = 0; return cudaSuccess; }
+    const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    hist_scan_kernel<<<npass, RADIX, 0, st>>>(s.hist);
+    if (launches) (*launches)++;
+    for (int p = 0; p < npass; p++) {
+        uint32_t* desc = s.tile_desc + (size_t)p * tiles * RADIX;
+        const uint32_t* h = s.hist + p * RADIX;
+        if (p == 0)
+            onesweep_kernel<true><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS);
+        else
+            onesweep_kernel<false><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS);
+        if (launches) (*launches)++;
+    }
+    *result_buf = (npass - 1) & 1;
+    return cudaGetLastError();
+}
+
+}  // namespace pbf

@@ -1,0 +1,59 @@
+// reorder.cu — gather the particle state into cell-sorted SoA and build the cell table.
+//
+// Replaces (a) the payload movement inside the reference's sort_by_key (Simulator.cu:196-198),
+// (b) the two cudaMemset + computeGridRange (Simulator.cu:200-204, Simulator_kernel.cuh:21-50).
+// For sorted slot s with source index j:
+//   x0[s]      = (advect(pos[j], vel[j]), 0)      float4, the iterate the solver works on
+//   pos0[s]    = pos[j]                           tight float3, parked in the caller's npos buffer
+//   iid_s[s]   = iid[j]
+//   cell_range[key] = {first slot, one past last slot}; empty cells stay {0,0} (reference
+//   semantics: gridStart == gridEnd == 0).
+// The advected position is recomputed with the same two fma as in advect_key.cu, so the key the
+// particle was sorted by is exactly the cell of x0[s].
+//
+// HBM traffic: R 8 (pair) + 28 (gathered pos, vel, iid; near-sequential because the input is
+// last step's sorted order) ; W 16 + 12 + 4 per particle, + 8 B per occupied cell.
+#include "pbf_math.cuh"
+
+namespace pbf {
+
+constexpr int RO_THREADS = 256;
+
+__global__ void __launch_bounds__(RO_THREADS)
+reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
+               const float* __restrict__ vel, const uint32_t* __restrict__ iid,
+               float4* __restrict__ x0, float* __restrict__ pos0_out, uint32_t* __restrict__ iid_sorted,
+               uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
+               const __grid_constant__ SolverConsts c) {
+    const int64_t s = (int64_t)blockIdx.x * RO_THREADS + threadIdx.x;
+    if (s >= n) return;
+    const KeyIdx e = sorted[s];
+    const uint32_t prev = s == 0 ? 0xffffffffu : sorted[s - 1].key;
+    const float3 p = load_f3(pos, e.idx), v = load_f3(vel, e.idx);
+    const float3 q = advect_pos(p, v, c);
+    x0[s] = make_float4(q.x, q.y, q.z, 0.f);
+    store_f3(pos0_out, s, p.x, p.y, p.z);
+    iid_sorted[s] = iid[e.idx];
+    // Green-style range detection (reference computeGridRange)
+    if (e.key != prev) {
+        cell_range[e.key].x = (uint32_t)s;
+        if (prev != 0xffffffffu) cell_range[prev].y = (uint32_t)s;
+    }
+    if (s == n - 1) cell_range[e.key].y = (uint32_t)n;
+}
+
+cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
+                           float4* x0, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
+                           int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                           int64_t* launches) {
+    cudaError_t e = cudaMemsetAsync(cell_range, 0, sizeof(uint2) * (size_t)g.ncell, st);
+    if (e != cudaSuccess) return e;
+    if (launches) (*launches)++;
+    if (n <= 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n + RO_THREADS - 1) / RO_THREADS);
+    reorder_kernel<<<blocks, RO_THREADS, 0, st>>>(sorted, pos, vel, iid, x0, pos0_out, iid_sorted, cell_range, n, g, c);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace pbf

@@ -1,0 +1,236 @@
+// solver.cu — the constraint-solver passes of the step on the cell-sorted float4 SoA.
+//
+//   lambda pass   <- computeLambda  (reference Simulator_kernel.cuh:52-129)
+//   delta-p pass  <- computetpos    (reference Simulator_kernel.cuh:131-194) + the Jacobi commit
+//                    thrust::copy_n (Simulator.cu:247-248), which becomes a ping-pong
+//   velocity      <- h_updateVelocity (Simulator.cu:127-137, 267-274)
+//   XSPH          <- computeXSPH    (reference Simulator_kernel.cuh:196-239)
+//
+// Parity design: a particle's sums are accumulated by ONE thread in the reference's visiting
+// order (dx, dy, dz nested, ascending slot inside a cell) with the reference's exact fp32
+// operation sequence (pbf_math.cuh), so rho / lambda / positions reproduce the reference's CUDA
+// build bit for bit (with exact_pow) instead of merely within tolerance. What changes is the
+// data path: one 16-byte load per candidate from the sorted float4 array instead of three
+// scalar loads from AoS float3 (+1 for lambda), the three z-cells of a column visited as one
+// contiguous slot run (9 runs instead of 27 cells), and the expensive part (sqrt, 4 IEEE
+// divisions, pow) only for pairs that pass an r2 cull — candidates outside h contribute exact
+// zeros in the reference, so skipping them does not change a single bit.
+#include "pbf_math.cuh"
+
+namespace pbf {
+
+constexpr int GATHER_THREADS = 128;
+
+// Visit the candidates of home cell `cc` in the reference's order. The three dz cells of a
+// column are consecutive keys, hence one contiguous slot run [start, end).
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const int3 cc, const uint2* __restrict__ cell_range,
+                                                   const GridConsts& g, F&& body) {
+    const int zlo = max(cc.z - 1, 0), zhi = min(cc.z + 1, g.dim[2] - 1);
+    for (int dx = -1; dx <= 1; dx++) {
+        const int x = cc.x + dx;
+        if (x < 0 || x >= g.dim[0]) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int y = cc.y + dy;
+            if (y < 0 || y >= g.dim[1]) continue;
+            const int base = x * g.dyz + y * g.dim[2];
+            uint32_t start = 0, end = 0;
+            bool any = false;
+            for (int z = zlo; z <= zhi; z++) {
+                const uint2 r = __ldg(&cell_range[base + z]);
+                if (r.y > r.x) {
+                    if (!any) { start = r.x; any = true; }
+                    end = r.y;
+                }
+            }
+            for (uint32_t j = start; j < end; j++) body(j);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GATHER_THREADS)
+lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __restrict__ rho_out,
+              const uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
+              const __grid_constant__ SolverConsts c) {
+    const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = x[i];
+    const int3 cc = cell_of(p.x, p.y, p.z, g);
+    float rho = 0.f, gradj_l2 = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
+    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
+        const float4 q = __ldg(&x[j]);
+        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+        const float r2 = sumsq(dx, dy, dz);
+        if (r2 < c.h2_cull) {
+            rho = __fadd_rn(rho, poly6(r2, c));
+            const float s = spiky_scale(r2, c);
+            const float gx = __fdiv_rn(__fmul_rn(dx, s), c.pho0);
+            const float gy = __fdiv_rn(__fmul_rn(dy, s), c.pho0);
+            const float gz = __fdiv_rn(__fmul_rn(dz, s), c.pho0);
+            gix = __fadd_rn(gix, gx);
+            giy = __fadd_rn(giy, gy);
+            giz = __fadd_rn(giz, gz);
+            if ((int64_t)j != i) gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
+        }
+    });
+    if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
+    const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
+    const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
+    xl[i] = make_float4(p.x, p.y, p.z, lambda);
+    rho_out[i] = rho;
+}
+
+template <bool EXACT_POW>
+__global__ void __launch_bounds__(GATHER_THREADS)
+delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
+               const uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
+               const __grid_constant__ SolverConsts c) {
+    const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = xl[i];
+    const int3 cc = cell_of(p.x, p.y, p.z, g);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
+        if ((int64_t)j == i) return;
+        const float4 q = __ldg(&xl[j]);
+        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+        const float r2 = sumsq(dx, dy, dz);
+        if (r2 < c.h2_cull) {
+            const float w = poly6(r2, c);
+            float pw;
+            if (EXACT_POW) {
+                pw = powf(w, c.n_corr);
+            } else {  // n_corr == 4
+                const float w2 = __fmul_rn(w, w);
+                pw = __fmul_rn(w2, w2);
+            }
+            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+            const float s = spiky_scale(r2, c);
+            ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
+            ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
+            az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
+        }
+    });
+    const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
+    const float vx = fmaxf(fminf(__fdiv_rn(ax, c.pho0), max_dp), -max_dp);
+    const float vy = fmaxf(fminf(__fdiv_rn(ay, c.pho0), max_dp), -max_dp);
+    const float vz = fmaxf(fminf(__fdiv_rn(az, c.pho0), max_dp), -max_dp);
+    // box clamp in double like the reference (LIM_EPS is a double literal)
+    const float qx = (float)fmax(fmin((double)__fadd_rn(p.x, vx), c.lim_hi[0]), c.lim_lo[0]);
+    const float qy = (float)fmax(fmin((double)__fadd_rn(p.y, vy), c.lim_hi[1]), c.lim_lo[1]);
+    const float qz = (float)fmax(fmin((double)__fadd_rn(p.z, vz), c.lim_hi[2]), c.lim_lo[2]);
+    x_out[i] = make_float4(qx, qy, qz, 0.f);
+}
+
+// vel = (npos - pos) * inv_dt, plus everything the caller-facing buffers need from this point:
+// pos <- step-input position (parked in npos by the reorder pass), npos <- final iterate.
+__global__ void __launch_bounds__(256)
+update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ rho,
+                       float* __restrict__ pos_out, float* __restrict__ npos_io,
+                       float* __restrict__ vel_out, float4* __restrict__ v4, int64_t n,
+                       const __grid_constant__ SolverConsts c) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 q = x[i];
+    const float3 p0 = load_f3(npos_io, i);
+    const float vx = __fmul_rn(__fsub_rn(q.x, p0.x), c.inv_dt);
+    const float vy = __fmul_rn(__fsub_rn(q.y, p0.y), c.inv_dt);
+    const float vz = __fmul_rn(__fsub_rn(q.z, p0.z), c.inv_dt);
+    v4[i] = make_float4(vx, vy, vz, rho[i]);
+    store_f3(vel_out, i, vx, vy, vz);
+    store_f3(pos_out, i, p0.x, p0.y, p0.z);
+    store_f3(npos_io, i, q.x, q.y, q.z);
+}
+
+__global__ void __launch_bounds__(GATHER_THREADS)
+xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
+            const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
+            const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t n,
+            const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = x[i];
+    const float4 vi = v4[i];
+    const int3 cc = cell_of(p.x, p.y, p.z, g);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
+        const float4 q = __ldg(&x[j]);
+        const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
+        if (r2 < c.h2) {
+            const float4 vj = __ldg(&v4[j]);
+            const float w = poly6_in(r2, c);
+            const float den = __fadd_rn(vi.w, vj.w);
+            const float tx = __fsub_rn(vj.x, vi.x), ty = __fsub_rn(vj.y, vi.y), tz = __fsub_rn(vj.z, vi.z);
+            ax = __fadd_rn(ax, __fdiv_rn(__fmul_rn(__fadd_rn(tx, tx), w), den));
+            ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
+            az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
+        }
+    });
+    store_f3(nvel_out, i, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
+    iid_out[i] = iid_sorted[i];
+}
+
+__global__ void __launch_bounds__(GATHER_THREADS)
+neighbor_count_kernel(const float4* __restrict__ x, const uint2* __restrict__ cell_range,
+                      uint32_t* __restrict__ count, int64_t n, const __grid_constant__ GridConsts g,
+                      const __grid_constant__ SolverConsts c) {
+    const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = x[i];
+    const int3 cc = cell_of(p.x, p.y, p.z, g);
+    uint32_t cnt = 0;
+    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
+        const float4 q = __ldg(&x[j]);
+        const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
+        if (r2 < c.h2) cnt++;
+    });
+    count[i] = cnt;
+}
+
+static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t n,
+                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    lambda_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(x, xl, rho, cell_range, n, g, c);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t n,
+                           const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    if (c.exact_pow || c.n_corr != 4.0f)
+        delta_p_kernel<true><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(xl, x_out, cell_range, n, g, c);
+    else
+        delta_p_kernel<false><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(xl, x_out, cell_range, n, g, c);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
+                                   float* vel_out, float4* v4, int64_t n, const SolverConsts& c,
+                                   cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    update_velocity_kernel<<<nblocks(n, 256), 256, 0, st>>>(x, rho, pos_out, npos_io, vel_out, v4, n, c);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,
+                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t n, const GridConsts& g,
+                        const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(x, v4, cell_range, nvel_out, iid_sorted, iid_out, n, g, c);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
+                                  const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    neighbor_count_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(x, cell_range, count, n, g, c);
+    return cudaGetLastError();
+}
+
+}  // namespace pbf
