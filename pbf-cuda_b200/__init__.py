@@ -16,13 +16,15 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbf_b200.so")
+# PBF_LIB selects a tuning-experiment build (pbf-cuda_b200/Makefile VARIANT=...); default is the product
+LIB_PATH = os.environ.get("PBF_LIB") or os.path.join(_HERE, "libpbf_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, 1, 2, 3, 4
 
 READ_KEY, READ_SRC_INDEX, READ_IID, READ_CELL_START, READ_CELL_END, READ_NPOS, READ_LAMBDA, READ_RHO, \
     READ_POS0, READ_VEL, READ_NEIGHBOR_COUNT = range(11)
 
+KERNEL_NAMES = ("advect_key", "sort", "reorder", "lambda", "delta_p", "update_velocity", "xsph")
 STAGE_NAMES = ("ADVECT", "GRID", "DENSITY", "VELOCITY_UPDATE", "VELOCITY_CORRECT")  # reference Logger.h:7-23
 
 # every symbol include/pbf.h declares (tests check the library exports all of them)
@@ -31,7 +33,7 @@ EXPORTS = (
     "pbf_get_lim", "pbf_set_option_exact_pow", "pbf_get_grid_dim", "pbf_step", "pbf_step_host",
     "pbf_stage_begin", "pbf_stage_advect", "pbf_stage_build_grid", "pbf_stage_correct_density",
     "pbf_stage_update_velocity", "pbf_stage_correct_velocity", "pbf_stage_end", "pbf_read", "pbf_get_stats",
-    "pbf_enable_stage_timing", "pbf_get_stage_ms", "pbf_launch_count", "pbf_device_alloc", "pbf_device_free",
+    "pbf_enable_stage_timing", "pbf_get_stage_ms", "pbf_get_kernel_ms", "pbf_launch_count", "pbf_device_alloc", "pbf_device_free",
     "pbf_copy_h2d", "pbf_copy_d2h", "pbf_device_sync", "pbf_scene_cube", "pbf_scene_double_dam_reference",
     "pbf_scene_block_device", "pbf_scene_block_host", "pbf_last_error", "pbf_version",
 )
@@ -88,6 +90,7 @@ _lib.pbf_read.argtypes = [_vp, C.c_int, _vp, _i64]
 _lib.pbf_get_stats.argtypes = [_vp, _vp, _vp, _i64, C.POINTER(Stats)]
 _lib.pbf_enable_stage_timing.argtypes = [_vp, C.c_int]
 _lib.pbf_get_stage_ms.argtypes = [_vp, _f3]
+_lib.pbf_get_kernel_ms.argtypes = [_vp, _f3]
 _lib.pbf_launch_count.argtypes = [_vp]
 _lib.pbf_launch_count.restype = _i64
 _lib.pbf_device_alloc.argtypes = [C.c_int, _i64, C.POINTER(_vp)]
@@ -292,6 +295,11 @@ class Simulator:
         ms = (C.c_float * 5)()
         _check(_lib.pbf_get_stage_ms(self._h, ms))
         return dict(zip(STAGE_NAMES, list(ms)))
+
+    def kernel_ms(self):
+        ms = (C.c_float * len(KERNEL_NAMES))()
+        _check(_lib.pbf_get_kernel_ms(self._h, ms))
+        return dict(zip(KERNEL_NAMES, list(ms)))
 
     def launch_count(self):
         return int(_lib.pbf_launch_count(self._h))

@@ -58,7 +58,7 @@ struct pbf_sim {
     float ulim[3]{}, llim[3]{};
     int64_t max_particles = 0;
     int64_t cell_capacity = 0;
-    int exact_pow = 0;
+    int exact_pow = 1;
 
     // scratch (device)
     uint32_t* keys = nullptr;
@@ -95,6 +95,7 @@ struct pbf_sim {
     int64_t launches = 0;
     bool timing = false;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t kev[2 * PBF_KERNEL_SLOTS] = {};  // [2k] before / [2k+1] after kernel slot k
     bool ev_valid = false;
 };
 
@@ -176,7 +177,10 @@ void free_all(pbf_sim* s) {
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
     if (s->stats_host) cudaFreeHost(s->stats_host);
-    if (s->ev_valid) for (auto& e : s->ev) cudaEventDestroy(e);
+    if (s->ev_valid) {
+        for (auto& e : s->ev) cudaEventDestroy(e);
+        for (auto& e : s->kev) cudaEventDestroy(e);
+    }
 }
 
 }  // namespace
@@ -234,8 +238,9 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (cap < 1) cap = 1;
     if (cap >= ((int64_t)1 << 30)) cap = ((int64_t)1 << 30) - 1;
     s->cell_capacity = cap;
-    const char* ep = getenv("PBF_EXACT_POW");
-    s->exact_pow = (ep && ep[0] == '1') ? 1 : 0;
+    // default: powf like the reference (bit-identical results); PBF_FAST_POW=1 opts into (w*w)^2
+    const char* ep = getenv("PBF_FAST_POW");
+    s->exact_pow = (ep && ep[0] == '1') ? 0 : 1;
 
     const size_t n = (size_t)max_particles;
     s->sort_zero_capacity = sort_scratch_zero_bytes(max_particles, MAX_PASSES);
@@ -319,6 +324,18 @@ static int stage_event(pbf_sim* s, int k) {
     if (s->timing) CUDA_TRY(cudaEventRecord(s->ev[k], s->stream));
     return PBF_OK;
 }
+// brackets one kernel slot (PBF_KERNEL_*) with events when timing is on
+static int kernel_event(pbf_sim* s, int slot, int after) {
+    if (s->timing) CUDA_TRY(cudaEventRecord(s->kev[2 * slot + after], s->stream));
+    return PBF_OK;
+}
+#define KTIMED(slot, call)                                   \
+    do {                                                     \
+        int rc__ = kernel_event(s, slot, 0);                 \
+        if (rc__) return rc__;                               \
+        CUDA_TRY(call);                                      \
+        if ((rc__ = kernel_event(s, slot, 1))) return rc__;  \
+    } while (0)
 
 int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n,
                     void* stream) {
@@ -342,7 +359,7 @@ int pbf_stage_advect(pbf_sim* s) {
     const size_t zero_bytes = sort_scratch_zero_bytes(s->n, s->npass);
     CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, zero_bytes, s->stream));
     s->launches++;
-    CUDA_TRY(launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_ADVECT_KEY, launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_ADVECTED;
     return stage_event(s, 1);
 }
@@ -356,9 +373,9 @@ int pbf_stage_build_grid(pbf_sim* s) {
     sc.bufs[0] = s->pairs[0];
     sc.bufs[1] = s->pairs[1];
     sc.tile_desc_words = 0;
-    CUDA_TRY(launch_sort(s->keys, sc, s->n, s->npass, &s->sorted_buf, s->stream, &s->launches));
-    CUDA_TRY(launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->npos, s->iid_sorted,
-                            s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_SORT, launch_sort(s->keys, sc, s->n, s->npass, &s->sorted_buf, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_REORDER, launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->npos, s->iid_sorted,
+                                              s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
     s->cur = 0;
     s->pos0_in_npos = true;
     s->stage = ST_GRID;
@@ -367,8 +384,9 @@ int pbf_stage_build_grid(pbf_sim* s) {
 
 int pbf_stage_correct_density(pbf_sim* s) {
     if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "correct_density: build_grid first");
-    CUDA_TRY(launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
-    CUDA_TRY(launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+    // (each iteration overwrites the slot: the timers report the LAST iteration of the step)
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;
@@ -380,7 +398,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
     int rc = stage_event(s, 3);
     if (rc) return rc;
     // xl is dead after the last delta-p pass: reuse it for (velocity, rho)
-    CUDA_TRY(launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->n, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->n, s->c, s->stream, &s->launches));
     s->pos0_in_npos = false;
     s->stage = ST_VELOCITY;
     return stage_event(s, 4);
@@ -388,7 +406,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
 
 int pbf_stage_correct_velocity(pbf_sim* s) {
     if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
-    CUDA_TRY(launch_xsph(s->x[s->cur], s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->n, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->n, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
 }
@@ -433,8 +451,6 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     CUDA_TRY(cudaMemcpyAsync(npos, s->h_npos, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(nvel, s->h_nvel, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(iid, s->h_iid, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(pos, s->h_pos, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(vel, s->h_vel, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PBF_OK;
 }
@@ -521,6 +537,7 @@ int pbf_enable_stage_timing(pbf_sim* s, int enable) {
     CUDA_TRY(cudaSetDevice(s->device));
     if (enable && !s->ev_valid) {
         for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+        for (auto& e : s->kev) CUDA_TRY(cudaEventCreate(&e));
         s->ev_valid = true;
     }
     s->timing = enable != 0;
@@ -532,6 +549,14 @@ int pbf_get_stage_ms(pbf_sim* s, float ms[5]) {
     if (!s->timing || !s->ev_valid) return fail(PBF_ERR_STATE, "stage timing is not enabled");
     CUDA_TRY(cudaEventSynchronize(s->ev[5]));
     for (int k = 0; k < 5; k++) CUDA_TRY(cudaEventElapsedTime(&ms[k], s->ev[k], s->ev[k + 1]));
+    return PBF_OK;
+}
+
+int pbf_get_kernel_ms(pbf_sim* s, float ms[PBF_KERNEL_SLOTS]) {
+    if (!s || !ms) return fail(PBF_ERR_INVALID, "null argument");
+    if (!s->timing || !s->ev_valid) return fail(PBF_ERR_STATE, "stage timing is not enabled");
+    CUDA_TRY(cudaEventSynchronize(s->ev[5]));
+    for (int k = 0; k < PBF_KERNEL_SLOTS; k++) CUDA_TRY(cudaEventElapsedTime(&ms[k], s->kev[2 * k], s->kev[2 * k + 1]));
     return PBF_OK;
 }
 

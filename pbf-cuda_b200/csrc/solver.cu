@@ -19,59 +19,126 @@
 
 namespace pbf {
 
+#ifndef PBF_GATHER_MINBLOCKS
+#define PBF_GATHER_MINBLOCKS 8
+#endif
+#ifndef PBF_LIST_CAP
+#define PBF_LIST_CAP 32
+#endif
 constexpr int GATHER_THREADS = 128;
+constexpr int LIST_CAP = PBF_LIST_CAP;  // in-range neighbours buffered per thread and x-slab before a flush
+constexpr size_t LIST_SMEM = (size_t)LIST_CAP * GATHER_THREADS * sizeof(uint16_t);  // 8 KB per CTA
 
-// Visit the candidates of home cell `cc` in the reference's order. The three dz cells of a
-// column are consecutive keys, hence one contiguous slot run [start, end).
-template <typename F>
-__device__ __forceinline__ void for_each_candidate(const int3 cc, const uint2* __restrict__ cell_range,
-                                                   const GridConsts& g, F&& body) {
+// Two-phase gather of one particle (one thread), the core of all three neighbour sweeps.
+//
+// Phase 1 (cull) walks the candidates in the reference's visiting order — dx, dy, dz nested,
+// ascending slot inside a cell; the three dz cells of a column are consecutive keys, hence ONE
+// contiguous slot run per (dx, dy), and the three runs of one dx are ascending too — with one
+// 16-byte load and 7 flops per candidate, branch-free: the slot offset is always stored to the
+// tail of a per-thread list in shared memory (entry k of thread t at [k][t]: conflict-free) and
+// the tail only advances when `r2 < limit`. Phase 2 (`heavy`) then runs the expensive exact
+// arithmetic over the list only, every lane busy, still in visiting order. Without the list a
+// warp executes the heavy path for nearly every candidate, because some lane is almost always
+// in range (~15 % of the candidates are), at ~15 % lane utilisation.
+// The list is flushed after each dx slab (3 runs, ~11 neighbours) and whenever it is nearly
+// full, so any neighbour count stays correct and ordered; entries are 16-bit offsets from the
+// slab's first slot (re-based if a slab ever spans more than 65535 slots), which keeps the
+// shared-memory footprint at 8 KB per CTA and leaves the rest of the 256 KB for L1.
+template <bool SKIP_SELF, typename Heavy>
+__device__ __forceinline__ void gather(const float4 p, const uint32_t self, const float limit,
+                                       const float4* __restrict__ x, const uint2* __restrict__ cell_range,
+                                       const GridConsts& g, uint16_t* __restrict__ my_list, Heavy&& heavy) {
+    const int3 cc = cell_of(p.x, p.y, p.z, g);
     const int zlo = max(cc.z - 1, 0), zhi = min(cc.z + 1, g.dim[2] - 1);
+    uint16_t* const list_full = my_list + (LIST_CAP - 4) * GATHER_THREADS;
+#pragma unroll 1
     for (int dx = -1; dx <= 1; dx++) {
-        const int x = cc.x + dx;
-        if (x < 0 || x >= g.dim[0]) continue;
+        const int cx = cc.x + dx;
+        if (cx < 0 || cx >= g.dim[0]) continue;
+        uint32_t base = 0xffffffffu;
+        uint16_t* tail = my_list;  // next free entry of this thread's list
+        auto flush = [&]() {
+#pragma unroll 2
+            for (const uint16_t* e = my_list; e < tail; e += GATHER_THREADS) {
+                const uint32_t j = base + *e;
+                heavy(j, __ldg(&x[j]));
+            }
+            tail = my_list;
+        };
+        // branch-free append: always store the offset, advance the tail only on a hit
+        auto test = [&](const uint32_t j, const float4 q) {
+            const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
+            bool pass = r2 < limit;
+            if (SKIP_SELF) pass &= (j != self);
+            *tail = (uint16_t)(j - base);
+            tail += pass ? GATHER_THREADS : 0;
+        };
+#pragma unroll 1
         for (int dy = -1; dy <= 1; dy++) {
-            const int y = cc.y + dy;
-            if (y < 0 || y >= g.dim[1]) continue;
-            const int base = x * g.dyz + y * g.dim[2];
+            const int cy = cc.y + dy;
+            if (cy < 0 || cy >= g.dim[1]) continue;
+            const int cbase = cx * g.dyz + cy * g.dim[2];
             uint32_t start = 0, end = 0;
             bool any = false;
             for (int z = zlo; z <= zhi; z++) {
-                const uint2 r = __ldg(&cell_range[base + z]);
+                const uint2 r = __ldg(&cell_range[cbase + z]);
                 if (r.y > r.x) {
                     if (!any) { start = r.x; any = true; }
                     end = r.y;
                 }
             }
-            for (uint32_t j = start; j < end; j++) body(j);
+            if (!any) continue;
+            if (base == 0xffffffffu) base = start;
+            uint32_t j = start;
+            while (j < end) {
+                if (end - base > 0xffffu) {  // offsets would not fit 16 bits: drain and re-base (rare)
+                    flush();
+                    base = j;
+                }
+                const uint32_t stop = min(end, base + 0xffffu);
+                for (; j + 4 <= stop; j += 4) {  // four independent loads in flight, tested in order
+                    const float4* xp = x + j;
+                    const float4 q0 = __ldg(xp), q1 = __ldg(xp + 1), q2 = __ldg(xp + 2), q3 = __ldg(xp + 3);
+                    test(j, q0); test(j + 1, q1); test(j + 2, q2); test(j + 3, q3);
+                    if (tail > list_full) flush();
+                }
+                for (; j < stop; j++) test(j, __ldg(&x[j]));
+                if (tail > list_full) flush();
+            }
         }
+        flush();
     }
 }
 
-__global__ void __launch_bounds__(GATHER_THREADS)
+__global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
               const __grid_constant__ SolverConsts c) {
+    extern __shared__ uint16_t s_list[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
     const float4 p = x[i];
-    const int3 cc = cell_of(p.x, p.y, p.z, g);
     float rho = 0.f, gradj_l2 = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
-    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
-        const float4 q = __ldg(&x[j]);
+    // the particle itself: r2 = 0 adds poly6(0) to rho at its place in the visiting order and
+    // nothing else (spiky is 0 below KERNAL_EPS, and gradj skips j == i). Taking it out of the
+    // general path keeps three 0/rho0 divisions off IEEE division's slow path in every warp.
+    const float w_self = poly6_in(0.f, c);
+    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q) {
+        if (j == (uint32_t)i) {
+            rho = __fadd_rn(rho, w_self);
+            return;
+        }
         const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
         const float r2 = sumsq(dx, dy, dz);
-        if (r2 < c.h2_cull) {
-            rho = __fadd_rn(rho, poly6(r2, c));
-            const float s = spiky_scale(r2, c);
-            const float gx = __fdiv_rn(__fmul_rn(dx, s), c.pho0);
-            const float gy = __fdiv_rn(__fmul_rn(dy, s), c.pho0);
-            const float gz = __fdiv_rn(__fmul_rn(dz, s), c.pho0);
-            gix = __fadd_rn(gix, gx);
-            giy = __fadd_rn(giy, gy);
-            giz = __fadd_rn(giz, gz);
-            if ((int64_t)j != i) gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
-        }
+        rho = __fadd_rn(rho, poly6(r2, c));
+        const float s = spiky_scale(r2, c);
+        const float gx = __fdiv_rn(__fmul_rn(dx, s), c.pho0);
+        const float gy = __fdiv_rn(__fmul_rn(dy, s), c.pho0);
+        const float gz = __fdiv_rn(__fmul_rn(dz, s), c.pho0);
+        gix = __fadd_rn(gix, gx);
+        giy = __fadd_rn(giy, gy);
+        giz = __fadd_rn(giz, gz);
+        gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
     });
     if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
     const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
@@ -81,35 +148,31 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
 }
 
 template <bool EXACT_POW>
-__global__ void __launch_bounds__(GATHER_THREADS)
+__global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                const uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
                const __grid_constant__ SolverConsts c) {
+    extern __shared__ uint16_t s_list[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
     const float4 p = xl[i];
-    const int3 cc = cell_of(p.x, p.y, p.z, g);
     float ax = 0.f, ay = 0.f, az = 0.f;
-    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
-        if ((int64_t)j == i) return;
-        const float4 q = __ldg(&xl[j]);
+    gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4 q) {
         const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
         const float r2 = sumsq(dx, dy, dz);
-        if (r2 < c.h2_cull) {
-            const float w = poly6(r2, c);
-            float pw;
-            if (EXACT_POW) {
-                pw = powf(w, c.n_corr);
-            } else {  // n_corr == 4
-                const float w2 = __fmul_rn(w, w);
-                pw = __fmul_rn(w2, w2);
-            }
-            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-            const float s = spiky_scale(r2, c);
-            ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
-            ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
-            az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
+        const float w = poly6(r2, c);
+        float pw;
+        if (EXACT_POW) {
+            pw = powf(w, c.n_corr);
+        } else {  // n_corr == 4
+            const float w2 = __fmul_rn(w, w);
+            pw = __fmul_rn(w2, w2);
         }
+        const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+        const float s = spiky_scale(r2, c);
+        ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
+        ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
+        az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
     });
     const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
     const float vx = fmaxf(fminf(__fdiv_rn(ax, c.pho0), max_dp), -max_dp);
@@ -142,29 +205,26 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
     store_f3(npos_io, i, q.x, q.y, q.z);
 }
 
-__global__ void __launch_bounds__(GATHER_THREADS)
+__global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t n,
             const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    extern __shared__ uint16_t s_list[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
     const float4 p = x[i];
     const float4 vi = v4[i];
-    const int3 cc = cell_of(p.x, p.y, p.z, g);
     float ax = 0.f, ay = 0.f, az = 0.f;
-    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
-        const float4 q = __ldg(&x[j]);
+    gather<false>(p, (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q) {
         const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
-        if (r2 < c.h2) {
-            const float4 vj = __ldg(&v4[j]);
-            const float w = poly6_in(r2, c);
-            const float den = __fadd_rn(vi.w, vj.w);
-            const float tx = __fsub_rn(vj.x, vi.x), ty = __fsub_rn(vj.y, vi.y), tz = __fsub_rn(vj.z, vi.z);
-            ax = __fadd_rn(ax, __fdiv_rn(__fmul_rn(__fadd_rn(tx, tx), w), den));
-            ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
-            az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
-        }
+        const float4 vj = __ldg(&v4[j]);
+        const float w = poly6_in(r2, c);
+        const float den = __fadd_rn(vi.w, vj.w);
+        const float tx = __fsub_rn(vj.x, vi.x), ty = __fsub_rn(vj.y, vi.y), tz = __fsub_rn(vj.z, vi.z);
+        ax = __fadd_rn(ax, __fdiv_rn(__fmul_rn(__fadd_rn(tx, tx), w), den));
+        ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
+        az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
     });
     store_f3(nvel_out, i, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
     iid_out[i] = iid_sorted[i];
@@ -174,16 +234,11 @@ __global__ void __launch_bounds__(GATHER_THREADS)
 neighbor_count_kernel(const float4* __restrict__ x, const uint2* __restrict__ cell_range,
                       uint32_t* __restrict__ count, int64_t n, const __grid_constant__ GridConsts g,
                       const __grid_constant__ SolverConsts c) {
+    extern __shared__ uint16_t s_list[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
-    const float4 p = x[i];
-    const int3 cc = cell_of(p.x, p.y, p.z, g);
     uint32_t cnt = 0;
-    for_each_candidate(cc, cell_range, g, [&](uint32_t j) {
-        const float4 q = __ldg(&x[j]);
-        const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
-        if (r2 < c.h2) cnt++;
-    });
+    gather<false>(x[i], (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4) { cnt++; });
     count[i] = cnt;
 }
 
@@ -192,7 +247,7 @@ static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1)
 cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t n,
                           const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    lambda_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(x, xl, rho, cell_range, n, g, c);
+    lambda_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -201,9 +256,9 @@ cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_ra
                            const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     if (c.exact_pow || c.n_corr != 4.0f)
-        delta_p_kernel<true><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(xl, x_out, cell_range, n, g, c);
+        delta_p_kernel<true><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, g, c);
     else
-        delta_p_kernel<false><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(xl, x_out, cell_range, n, g, c);
+        delta_p_kernel<false><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -221,7 +276,7 @@ cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_ran
                         const uint32_t* iid_sorted, uint32_t* iid_out, int64_t n, const GridConsts& g,
                         const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(x, v4, cell_range, nvel_out, iid_sorted, iid_out, n, g, c);
+    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, v4, cell_range, nvel_out, iid_sorted, iid_out, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -229,7 +284,7 @@ cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_ran
 cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
                                   const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    neighbor_count_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, 0, st>>>(x, cell_range, count, n, g, c);
+    neighbor_count_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, cell_range, count, n, g, c);
     return cudaGetLastError();
 }
 

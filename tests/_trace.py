@@ -31,12 +31,12 @@ def make_scene(name):
     elif name == "cube2k":  # one suspended block in a small box; full dumps stay small
         ulim, llim = np.float32([1.2, 1.0, 1.5]), np.float32([0, 0, 0])
         pos, vel, iid = O.scene_cube([0.9, 0.8, 1.3], [0.3, 0.2, 0.5], [12, 12, 16])
-        steps = 3
+        steps = 2
     elif name == "floor2k":  # block resting on the floor in a corner: boundary clamps + boundary density on
         ulim, llim = np.float32([1.0, 1.0, 1.0]), np.float32([0, 0, 0])
         pos, vel, iid = O.scene_cube([0.62, 0.62, 0.82], [0.02, 0.02, 0.02], [12, 12, 16])
         p.k_boundaryDensity = 0.5
-        steps = 3
+        steps = 2
     elif name == "wall2k":  # moving wall (FluidSystem.cpp:104-110) squeezing a block, non-cubic box
         ulim, llim = np.float32([0.85, 0.7, 1.1]), np.float32([0, 0, 0])
         pos, vel, iid = O.scene_cube([0.65, 0.62, 0.82], [0.05, 0.02, 0.02], [12, 12, 16])
@@ -147,7 +147,7 @@ def trace_reference(scene):
     return T
 
 
-def trace_product(scene, pbf, exact_pow=False, use_step=False):
+def trace_product(scene, pbf, exact_pow=True, use_step=False):
     """libpbf_b200.so through the C-ABI. use_step=True runs the fused pbf_step instead of the stage
     entry points (then only the step outputs and the grid are recorded)."""
     import torch
