@@ -70,6 +70,7 @@ struct pbf_sim {
     float* rho = nullptr;
     uint32_t* iid_sorted = nullptr;
     uint2* cell_range = nullptr;
+    PairList pairs_list;            // lambda -> delta-p neighbour list (null when disabled / too large)
     uint32_t* count_scratch = nullptr;
     uint32_t* read_scratch = nullptr;
     double* stats_partial = nullptr;
@@ -174,6 +175,7 @@ int refresh_consts(pbf_sim* s) {
 void free_all(pbf_sim* s) {
     cudaFree(s->keys); cudaFree(s->sort_zero); cudaFree(s->pairs[0]); cudaFree(s->pairs[1]);
     cudaFree(s->x[0]); cudaFree(s->x[1]); cudaFree(s->xl); cudaFree(s->rho); cudaFree(s->iid_sorted);
+    cudaFree(s->pairs_list.idx); cudaFree(s->pairs_list.sw); cudaFree(s->pairs_list.cnt);
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
     if (s->stats_host) cudaFreeHost(s->stats_host);
@@ -262,6 +264,24 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
         free_all(s);
         delete s;
         return fail(PBF_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    }
+    // Neighbour-list reuse between the lambda and delta-p passes: ~1.1 KB per particle of scratch.
+    // Taken only if it fits comfortably (<= 40 % of the free memory); PBF_NO_PAIR_REUSE=1 disables it.
+    {
+        const char* np = getenv("PBF_NO_PAIR_REUSE");
+        size_t ib, sb, cb, free_b = 0, total_b = 0;
+        const size_t need = pair_list_bytes(max_particles, &ib, &sb, &cb);
+        cudaMemGetInfo(&free_b, &total_b);
+        if (!(np && np[0] == '1') && need <= free_b / 10 * 4) {
+            cudaError_t pe = cudaMalloc((void**)&s->pairs_list.idx, ib);
+            if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.sw, sb);
+            if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.cnt, cb);
+            if (pe != cudaSuccess) {
+                cudaFree(s->pairs_list.idx); cudaFree(s->pairs_list.sw); cudaFree(s->pairs_list.cnt);
+                s->pairs_list = PairList();
+                cudaGetLastError();
+            }
+        }
     }
     int rc = refresh_consts(s);
     if (rc != PBF_OK) { free_all(s); delete s; return rc; }
@@ -385,8 +405,8 @@ int pbf_stage_build_grid(pbf_sim* s) {
 int pbf_stage_correct_density(pbf_sim* s) {
     if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "correct_density: build_grid first");
     // (each iteration overwrites the slot: the timers report the LAST iteration of the step)
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->n, s->pairs_list, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->n, s->pairs_list, s->g, s->c, s->stream, &s->launches));
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;

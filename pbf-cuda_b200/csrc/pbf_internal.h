@@ -81,10 +81,19 @@ cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* 
                            int64_t* launches);
 
 // solver passes (solver.cu)
+// Neighbour list the lambda pass saves for the delta-p pass of the same iteration (null = off).
+struct PairList {
+    uint32_t* idx = nullptr;  // slot of the k-th in-range neighbour
+    float2* sw = nullptr;     // (spiky scale, poly6^n_corr) of that pair
+    uint32_t* cnt = nullptr;  // per particle: number of entries, or the overflow flag
+};
+size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_bytes, size_t* cnt_bytes);
 cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t n,
-                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+                          const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                          int64_t* launches);
 cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t n,
-                           const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+                           const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                           int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t n, const SolverConsts& c,
                                    cudaStream_t st, int64_t* launches);

@@ -25,8 +25,12 @@ namespace pbf {
 #ifndef PBF_LIST_CAP
 #define PBF_LIST_CAP 32
 #endif
+#ifndef PBF_PAIR_CAP
+#define PBF_PAIR_CAP 96
+#endif
 constexpr int GATHER_THREADS = 128;
-constexpr int LIST_CAP = PBF_LIST_CAP;  // in-range neighbours buffered per thread and x-slab before a flush
+constexpr int LIST_CAP = PBF_LIST_CAP;
+constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pass can hand to the delta-p pass  // in-range neighbours buffered per thread and x-slab before a flush
 constexpr size_t LIST_SMEM = (size_t)LIST_CAP * GATHER_THREADS * sizeof(uint16_t);  // 8 KB per CTA
 
 // Two-phase gather of one particle (one thread), the core of all three neighbour sweeps.
@@ -44,76 +48,102 @@ constexpr size_t LIST_SMEM = (size_t)LIST_CAP * GATHER_THREADS * sizeof(uint16_t
 // full, so any neighbour count stays correct and ordered; entries are 16-bit offsets from the
 // slab's first slot (re-based if a slab ever spans more than 65535 slots), which keeps the
 // shared-memory footprint at 8 KB per CTA and leaves the rest of the 256 KB for L1.
-template <bool SKIP_SELF, typename Heavy>
+struct NoHooks {
+    __device__ __forceinline__ void slab_done(int, uint32_t, int) {}
+    __device__ __forceinline__ void rebased() {}
+};
+
+template <bool SKIP_SELF, typename Heavy, typename Hooks>
 __device__ __forceinline__ void gather(const float4 p, const uint32_t self, const float limit,
                                        const float4* __restrict__ x, const uint2* __restrict__ cell_range,
-                                       const GridConsts& g, uint16_t* __restrict__ my_list, Heavy&& heavy) {
+                                       const GridConsts& g, uint16_t* __restrict__ my_list, Heavy&& heavy,
+                                       Hooks&& hooks) {
     const int3 cc = cell_of(p.x, p.y, p.z, g);
     const int zlo = max(cc.z - 1, 0), zhi = min(cc.z + 1, g.dim[2] - 1);
     uint16_t* const list_full = my_list + (LIST_CAP - 4) * GATHER_THREADS;
+    int k_total = 0;  // in-range neighbours handed to `heavy` so far (its third argument)
 #pragma unroll 1
     for (int dx = -1; dx <= 1; dx++) {
         const int cx = cc.x + dx;
-        if (cx < 0 || cx >= g.dim[0]) continue;
         uint32_t base = 0xffffffffu;
-        uint16_t* tail = my_list;  // next free entry of this thread's list
-        auto flush = [&]() {
+        if (cx >= 0 && cx < g.dim[0]) {
+            uint16_t* tail = my_list;  // next free entry of this thread's list
+            auto flush = [&]() {
 #pragma unroll 2
-            for (const uint16_t* e = my_list; e < tail; e += GATHER_THREADS) {
-                const uint32_t j = base + *e;
-                heavy(j, __ldg(&x[j]));
-            }
-            tail = my_list;
-        };
-        // branch-free append: always store the offset, advance the tail only on a hit
-        auto test = [&](const uint32_t j, const float4 q) {
-            const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
-            bool pass = r2 < limit;
-            if (SKIP_SELF) pass &= (j != self);
-            *tail = (uint16_t)(j - base);
-            tail += pass ? GATHER_THREADS : 0;
-        };
+                for (const uint16_t* e = my_list; e < tail; e += GATHER_THREADS) {
+                    const uint32_t j = base + *e;
+                    heavy(j, __ldg(&x[j]), k_total);
+                    k_total++;
+                }
+                tail = my_list;
+            };
+            // branch-free append: always store the offset, advance the tail only on a hit
+            auto test = [&](const uint32_t j, const float4 q) {
+                const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
+                bool pass = r2 < limit;
+                if (SKIP_SELF) pass &= (j != self);
+                *tail = (uint16_t)(j - base);
+                tail += pass ? GATHER_THREADS : 0;
+            };
 #pragma unroll 1
-        for (int dy = -1; dy <= 1; dy++) {
-            const int cy = cc.y + dy;
-            if (cy < 0 || cy >= g.dim[1]) continue;
-            const int cbase = cx * g.dyz + cy * g.dim[2];
-            uint32_t start = 0, end = 0;
-            bool any = false;
-            for (int z = zlo; z <= zhi; z++) {
-                const uint2 r = __ldg(&cell_range[cbase + z]);
-                if (r.y > r.x) {
-                    if (!any) { start = r.x; any = true; }
-                    end = r.y;
+            for (int dy = -1; dy <= 1; dy++) {
+                const int cy = cc.y + dy;
+                if (cy < 0 || cy >= g.dim[1]) continue;
+                const int cbase = cx * g.dyz + cy * g.dim[2];
+                uint32_t start = 0, end = 0;
+                bool any = false;
+                for (int z = zlo; z <= zhi; z++) {
+                    const uint2 r = __ldg(&cell_range[cbase + z]);
+                    if (r.y > r.x) {
+                        if (!any) { start = r.x; any = true; }
+                        end = r.y;
+                    }
                 }
-            }
-            if (!any) continue;
-            if (base == 0xffffffffu) base = start;
-            uint32_t j = start;
-            while (j < end) {
-                if (end - base > 0xffffu) {  // offsets would not fit 16 bits: drain and re-base (rare)
-                    flush();
-                    base = j;
-                }
-                const uint32_t stop = min(end, base + 0xffffu);
-                for (; j + 4 <= stop; j += 4) {  // four independent loads in flight, tested in order
-                    const float4* xp = x + j;
-                    const float4 q0 = __ldg(xp), q1 = __ldg(xp + 1), q2 = __ldg(xp + 2), q3 = __ldg(xp + 3);
-                    test(j, q0); test(j + 1, q1); test(j + 2, q2); test(j + 3, q3);
+                if (!any) continue;
+                if (base == 0xffffffffu) base = start;
+                uint32_t j = start;
+                while (j < end) {
+                    if (end - base > 0xffffu) {  // offsets would not fit 16 bits: drain and re-base (rare)
+                        flush();
+                        base = j;
+                        hooks.rebased();
+                    }
+                    const uint32_t stop = min(end, base + 0xffffu);
+                    for (; j + 4 <= stop; j += 4) {  // four independent loads in flight, tested in order
+                        const float4* xp = x + j;
+                        const float4 q0 = __ldg(xp), q1 = __ldg(xp + 1), q2 = __ldg(xp + 2), q3 = __ldg(xp + 3);
+                        test(j, q0); test(j + 1, q1); test(j + 2, q2); test(j + 3, q3);
+                        if (tail > list_full) flush();
+                    }
+                    for (; j < stop; j++) test(j, __ldg(&x[j]));
                     if (tail > list_full) flush();
                 }
-                for (; j < stop; j++) test(j, __ldg(&x[j]));
-                if (tail > list_full) flush();
             }
+            flush();
         }
-        flush();
+        hooks.slab_done(dx + 1, base, k_total);
     }
 }
 
+// ---- neighbour-list reuse between the two passes of one Jacobi iteration ------------------------
+// The lambda and delta-p passes of an iteration read the SAME positions (the reference runs
+// computeLambda and computetpos on the same dc_npos, Simulator.cu:222-245), so their in-range
+// neighbour sets and the per-pair kernel values coincide. The lambda pass therefore saves, per
+// particle and in visiting order, the slot offset of every in-range neighbour plus the two values
+// the delta-p pass needs from the pair geometry: the spiky scale s and w^n_corr. The delta-p pass
+// replays the list: no cull, no sqrt, no division, no pow — and produces the same bits, because it
+// consumes the very values its own evaluation would have produced.
+// Layout (block b of 128 threads, entry k, thread t): [(b*PAIR_CAP + k)*128 + t] — a warp's k-th
+// entries are contiguous (4 B slot + 8 B (s, w^n)). A particle with more than PAIR_CAP neighbours
+// is flagged in its count word and handled by the delta-p pass's full gather instead.
+constexpr uint32_t PAIR_OVERFLOW = 1u << 31;
+
+template <bool EXACT_POW, bool SAVE_PAIRS>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __restrict__ rho_out,
-              const uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
-              const __grid_constant__ SolverConsts c) {
+              const uint2* __restrict__ cell_range, int64_t n, uint32_t* __restrict__ pair_idx,
+              float2* __restrict__ pair_sw, uint32_t* __restrict__ pair_cnt,
+              const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
@@ -123,66 +153,114 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
     // nothing else (spiky is 0 below KERNAL_EPS, and gradj skips j == i). Taking it out of the
     // general path keeps three 0/rho0 divisions off IEEE division's slow path in every warp.
     const float w_self = poly6_in(0.f, c);
-    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q) {
+    const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
+    int n_pairs = 0;
+    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q, int k) {
+        float s = 0.f, pw = 0.f;
         if (j == (uint32_t)i) {
             rho = __fadd_rn(rho, w_self);
-            return;
+        } else {
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            const float r2 = sumsq(dx, dy, dz);
+            const float w = poly6(r2, c);
+            rho = __fadd_rn(rho, w);
+            s = spiky_scale(r2, c);
+            const float gx = __fdiv_rn(__fmul_rn(dx, s), c.pho0);
+            const float gy = __fdiv_rn(__fmul_rn(dy, s), c.pho0);
+            const float gz = __fdiv_rn(__fmul_rn(dz, s), c.pho0);
+            gix = __fadd_rn(gix, gx);
+            giy = __fadd_rn(giy, gy);
+            giz = __fadd_rn(giz, gz);
+            gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
+            if (SAVE_PAIRS) {
+                if (EXACT_POW) {
+                    pw = powf(w, c.n_corr);
+                } else {  // n_corr == 4
+                    const float w2 = __fmul_rn(w, w);
+                    pw = __fmul_rn(w2, w2);
+                }
+            }
         }
-        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-        const float r2 = sumsq(dx, dy, dz);
-        rho = __fadd_rn(rho, poly6(r2, c));
-        const float s = spiky_scale(r2, c);
-        const float gx = __fdiv_rn(__fmul_rn(dx, s), c.pho0);
-        const float gy = __fdiv_rn(__fmul_rn(dy, s), c.pho0);
-        const float gz = __fdiv_rn(__fmul_rn(dz, s), c.pho0);
-        gix = __fadd_rn(gix, gx);
-        giy = __fadd_rn(giy, gy);
-        giz = __fadd_rn(giz, gz);
-        gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
-    });
+        // (the self entry is saved with s = pw = 0: the delta-p pass then adds an exact zero)
+        if (SAVE_PAIRS) {
+            if (k < PAIR_CAP) {
+                const size_t e = pair0 + (size_t)k * GATHER_THREADS;
+                pair_idx[e] = j;
+                pair_sw[e] = make_float2(s, pw);
+            }
+            n_pairs = k + 1;
+        }
+    }, NoHooks());
     if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
     const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
     const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
     xl[i] = make_float4(p.x, p.y, p.z, lambda);
     rho_out[i] = rho;
+    if (SAVE_PAIRS) pair_cnt[i] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
 }
 
-template <bool EXACT_POW>
+// shared tail of the delta-p pass: divide, clamp to MAX_DP, add, clamp to the box (f64 like the reference)
+__device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float ay, float az, const SolverConsts& c) {
+    const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
+    const float vx = fmaxf(fminf(__fdiv_rn(ax, c.pho0), max_dp), -max_dp);
+    const float vy = fmaxf(fminf(__fdiv_rn(ay, c.pho0), max_dp), -max_dp);
+    const float vz = fmaxf(fminf(__fdiv_rn(az, c.pho0), max_dp), -max_dp);
+    const float qx = (float)fmax(fmin((double)__fadd_rn(p.x, vx), c.lim_hi[0]), c.lim_lo[0]);
+    const float qy = (float)fmax(fmin((double)__fadd_rn(p.y, vy), c.lim_hi[1]), c.lim_lo[1]);
+    const float qz = (float)fmax(fmin((double)__fadd_rn(p.z, vz), c.lim_hi[2]), c.lim_lo[2]);
+    return make_float4(qx, qy, qz, 0.f);
+}
+
+template <bool EXACT_POW, bool USE_PAIRS>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
-               const uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
-               const __grid_constant__ SolverConsts c) {
+               const uint2* __restrict__ cell_range, int64_t n, const uint32_t* __restrict__ pair_idx,
+               const float2* __restrict__ pair_sw, const uint32_t* __restrict__ pair_cnt,
+               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4 q) {
-        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-        const float r2 = sumsq(dx, dy, dz);
-        const float w = poly6(r2, c);
-        float pw;
-        if (EXACT_POW) {
-            pw = powf(w, c.n_corr);
-        } else {  // n_corr == 4
-            const float w2 = __fmul_rn(w, w);
-            pw = __fmul_rn(w2, w2);
+    bool replayed = false;
+    if (USE_PAIRS) {
+        const uint32_t cnt = pair_cnt[i];
+        if (!(cnt & PAIR_OVERFLOW)) {
+            replayed = true;
+            const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
+#pragma unroll 4
+            for (uint32_t k = 0; k < cnt; k++) {
+                const size_t e = pair0 + (size_t)k * GATHER_THREADS;
+                const uint32_t j = __ldg(&pair_idx[e]);
+                const float2 sw = __ldg(&pair_sw[e]);
+                const float4 q = __ldg(&xl[j]);
+                const float sc = __fmaf_rn(c.coef_corr, sw.y, __fadd_rn(p.w, q.w));
+                ax = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.x, q.x), sw.x), ax);
+                ay = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.y, q.y), sw.x), ay);
+                az = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.z, q.z), sw.x), az);
+            }
         }
-        const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-        const float s = spiky_scale(r2, c);
-        ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
-        ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
-        az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
-    });
-    const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
-    const float vx = fmaxf(fminf(__fdiv_rn(ax, c.pho0), max_dp), -max_dp);
-    const float vy = fmaxf(fminf(__fdiv_rn(ay, c.pho0), max_dp), -max_dp);
-    const float vz = fmaxf(fminf(__fdiv_rn(az, c.pho0), max_dp), -max_dp);
-    // box clamp in double like the reference (LIM_EPS is a double literal)
-    const float qx = (float)fmax(fmin((double)__fadd_rn(p.x, vx), c.lim_hi[0]), c.lim_lo[0]);
-    const float qy = (float)fmax(fmin((double)__fadd_rn(p.y, vy), c.lim_hi[1]), c.lim_lo[1]);
-    const float qz = (float)fmax(fmin((double)__fadd_rn(p.z, vz), c.lim_hi[2]), c.lim_lo[2]);
-    x_out[i] = make_float4(qx, qy, qz, 0.f);
+    }
+    if (!replayed) {
+        gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4 q, int) {
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            const float r2 = sumsq(dx, dy, dz);
+            const float w = poly6(r2, c);
+            float pw;
+            if (EXACT_POW) {
+                pw = powf(w, c.n_corr);
+            } else {  // n_corr == 4
+                const float w2 = __fmul_rn(w, w);
+                pw = __fmul_rn(w2, w2);
+            }
+            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+            const float s = spiky_scale(r2, c);
+            ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
+            ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
+            az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
+        }, NoHooks());
+    }
+    x_out[i] = delta_p_finish(p, ax, ay, az, c);
 }
 
 // vel = (npos - pos) * inv_dt, plus everything the caller-facing buffers need from this point:
@@ -216,7 +294,7 @@ xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
     const float4 p = x[i];
     const float4 vi = v4[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<false>(p, (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q) {
+    gather<false>(p, (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q, int) {
         const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
         const float4 vj = __ldg(&v4[j]);
         const float w = poly6_in(r2, c);
@@ -225,7 +303,7 @@ xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
         ax = __fadd_rn(ax, __fdiv_rn(__fmul_rn(__fadd_rn(tx, tx), w), den));
         ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
         az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
-    });
+    }, NoHooks());
     store_f3(nvel_out, i, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
     iid_out[i] = iid_sorted[i];
 }
@@ -238,27 +316,49 @@ neighbor_count_kernel(const float4* __restrict__ x, const uint2* __restrict__ ce
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
     uint32_t cnt = 0;
-    gather<false>(x[i], (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4) { cnt++; });
+    gather<false>(x[i], (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4, int) { cnt++; }, NoHooks());
     count[i] = cnt;
 }
 
 static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_bytes, size_t* cnt_bytes) {
+    const size_t blocks = (size_t)((max_particles + GATHER_THREADS - 1) / GATHER_THREADS);
+    *idx_bytes = blocks * PAIR_CAP * GATHER_THREADS * sizeof(uint32_t);
+    *sw_bytes = blocks * PAIR_CAP * GATHER_THREADS * sizeof(float2);
+    *cnt_bytes = blocks * GATHER_THREADS * sizeof(uint32_t);
+    return *idx_bytes + *sw_bytes + *cnt_bytes;
+}
+
 cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t n,
-                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+                          const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                          int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    lambda_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, g, c);
+    const bool exact = c.exact_pow || c.n_corr != 4.0f;
+    const unsigned nb = nblocks(n, GATHER_THREADS);
+    if (!pl.idx)
+        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, nullptr, nullptr, nullptr, g, c);
+    else if (exact)
+        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
+    else
+        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t n,
-                           const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+                           const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                           int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    if (c.exact_pow || c.n_corr != 4.0f)
-        delta_p_kernel<true><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, g, c);
-    else
-        delta_p_kernel<false><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, g, c);
+    const bool exact = c.exact_pow || c.n_corr != 4.0f;
+    const unsigned nb = nblocks(n, GATHER_THREADS);
+    if (pl.idx) {
+        if (exact) delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
+        else delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
+    } else {
+        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, nullptr, nullptr, nullptr, g, c);
+        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, nullptr, nullptr, nullptr, g, c);
+    }
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

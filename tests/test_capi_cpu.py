@@ -93,3 +93,17 @@ def test_no_cpu_fallback(pbf):
     assert e.value.code == pbf.ERR_CUDA
     assert pbf.lib().pbf_step(None, None, None, None, None, None, 0, None) == pbf.ERR_INVALID
     assert b"null" in pbf.lib().pbf_last_error()
+
+
+def test_cpp_shim_builds_and_fails_loudly_without_gpu(pbf):
+    """The C++ mirror of the reference's Simulator / ParticleSource (pbf-cuda_b200/host) compiles with
+    plain g++ against include/pbf.h, and keeps the reference's print-and-exit error convention."""
+    import subprocess
+    import torch
+    pkg = os.path.join(ROOT, "pbf-cuda_b200")
+    subprocess.check_call(["make", "-C", pkg, "harness"], stdout=subprocess.DEVNULL)
+    exe = os.path.join(pkg, "pbf_headless")
+    assert os.path.exists(exe)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "1"], capture_output=True, text=True)
+        assert r.returncode == 1 and "PBF error at" in r.stderr and "pbf_create" in r.stderr
