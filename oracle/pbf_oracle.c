@@ -374,13 +374,20 @@ static void tpos_pass(orc_sim* s) {
     }
 }
 
-/* correctDensity (Simulator.cu:213-249): lambda pass, coef_corr, tpos pass, commit. */
-void orc_correct_density(orc_sim* s) {
-    lambda_pass(s);
+/* The two halves of correctDensity, exported separately so that the slab-protocol tests can
+ * refresh ghost lambdas between them (tests/_slab_cpu.py): Simulator.cu:222-233 and :235-248. */
+void orc_lambda_pass(orc_sim* s) { lambda_pass(s); }
+void orc_delta_p_pass(orc_sim* s) {
     poly6_t poly6 = make_poly6(s->p.h);
     s->coef_corr = -s->p.k_corr / powf(poly6_eval(poly6, s->p.delta_q * s->p.delta_q), s->p.n_corr); /* :235 */
     tpos_pass(s);
     memcpy(s->npos, s->tpos, sizeof(float) * 3 * (size_t)s->n); /* thrust::copy_n, :247-248 */
+}
+
+/* correctDensity (Simulator.cu:213-249): lambda pass, coef_corr, tpos pass, commit. */
+void orc_correct_density(orc_sim* s) {
+    orc_lambda_pass(s);
+    orc_delta_p_pass(s);
 }
 
 /* h_updateVelocity (Simulator.cu:127-137). */

@@ -46,6 +46,8 @@ void orc_bind(orc_sim* s, float* pos, float* npos, float* vel, float* nvel, uint
 void orc_advect(orc_sim* s);            /* Simulator.cu:165-176, Simulator_kernel.cuh:7-19 */
 void orc_build_grid(orc_sim* s);        /* Simulator.cu:178-211, Simulator_kernel.cuh:21-50 */
 void orc_correct_density(orc_sim* s);   /* Simulator.cu:213-249, one iteration */
+void orc_lambda_pass(orc_sim* s);       /*   its first half:  Simulator.cu:222-233 */
+void orc_delta_p_pass(orc_sim* s);      /*   its second half: Simulator.cu:235-248 */
 void orc_update_velocity(orc_sim* s);   /* Simulator.cu:267-274 */
 void orc_correct_velocity(orc_sim* s);  /* Simulator.cu:251-265 */
 

@@ -36,7 +36,13 @@ EXPORTS = (
     "pbf_enable_stage_timing", "pbf_get_stage_ms", "pbf_get_kernel_ms", "pbf_launch_count", "pbf_device_alloc", "pbf_device_free",
     "pbf_copy_h2d", "pbf_copy_d2h", "pbf_device_sync", "pbf_scene_cube", "pbf_scene_double_dam_reference",
     "pbf_scene_block_device", "pbf_scene_block_host", "pbf_last_error", "pbf_version",
+    "pbf_slab_begin", "pbf_slab_get_layout", "pbf_slab_plane_counts", "pbf_stage_lambda", "pbf_stage_delta_p",
+    "pbf_slab_halo", "pbf_slab_flags", "pbf_slab_sort_state", "pbf_scene_block_slice_device",
+    "pbf_scene_block_slice_host",
 )
+
+HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
+SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST = 1, 2
 
 
 class PbfError(RuntimeError):
@@ -56,6 +62,20 @@ class GUIParams(C.Structure):
         q = GUIParams()
         C.memmove(C.byref(q), C.byref(self), C.sizeof(GUIParams))
         return q
+
+
+class SlabStep(C.Structure):
+    """pbf_slab_step (include/pbf.h): one rank's view of one step of the x-slab decomposition."""
+    _fields_ = [("x_begin", C.c_int32), ("x_end", C.c_int32), ("ghost", C.c_int32), ("has_left", C.c_int32),
+                ("has_right", C.c_int32), ("n_own", C.c_int64), ("m_left", C.c_int64), ("m_right", C.c_int64),
+                ("send_left_end", C.c_int64), ("send_right_begin", C.c_int64)]
+
+
+class SlabLayout(C.Structure):
+    """pbf_slab_layout (include/pbf.h)."""
+    _fields_ = [("n_local", C.c_int64), ("own_first", C.c_int64), ("own_count", C.c_int64),
+                ("send_left_count", C.c_int64), ("send_right_count", C.c_int64),
+                ("recv_left_count", C.c_int64), ("recv_right_count", C.c_int64), ("flags", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -103,6 +123,18 @@ _lib.pbf_scene_cube.argtypes = [_f3, _f3, C.POINTER(C.c_int32), C.POINTER(C.c_ui
 _lib.pbf_scene_double_dam_reference.argtypes = [_vp, _vp, _vp, _i64, C.POINTER(_i64), _f3, _f3]
 _lib.pbf_scene_block_device.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]
 _lib.pbf_scene_block_host.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, _vp, _vp, _vp]
+_lib.pbf_slab_begin.argtypes = [_vp, C.POINTER(SlabStep), _vp, _vp, _vp, _vp, _vp, _vp]
+_lib.pbf_slab_get_layout.argtypes = [_vp, C.POINTER(SlabLayout)]
+_lib.pbf_slab_plane_counts.argtypes = [_vp, C.c_int32, C.c_int32, C.POINTER(_i64)]
+_lib.pbf_stage_lambda.argtypes = [_vp]
+_lib.pbf_stage_delta_p.argtypes = [_vp]
+_lib.pbf_slab_halo.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
+_lib.pbf_slab_flags.argtypes = [_vp, C.POINTER(C.c_uint32)]
+_lib.pbf_slab_sort_state.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.pbf_scene_block_slice_device.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, C.c_int32,
+                                              C.c_int32, _vp, _vp, _vp, _vp]
+_lib.pbf_scene_block_slice_host.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, C.c_int32,
+                                            C.c_int32, _vp, _vp, _vp]
 _lib.pbf_last_error.restype = C.c_char_p
 _lib.pbf_version.restype = C.c_char_p
 
@@ -261,9 +293,41 @@ class Simulator:
     def advect(self): _check(_lib.pbf_stage_advect(self._h))
     def buildGridHash(self): _check(_lib.pbf_stage_build_grid(self._h))
     def correctDensity(self): _check(_lib.pbf_stage_correct_density(self._h))
+    def computeLambda(self): _check(_lib.pbf_stage_lambda(self._h))     # first half of correctDensity
+    def computeDeltaP(self): _check(_lib.pbf_stage_delta_p(self._h))    # second half (+ the Jacobi commit)
     def updateVelocity(self): _check(_lib.pbf_stage_update_velocity(self._h))
     def correctVelocity(self): _check(_lib.pbf_stage_correct_velocity(self._h))
     def end(self): _check(_lib.pbf_stage_end(self._h))
+
+    # -- multi-GPU x-slab decomposition (include/pbf.h "multi-GPU"); the transport lives in slab.py
+    def slab_begin(self, step, pos, npos, vel, nvel, iid, stream=None):
+        _check(_lib.pbf_slab_begin(self._h, C.byref(step), _ptr(pos), _ptr(npos), _ptr(vel), _ptr(nvel), _ptr(iid), stream))
+
+    def slab_layout(self):
+        lay = SlabLayout()
+        _check(_lib.pbf_slab_get_layout(self._h, C.byref(lay)))
+        self.n = int(lay.n_local)
+        return lay
+
+    def slab_plane_counts(self, x_first, count):
+        out = np.zeros(count, np.int64)
+        _check(_lib.pbf_slab_plane_counts(self._h, int(x_first), int(count), out.ctypes.data_as(C.POINTER(_i64))))
+        return out
+
+    def slab_halo(self, what):
+        """Device pointers (send_left, recv_left, send_right, recv_right) of one halo refresh."""
+        p = [_vp() for _ in range(4)]
+        _check(_lib.pbf_slab_halo(self._h, int(what), *[C.byref(q) for q in p]))
+        return tuple(q.value or 0 for q in p)
+
+    def slab_flags(self):
+        f = C.c_uint32()
+        _check(_lib.pbf_slab_flags(self._h, C.byref(f)))
+        return int(f.value)
+
+    def slab_sort_state(self, x_begin, x_end, has_left, has_right, pos, npos, vel, nvel, iid, n, stream=None):
+        _check(_lib.pbf_slab_sort_state(self._h, int(x_begin), int(x_end), int(bool(has_left)), int(bool(has_right)),
+                                        _ptr(pos), _ptr(npos), _ptr(vel), _ptr(nvel), _ptr(iid), int(n), stream))
 
     # -- read-backs
     def read(self, what, count=None):
@@ -396,6 +460,28 @@ def scene_block_device(origin, n3, d_pos, d_vel, d_iid, spacing=0.05, seed=27, f
     n3a = (C.c_int32 * 3)(*[int(v) for v in n3])
     _check(_lib.pbf_scene_block_device(op, n3a, spacing, seed, first_iid, _ptr(d_pos), _ptr(d_vel), _ptr(d_iid), stream))
     return int(n3[0]) * int(n3[1]) * int(n3[2])
+
+
+def scene_block_slice_device(origin, n3, ix_begin, ix_end, d_pos, d_vel, d_iid, spacing=0.05, seed=27, first_iid=0,
+                             stream=None):
+    """Lattice layers [ix_begin, ix_end) of the block, bit-identical to the full block's particles."""
+    o, op = _f3arr(origin)
+    n3a = (C.c_int32 * 3)(*[int(v) for v in n3])
+    _check(_lib.pbf_scene_block_slice_device(op, n3a, spacing, seed, first_iid, int(ix_begin), int(ix_end),
+                                             _ptr(d_pos), _ptr(d_vel), _ptr(d_iid), stream))
+    return (int(ix_end) - int(ix_begin)) * int(n3[1]) * int(n3[2])
+
+
+def scene_block_slice_host(origin, n3, ix_begin, ix_end, spacing=0.05, seed=27, first_iid=0):
+    o, op = _f3arr(origin)
+    n3a = (C.c_int32 * 3)(*[int(v) for v in n3])
+    total = (int(ix_end) - int(ix_begin)) * int(n3[1]) * int(n3[2])
+    pos = np.zeros((total, 3), np.float32)
+    vel = np.zeros((total, 3), np.float32)
+    iid = np.zeros(total, np.uint32)
+    _check(_lib.pbf_scene_block_slice_host(op, n3a, spacing, seed, first_iid, int(ix_begin), int(ix_end),
+                                           pos.ctypes.data, vel.ctypes.data, iid.ctypes.data))
+    return pos, vel, iid
 
 
 def wall_lim(ulim0, llim0, a_ulim, a_llim, w, frame, start_frame=0):

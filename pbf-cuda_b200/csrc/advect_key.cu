@@ -8,6 +8,12 @@
 // 24 B/particle of reads.
 //
 // HBM traffic: R 24 B (pos, vel) + W 4 B (key) per particle.
+//
+// Slab mode (multi-GPU, slab.cu): the caller's arrays hold [own | from left | from right]; keys are
+// written in the sort's logical order [from left | own | from right] (SlabInput), particles that
+// land outside the planes this rank stores get the discard key (one past the last local cell, so
+// the sort parks them behind everything else), and an own particle that a neighbour rank needed
+// but was not in the range sent to it raises PBF_SLAB_FLAG_MIGRATION.
 #include "pbf_math.cuh"
 
 namespace pbf {
@@ -17,7 +23,8 @@ constexpr int AK_THREADS = 256;
 __global__ void __launch_bounds__(AK_THREADS)
 advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
                   uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, int64_t n, int npass,
-                  const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+                  const __grid_constant__ SlabInput si, const __grid_constant__ GridConsts g,
+                  const __grid_constant__ SolverConsts c) {
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
     for (int k = threadIdx.x; k < npass * RADIX; k += AK_THREADS) s_hist[k] = 0;
     __syncthreads();
@@ -29,8 +36,13 @@ advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
         float3 p = load_f3(pos, i), v = load_f3(vel, i);
         float3 q = advect_pos(p, v, c);
         int3 cc = cell_of(q.x, q.y, q.z, g);
-        key = (uint32_t)cell_id(cc.x, cc.y, cc.z, g);
-        keys[i] = key;
+        const int lx = cc.x - g.xoff;
+        key = (lx >= 0 && lx < g.nxl) ? (uint32_t)cell_id(cc.x, cc.y, cc.z, g) : (uint32_t)g.ncell;
+        if (si.flags && i < si.n_own &&
+            ((cc.x < si.need_left_below && i >= si.send_left_end) ||
+             (cc.x >= si.need_right_from && i < si.send_right_begin)))
+            atomicOr(si.flags, (uint32_t)PBF_SLAB_FLAG_MIGRATION);
+        keys[slab_logical(si, i)] = key;
     }
     // warp-aggregated shared-memory histogram: particles of one block share their high digits,
     // so a plain atomicAdd per thread would serialise on one bank word.
@@ -48,11 +60,11 @@ advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
 }
 
 cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist,
-                              int64_t n, int npass, const GridConsts& g, const SolverConsts& c,
-                              cudaStream_t st, int64_t* launches) {
+                              int64_t n, int npass, const SlabInput& si, const GridConsts& g,
+                              const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     unsigned blocks = (unsigned)((n + AK_THREADS - 1) / AK_THREADS);
-    advect_key_kernel<<<blocks, AK_THREADS, 0, st>>>(pos, vel, keys, hist, n, npass, g, c);
+    advect_key_kernel<<<blocks, AK_THREADS, 0, st>>>(pos, vel, keys, hist, n, npass, si, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

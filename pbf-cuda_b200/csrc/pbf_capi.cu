@@ -4,6 +4,7 @@
 // stages in the same order; GL interop replaced by raw device pointers; the process-wide
 // GUIParams singleton replaced by a parameter block in the handle; checkCudaErrors' print+exit
 // replaced by status codes.
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -48,7 +49,7 @@ __global__ void extract_words_kernel(const uint32_t* __restrict__ src, int strid
     dst[t] = src[i * stride + offset + k];
 }
 
-enum Stage { ST_IDLE = 0, ST_BOUND, ST_ADVECTED, ST_GRID, ST_DENSITY, ST_VELOCITY, ST_XSPH };
+enum Stage { ST_IDLE = 0, ST_BOUND, ST_ADVECTED, ST_GRID, ST_LAMBDA, ST_DENSITY, ST_VELOCITY, ST_XSPH };
 
 }  // namespace
 
@@ -93,6 +94,22 @@ struct pbf_sim {
     int iters_done = 0;
     bool pos0_in_npos = false;
 
+    // x-slab decomposition (multi-GPU); off for the plain single-GPU handle
+    bool slab_on = false;
+    pbf_slab_step slab{};
+    SlabInput si{};
+    int64_t n_local = 0;      // slots the solver arrays hold this step (single GPU: n)
+    int64_t own_first = 0;    // first owned slot                        (single GPU: 0)
+    int64_t own_count = 0;    // owned particles                         (single GPU: n)
+    int32_t ghost_left = 0;   // ghost planes actually stored left of x_begin
+    int64_t* plane_dev = nullptr;
+    int64_t* plane_host = nullptr;   // pinned copy: first slot of every local plane, + total
+    int64_t plane_capacity = 0;
+    uint32_t* flags_host = nullptr;  // mapped pinned word the kernels raise PBF_SLAB_FLAG_* in
+    uint32_t* flags_dev = nullptr;
+    pbf_slab_layout layout{};
+    bool layout_valid = false;
+
     int64_t launches = 0;
     bool timing = false;
     cudaEvent_t ev[6] = {};
@@ -125,12 +142,31 @@ int refresh_consts(pbf_sim* s) {
     g.h = p.h;
     compute_dim(s->ulim, s->llim, p.h, g.dim);
     if (g.dim[0] < 1 || g.dim[1] < 1 || g.dim[2] < 1) return fail(PBF_ERR_INVALID, "empty box");
-    const int64_t ncell = (int64_t)g.dim[0] * g.dim[1] * g.dim[2];
-    if (ncell > s->cell_capacity || ncell >= ((int64_t)1 << 30))
+    // planes this handle stores: the whole grid, or in slab mode ghost | owned | ghost
+    g.xoff = 0;
+    g.nxl = g.dim[0];
+    g.flags = nullptr;
+    s->ghost_left = 0;
+    if (s->slab_on) {
+        const pbf_slab_step& sl = s->slab;
+        int lo = sl.has_left ? sl.x_begin - sl.ghost : 0;
+        int hi = sl.has_right ? sl.x_end + sl.ghost : g.dim[0];
+        if (lo < 0) lo = 0;
+        if (hi > g.dim[0]) hi = g.dim[0];
+        if (sl.x_begin < lo || sl.x_end > hi || sl.x_begin >= sl.x_end)
+            return fail(PBF_ERR_INVALID, "slab [%d, %d) does not fit the grid (%d planes)", sl.x_begin, sl.x_end, g.dim[0]);
+        g.xoff = lo;
+        g.nxl = hi - lo;
+        g.flags = s->flags_dev;
+        s->ghost_left = sl.x_begin - lo;
+    }
+    const int64_t ncell = (int64_t)g.nxl * g.dim[1] * g.dim[2];
+    if (ncell > s->cell_capacity || ncell >= ((int64_t)1 << 30) - 1)
         return fail(PBF_ERR_CAPACITY, "box has %lld cells, handle holds %lld", (long long)ncell, (long long)s->cell_capacity);
     g.ncell = (int32_t)ncell;
     g.dyz = g.dim[1] * g.dim[2];
-    s->npass = (key_bits(ncell) + RADIX_BITS - 1) / RADIX_BITS;
+    // slab mode sorts one more key value: the discard key == ncell
+    s->npass = (key_bits(ncell + (s->slab_on ? 1 : 0)) + RADIX_BITS - 1) / RADIX_BITS;
 
     // getPoly6 / getSpikyGrad constructors and h_updateVelocity, host arithmetic as in the
     // reference (Simulator.cu:77-83, 94-98, 129); M_PI there is the double literal 3.14159265359.
@@ -179,6 +215,9 @@ void free_all(pbf_sim* s) {
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
     if (s->stats_host) cudaFreeHost(s->stats_host);
+    cudaFree(s->plane_dev);
+    if (s->plane_host) cudaFreeHost(s->plane_host);
+    if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->ev_valid) {
         for (auto& e : s->ev) cudaEventDestroy(e);
         for (auto& e : s->kev) cudaEventDestroy(e);
@@ -260,6 +299,12 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     A((void**)&s->cell_range, (size_t)cap * sizeof(uint2));
     A((void**)&s->stats_partial, 1024 * 5 * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->stats_host, 1024 * 5 * sizeof(double));
+    // slab mode: plane table (every plane the box can have, x2 for a moving wall) + flag word
+    s->plane_capacity = 2 * (int64_t)dim[0] + 8;
+    A((void**)&s->plane_dev, (size_t)s->plane_capacity * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->plane_host, (size_t)s->plane_capacity * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->flags_host, sizeof(uint32_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) { *s->flags_host = 0; e = cudaHostGetDevicePointer((void**)&s->flags_dev, s->flags_host, 0); }
     if (e != cudaSuccess) {
         free_all(s);
         delete s;
@@ -357,6 +402,36 @@ static int kernel_event(pbf_sim* s, int slot, int after) {
         if ((rc__ = kernel_event(s, slot, 1))) return rc__;  \
     } while (0)
 
+// Slab mode, after the sort: where every stored plane starts in the sorted order. One small
+// kernel + a 8*(nxl+1)-byte download + the step's only host synchronisation; from the table
+// follow the owned range, the ghost counts and the sizes of every halo message.
+static int slab_learn_layout(pbf_sim* s) {
+    const GridConsts& g = s->g;
+    if (g.nxl + 1 > s->plane_capacity) return fail(PBF_ERR_CAPACITY, "slab stores %d planes, handle holds %lld", g.nxl, (long long)s->plane_capacity - 1);
+    CUDA_TRY(launch_plane_table(s->pairs[s->sorted_buf], s->n, s->plane_dev, g, s->stream, &s->launches));
+    CUDA_TRY(cudaMemcpyAsync(s->plane_host, s->plane_dev, (size_t)(g.nxl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const pbf_slab_step& sl = s->slab;
+    const int64_t* ps = s->plane_host;
+    const int gl = s->ghost_left, nx = sl.x_end - sl.x_begin;
+    const int gw_l = sl.has_left ? (sl.ghost < nx ? sl.ghost : nx) : 0;   // owned planes a neighbour mirrors
+    const int gw_r = sl.has_right ? (sl.ghost < nx ? sl.ghost : nx) : 0;
+    pbf_slab_layout& L = s->layout;
+    L.n_local = ps[g.nxl];
+    L.own_first = ps[gl];
+    L.own_count = ps[gl + nx] - ps[gl];
+    L.recv_left_count = ps[gl];
+    L.recv_right_count = ps[g.nxl] - ps[gl + nx];
+    L.send_left_count = ps[gl + gw_l] - ps[gl];
+    L.send_right_count = ps[gl + nx] - ps[gl + nx - gw_r];
+    L.flags = *s->flags_host;
+    s->n_local = L.n_local;
+    s->own_first = L.own_first;
+    s->own_count = L.own_count;
+    s->layout_valid = true;
+    return PBF_OK;
+}
+
 int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n,
                     void* stream) {
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
@@ -365,6 +440,15 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
     CUDA_TRY(cudaSetDevice(s->device));
     s->pos = pos; s->npos = npos; s->vel = vel; s->nvel = nvel; s->iid = iid; s->n = n;
     s->stream = (cudaStream_t)stream;
+    if (s->slab_on) {  // a plain step on a handle that ran slab steps before: back to the whole grid
+        s->slab_on = false;
+        int rc = refresh_consts(s);
+        if (rc) return rc;
+    }
+    s->si = SlabInput{};
+    s->si.n_own = n;
+    s->n_local = n; s->own_first = 0; s->own_count = n;
+    s->layout_valid = false;
     s->cur = 0;
     s->iters_done = 0;
     s->pos0_in_npos = false;
@@ -379,7 +463,7 @@ int pbf_stage_advect(pbf_sim* s) {
     const size_t zero_bytes = sort_scratch_zero_bytes(s->n, s->npass);
     CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, zero_bytes, s->stream));
     s->launches++;
-    KTIMED(PBF_KERNEL_ADVECT_KEY, launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_ADVECT_KEY, launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->si, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_ADVECTED;
     return stage_event(s, 1);
 }
@@ -393,24 +477,41 @@ int pbf_stage_build_grid(pbf_sim* s) {
     sc.bufs[0] = s->pairs[0];
     sc.bufs[1] = s->pairs[1];
     sc.tile_desc_words = 0;
-    KTIMED(PBF_KERNEL_SORT, launch_sort(s->keys, sc, s->n, s->npass, &s->sorted_buf, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_SORT, launch_sort(s->keys, sc, s->n, s->npass, s->si, &s->sorted_buf, s->stream, &s->launches));
+    if (s->slab_on) {
+        int rc = slab_learn_layout(s);
+        if (rc) return rc;
+    }
     KTIMED(PBF_KERNEL_REORDER, launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->npos, s->iid_sorted,
-                                              s->cell_range, s->n, s->g, s->c, s->stream, &s->launches));
+                                              s->cell_range, s->n_local, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
     s->cur = 0;
     s->pos0_in_npos = true;
     s->stage = ST_GRID;
     return stage_event(s, 2);
 }
 
-int pbf_stage_correct_density(pbf_sim* s) {
-    if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "correct_density: build_grid first");
+int pbf_stage_lambda(pbf_sim* s) {
+    if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "lambda: build_grid first");
     // (each iteration overwrites the slot: the timers report the LAST iteration of the step)
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->n, s->pairs_list, s->g, s->c, s->stream, &s->launches));
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->n, s->pairs_list, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, s->g, s->c, s->stream, &s->launches));
+    s->stage = ST_LAMBDA;
+    return PBF_OK;
+}
+
+int pbf_stage_delta_p(pbf_sim* s) {
+    if (!s || s->stage != ST_LAMBDA) return fail(PBF_ERR_STATE, "delta_p: lambda first");
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, s->g, s->c, s->stream, &s->launches));
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;
     return PBF_OK;
+}
+
+int pbf_stage_correct_density(pbf_sim* s) {
+    if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "correct_density: build_grid first");
+    int rc = pbf_stage_lambda(s);
+    if (rc) return rc;
+    return pbf_stage_delta_p(s);
 }
 
 int pbf_stage_update_velocity(pbf_sim* s) {
@@ -418,7 +519,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
     int rc = stage_event(s, 3);
     if (rc) return rc;
     // xl is dead after the last delta-p pass: reuse it for (velocity, rho)
-    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->n, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, s->c, s->stream, &s->launches));
     s->pos0_in_npos = false;
     s->stage = ST_VELOCITY;
     return stage_event(s, 4);
@@ -426,7 +527,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
 
 int pbf_stage_correct_velocity(pbf_sim* s) {
     if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
-    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->n, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
 }
@@ -475,6 +576,131 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     return PBF_OK;
 }
 
+/* ---- multi-GPU: x-slab decomposition ------------------------------------------------------ */
+
+int pbf_slab_begin(pbf_sim* s, const pbf_slab_step* st, float* pos, float* npos, float* vel, float* nvel,
+                   uint32_t* iid, void* stream) {
+    if (!s || !st) return fail(PBF_ERR_INVALID, "null argument");
+    const int64_t n_in = st->n_own + st->m_left + st->m_right;
+    if (st->n_own < 0 || st->m_left < 0 || st->m_right < 0) return fail(PBF_ERR_INVALID, "negative particle count");
+    if (st->ghost < 1) return fail(PBF_ERR_INVALID, "slab needs at least one ghost plane");
+    if ((st->has_left || st->has_right) && st->x_end - st->x_begin < st->ghost)
+        return fail(PBF_ERR_INVALID, "slab [%d, %d) is narrower than its %d ghost planes", st->x_begin, st->x_end, st->ghost);
+    if (st->send_left_end < 0 || st->send_right_begin > st->n_own || st->send_left_end > st->n_own || st->send_right_begin < 0)
+        return fail(PBF_ERR_INVALID, "send ranges outside the own particles");
+    int rc = pbf_stage_begin(s, pos, npos, vel, nvel, iid, n_in, stream);
+    if (rc) return rc;
+    s->slab_on = true;
+    s->slab = *st;
+    if ((rc = refresh_consts(s))) { s->slab_on = false; refresh_consts(s); s->stage = ST_IDLE; return rc; }
+    SlabInput& si = s->si;
+    si.n_own = st->n_own;
+    si.m_left = st->m_left;
+    si.send_left_end = st->has_left ? st->send_left_end : 0;
+    si.send_right_begin = st->has_right ? st->send_right_begin : st->n_own;
+    // what the neighbours keep of my side: their ghost planes reach `ghost` planes into my slab
+    si.need_left_below = st->has_left ? st->x_begin + st->ghost : INT32_MIN;
+    si.need_right_from = st->has_right ? st->x_end - st->ghost : INT32_MAX;
+    si.flags = s->flags_dev;
+    return PBF_OK;
+}
+
+int pbf_slab_get_layout(pbf_sim* s, pbf_slab_layout* out) {
+    if (!s || !out) return fail(PBF_ERR_INVALID, "null argument");
+    if (!s->slab_on || !s->layout_valid) return fail(PBF_ERR_STATE, "no slab layout: pbf_slab_begin .. pbf_stage_build_grid first");
+    s->layout.flags = *s->flags_host;
+    *out = s->layout;
+    return PBF_OK;
+}
+
+int pbf_slab_plane_counts(pbf_sim* s, int32_t x_first, int32_t count, int64_t* out) {
+    if (!s || !out || count < 0) return fail(PBF_ERR_INVALID, "bad argument");
+    if (!s->slab_on || !s->layout_valid) return fail(PBF_ERR_STATE, "no slab layout: pbf_slab_begin .. pbf_stage_build_grid first");
+    for (int32_t k = 0; k < count; k++) {
+        const int x = x_first + k;
+        const int lp = x - s->g.xoff;
+        out[k] = (x >= s->slab.x_begin && x < s->slab.x_end) ? s->plane_host[lp + 1] - s->plane_host[lp] : 0;
+    }
+    return PBF_OK;
+}
+
+int pbf_slab_halo(pbf_sim* s, int what, void** send_left, void** recv_left, void** send_right, void** recv_right) {
+    if (!s || !send_left || !recv_left || !send_right || !recv_right) return fail(PBF_ERR_INVALID, "null argument");
+    if (!s->slab_on || !s->layout_valid) return fail(PBF_ERR_STATE, "no slab layout: pbf_slab_begin .. pbf_stage_build_grid first");
+    float4* a = nullptr;
+    switch (what) {
+        case PBF_HALO_LAMBDA:
+            if (s->stage != ST_LAMBDA) return fail(PBF_ERR_STATE, "lambda halo: pbf_stage_lambda first");
+            a = s->xl; break;
+        case PBF_HALO_POSITION:
+            if (s->stage != ST_DENSITY && s->stage != ST_GRID) return fail(PBF_ERR_STATE, "position halo: pbf_stage_delta_p first");
+            a = s->x[s->cur]; break;
+        case PBF_HALO_VELOCITY:
+            if (s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "velocity halo: pbf_stage_update_velocity first");
+            a = s->xl; break;
+        default: return fail(PBF_ERR_INVALID, "unknown halo selector %d", what);
+    }
+    const pbf_slab_layout& L = s->layout;
+    *recv_left = a;
+    *send_left = a + L.own_first;
+    *send_right = a + L.own_first + L.own_count - L.send_right_count;
+    *recv_right = a + L.own_first + L.own_count;
+    return PBF_OK;
+}
+
+int pbf_slab_flags(pbf_sim* s, uint32_t* out) {
+    if (!s || !out) return fail(PBF_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *out = *s->flags_host;
+    *s->flags_host = 0;
+    return PBF_OK;
+}
+
+int pbf_slab_sort_state(pbf_sim* s, int32_t x_begin, int32_t x_end, int32_t has_left, int32_t has_right,
+                        float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    pbf_slab_step st{};
+    st.x_begin = x_begin; st.x_end = x_end; st.ghost = 1;
+    st.has_left = has_left; st.has_right = has_right;
+    st.n_own = n; st.send_right_begin = n;
+    int rc = pbf_slab_begin(s, &st, pos, npos, vel, nvel, iid, stream);
+    if (rc) return rc;
+    s->si.flags = nullptr;          // nothing was sent: no migration check
+    s->si.send_left_end = 0; s->si.send_right_begin = n;
+    // keys from the positions as they are: advect with dt = 0 is the identity (fma(0, v, p) == p)
+    SolverConsts c0 = s->c;
+    c0.dt = 0.f; c0.gravity = 0.f;
+    CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, sort_scratch_zero_bytes(s->n, s->npass), s->stream));
+    CUDA_TRY(launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->si, s->g, c0, s->stream, &s->launches));
+    SortScratch sc;
+    sc.hist = s->sort_zero;
+    sc.tile_counter = s->sort_zero + MAX_PASSES * RADIX;
+    sc.tile_desc = s->sort_zero + MAX_PASSES * RADIX + MAX_PASSES;
+    sc.bufs[0] = s->pairs[0];
+    sc.bufs[1] = s->pairs[1];
+    sc.tile_desc_words = 0;
+    CUDA_TRY(launch_sort(s->keys, sc, s->n, s->npass, s->si, &s->sorted_buf, s->stream, &s->launches));
+    if ((rc = slab_learn_layout(s))) return rc;
+    s->stage = ST_IDLE;
+    if (s->layout.own_count != n || s->layout.own_first != 0)
+        return fail(PBF_ERR_INVALID, "sort_state: %lld of %lld particles lie outside planes [%d, %d)",
+                    (long long)(n - s->layout.own_count), (long long)n, x_begin, x_end);
+    CUDA_TRY(launch_gather_state(s->pairs[s->sorted_buf], pos, vel, iid, npos, nvel, s->iid_sorted, n, s->stream, &s->launches));
+    CUDA_TRY(cudaMemcpyAsync(iid, s->iid_sorted, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->stream));
+    return PBF_OK;
+}
+
+int pbf_scene_block_slice_device(const float origin[3], const int32_t n[3], float spacing, uint32_t seed,
+                                 uint32_t first_iid, int32_t ix_begin, int32_t ix_end, float* d_pos,
+                                 float* d_vel, uint32_t* d_iid, void* stream) {
+    if (!origin || !n) return fail(PBF_ERR_INVALID, "null argument");
+    if (ix_begin < 0 || ix_end > n[0] || ix_begin > ix_end) return fail(PBF_ERR_INVALID, "bad layer range");
+    if (ix_end > ix_begin && (!d_pos || !d_vel || !d_iid)) return fail(PBF_ERR_INVALID, "null argument");
+    CUDA_TRY(launch_scene_block(origin, n, spacing, seed, first_iid, ix_begin, ix_end, d_pos, d_vel, d_iid, (cudaStream_t)stream));
+    return PBF_OK;
+}
+
 /* ---- read-backs --------------------------------------------------------------------------- */
 
 int pbf_read(pbf_sim* s, int what, void* dst, int64_t count) {
@@ -483,7 +709,7 @@ int pbf_read(pbf_sim* s, int what, void* dst, int64_t count) {
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (count < 0) return fail(PBF_ERR_INVALID, "negative count");
     const bool per_particle = what != PBF_READ_CELL_START && what != PBF_READ_CELL_END;
-    if (per_particle && count > s->n) return fail(PBF_ERR_INVALID, "count exceeds the bound particle count");
+    if (per_particle && count > s->n_local) return fail(PBF_ERR_INVALID, "count exceeds the bound particle count");
     if (!per_particle && count > s->g.ncell) return fail(PBF_ERR_INVALID, "count exceeds the cell count");
     if (count == 0) return PBF_OK;
     const KeyIdx* sorted = s->pairs[s->sorted_buf];
@@ -512,13 +738,15 @@ int pbf_read(pbf_sim* s, int what, void* dst, int64_t count) {
             if (s->stage != ST_DENSITY) return fail(PBF_ERR_STATE, "lambda is only valid between correct_density and update_velocity");
             return extract(s->xl, 4, 3, 1);
         case PBF_READ_RHO: return extract(s->rho, 1, 0, 1);
-        case PBF_READ_POS0: return extract(s->pos0_in_npos ? s->npos : s->pos, 3, 0, 3);
+        case PBF_READ_POS0:  // (slab mode: the owned particles only, from slot own_first on)
+            if (count > s->own_count) return fail(PBF_ERR_INVALID, "count exceeds the owned particle count");
+            return extract(s->pos0_in_npos ? s->npos : s->pos, 3, 0, 3);
         case PBF_READ_VEL:
             if (s->stage != ST_VELOCITY && s->stage != ST_XSPH) return fail(PBF_ERR_STATE, "velocity not computed yet");
             return extract(s->xl, 4, 0, 3);
         case PBF_READ_NEIGHBOR_COUNT: {
             if (!s->count_scratch) CUDA_TRY(cudaMalloc((void**)&s->count_scratch, (size_t)s->max_particles * 4));
-            CUDA_TRY(launch_neighbor_count(s->x[s->cur], s->cell_range, s->count_scratch, s->n, s->g, s->c, s->stream));
+            CUDA_TRY(launch_neighbor_count(s->x[s->cur], s->cell_range, s->count_scratch, s->n_local, s->g, s->c, s->stream));
             return extract(s->count_scratch, 1, 0, 1);
         }
         default:
@@ -532,7 +760,7 @@ int pbf_get_stats(pbf_sim* s, const float* npos, const float* nvel, int64_t n, p
     CUDA_TRY(cudaSetDevice(s->device));
     int nb = (int)((n + 255) / 256);
     if (nb > 1024) nb = 1024;
-    CUDA_TRY(launch_stats(s->rho, npos, nvel, n, s->p.pho0, s->stats_partial, nb, s->stream));
+    CUDA_TRY(launch_stats(s->rho + s->own_first, npos, nvel, n, s->p.pho0, s->stats_partial, nb, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->stats_host, s->stats_partial, (size_t)nb * 5 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     double e_sum = 0, e_max = -1e300, ke = 0, v_max = 0, z_sum = 0;
@@ -610,7 +838,7 @@ int pbf_device_sync(int device) {
 int pbf_scene_block_device(const float origin[3], const int32_t n[3], float spacing, uint32_t seed,
                            uint32_t first_iid, float* d_pos, float* d_vel, uint32_t* d_iid, void* stream) {
     if (!origin || !n || !d_pos || !d_vel || !d_iid) return fail(PBF_ERR_INVALID, "null argument");
-    CUDA_TRY(launch_scene_block(origin, n, spacing, seed, first_iid, d_pos, d_vel, d_iid, (cudaStream_t)stream));
+    CUDA_TRY(launch_scene_block(origin, n, spacing, seed, first_iid, 0, n[0], d_pos, d_vel, d_iid, (cudaStream_t)stream));
     return PBF_OK;
 }
 

@@ -15,9 +15,40 @@ struct GridConsts {
     float ulim[3];
     float h;
     int32_t dim[3];
-    int32_t ncell;
-    int32_t dyz;  // dim[1]*dim[2]
+    int32_t ncell;   // cells of the LOCAL table: nxl * dyz (== dim[0]*dyz on a single GPU)
+    int32_t dyz;     // dim[1]*dim[2]
+    // x-slab of a multi-GPU decomposition (slab.cu): this handle stores cell planes
+    // [xoff, xoff + nxl) of the global grid — the owned planes plus the ghost planes either
+    // side. Cell ids / sort keys are local: (x - xoff)*dyz + y*dim[2] + z. Single GPU: 0, dim[0].
+    int32_t xoff;
+    int32_t nxl;
+    uint32_t* flags;  // sticky PBF_SLAB_FLAG_* word (mapped host memory) in slab mode, else null
 };
+
+// How the caller's particle arrays map to the sort's input order in slab mode (slab.cu).
+// Physical layout [own (n_own) | from the left rank (m_left) | from the right rank]; logical
+// (= tie-break) order of the stable sort [from left | own | from right], which reproduces the
+// single-GPU within-cell order because every particle of the left rank preceded every own
+// particle in the previous global order. Single GPU: n_own = n, m_left = 0 (identity).
+struct SlabInput {
+    int64_t n_own;
+    int64_t m_left;
+    int64_t send_left_end;     // own slots [0, send_left_end) were sent to the left rank
+    int64_t send_right_begin;  // own slots [send_right_begin, n_own) were sent to the right rank
+    int32_t need_left_below;   // an unsent own particle landing in a plane < this was needed left
+    int32_t need_right_from;   // an unsent own particle landing in a plane >= this was needed right
+    uint32_t* flags;           // sticky PBF_SLAB_FLAG_* word (mapped host memory), or null
+};
+__host__ __device__ inline int64_t slab_logical(const SlabInput& si, int64_t phys) {
+    if (phys < si.n_own) return phys + si.m_left;
+    if (phys < si.n_own + si.m_left) return phys - si.n_own;
+    return phys;
+}
+__host__ __device__ inline int64_t slab_physical(const SlabInput& si, int64_t logical) {
+    if (logical < si.m_left) return logical + si.n_own;
+    if (logical < si.m_left + si.n_own) return logical - si.m_left;
+    return logical;
+}
 
 // Per-launch constants of the solver kernels. Host-side values are computed exactly the way
 // the reference's functor constructors compute them (Simulator.cu:77-83, 94-98, 129, 235).
@@ -58,8 +89,8 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 
 // advect + cell key + per-pass digit histograms, in input order (advect_key.cu)
 cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist,
-                              int64_t n, int npass, const GridConsts& g, const SolverConsts& c,
-                              cudaStream_t st, int64_t* launches);
+                              int64_t n, int npass, const SlabInput& si, const GridConsts& g,
+                              const SolverConsts& c, cudaStream_t st, int64_t* launches);
 
 // onesweep LSD radix sort of (key, idx) (radix_sort.cu). `keys` is consumed by pass 0 with the
 // implicit index; result ends in bufs[result_buf].
@@ -70,15 +101,17 @@ struct SortScratch {
     KeyIdx* bufs[2];
     int64_t tile_desc_words; // capacity per pass
 };
-cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, int* result_buf,
-                        cudaStream_t st, int64_t* launches);
+cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, const SlabInput& si,
+                        int* result_buf, cudaStream_t st, int64_t* launches);
 size_t sort_scratch_zero_bytes(int64_t n, int npass);
 
 // gather the payload into sorted SoA + cell ranges (reorder.cu)
+// `n` slots are gathered (slab mode: ghosts included); pos0_out is written for the owned slots
+// [own_first, own_first + own_count) only, at slot - own_first.
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                            float4* x0, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
-                           int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                           int64_t* launches);
+                           int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
+                           const SolverConsts& c, cudaStream_t st, int64_t* launches);
 
 // solver passes (solver.cu)
 // Neighbour list the lambda pass saves for the delta-p pass of the same iteration (null = off).
@@ -88,26 +121,39 @@ struct PairList {
     uint32_t* cnt = nullptr;  // per particle: number of entries, or the overflow flag
 };
 size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_bytes, size_t* cnt_bytes);
-cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t n,
-                          const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                          int64_t* launches);
-cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t n,
+// The passes compute slots [first, first + n) (slab mode: the owned slots; single GPU: 0, n) and
+// read neighbours from every slot. Internal arrays (x, xl, rho, v4, iid_sorted) are indexed by
+// slot; caller-facing arrays (pos/npos/vel/nvel/iid) and the pair list by slot - first.
+cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t first,
+                          int64_t n, const PairList& pl, const GridConsts& g, const SolverConsts& c,
+                          cudaStream_t st, int64_t* launches);
+cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t first, int64_t n,
                            const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
                            int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
-                                   float* vel_out, float4* v4, int64_t n, const SolverConsts& c,
-                                   cudaStream_t st, int64_t* launches);
+                                   float* vel_out, float4* v4, int64_t first, int64_t n,
+                                   const SolverConsts& c, cudaStream_t st, int64_t* launches);
 cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,
-                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t n, const GridConsts& g,
-                        const SolverConsts& c, cudaStream_t st, int64_t* launches);
+                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n,
+                        const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+// slab.cu: first slot of every local plane in the sorted pairs (nxl + 1 entries, the last one =
+// number of particles inside the local plane range; the rest carry the discard key)
+cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,
+                               cudaStream_t st, int64_t* launches);
+// slab.cu: npos/nvel/iid_out[s] = pos/vel/iid[sorted[s].idx] (state sort without a step)
+cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
+                                float* npos, float* nvel, uint32_t* iid_out, int64_t n, cudaStream_t st,
+                                int64_t* launches);
 cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
                                   const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 
 // scene + stats (scene.cu, stats.cu)
 cudaError_t launch_scene_block(const float origin[3], const int32_t n3[3], float spacing, uint32_t seed,
-                               uint32_t first_iid, float* pos, float* vel, uint32_t* iid, cudaStream_t st);
+                               uint32_t first_iid, int32_t ix_begin, int32_t ix_end, float* pos, float* vel,
+                               uint32_t* iid, cudaStream_t st);
 void scene_block_host(const float origin[3], const int32_t n3[3], float spacing, uint32_t seed,
-                      uint32_t first_iid, float* pos, float* vel, uint32_t* iid);
+                      uint32_t first_iid, int32_t ix_begin, int32_t ix_end, float* pos, float* vel,
+                      uint32_t* iid);
 cudaError_t launch_stats(const float* rho, const float* npos, const float* nvel, int64_t n, float pho0,
                          double* partial, int nblocks, cudaStream_t st);
 

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__ pairs_in,
                 KeyIdx* __restrict__ out, const uint32_t* __restrict__ hist_excl,
                 uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ tile_desc, int64_t n,
-                int shift) {
+                int shift, const __grid_constant__ SlabInput si) {
     __shared__ KeyIdx s_pairs[SORT_TILE];
     __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];
     __shared__ uint32_t s_digit_start[RADIX];
@@ -95,7 +95,8 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
         if (local < tile_n) {
             if (FIRST) {
                 item[k].key = keys_in[tile_base + local];
-                item[k].idx = (uint32_t)(tile_base + local);
+                // the keys are in the sort's logical order; the index names the caller's slot
+                item[k].idx = (uint32_t)slab_physical(si, tile_base + local);
             } else {
                 item[k] = pairs_in[tile_base + local];
             }
@@ -201,8 +202,8 @@ size_t sort_scratch_zero_bytes(int64_t n, int npass) {
     return sizeof(uint32_t) * ((size_t)MAX_PASSES * RADIX + MAX_PASSES + (size_t)npass * tiles * RADIX);
 }
 
-cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, int* result_buf,
-                        cudaStream_t st, int64_t* launches) {
+cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, const SlabInput& si,
+                        int* result_buf, cudaStream_t st, int64_t* launches) {
     if (n <= 0) { *result_buf = 0; return cudaSuccess; }
     const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
     hist_scan_kernel<<<npass, RADIX, 0, st>>>(s.hist);
@@ -211,9 +212,9 @@ cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npa
         uint32_t* desc = s.tile_desc + (size_t)p * tiles * RADIX;
         const uint32_t* h = s.hist + p * RADIX;
         if (p == 0)
-            onesweep_kernel<true><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS);
+            onesweep_kernel<true><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
         else
-            onesweep_kernel<false><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS);
+            onesweep_kernel<false><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
         if (launches) (*launches)++;
     }
     *result_buf = (npass - 1) & 1;

@@ -11,6 +11,10 @@
 // The advected position is recomputed with the same two fma as in advect_key.cu, so the key the
 // particle was sorted by is exactly the cell of x0[s].
 //
+// Slab mode: all `n` slots this rank stores are gathered (ghost planes included: a ghost's advected
+// position is recomputed here from the raw state the owner sent, bit-identical to the owner's);
+// pos0 is parked for the owned slots only.
+//
 // HBM traffic: R 8 (pair) + 28 (gathered pos, vel, iid; near-sequential because the input is
 // last step's sorted order) ; W 16 + 12 + 4 per particle, + 8 B per occupied cell.
 #include "pbf_math.cuh"
@@ -23,8 +27,8 @@ __global__ void __launch_bounds__(RO_THREADS)
 reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
                const float* __restrict__ vel, const uint32_t* __restrict__ iid,
                float4* __restrict__ x0, float* __restrict__ pos0_out, uint32_t* __restrict__ iid_sorted,
-               uint2* __restrict__ cell_range, int64_t n, const __grid_constant__ GridConsts g,
-               const __grid_constant__ SolverConsts c) {
+               uint2* __restrict__ cell_range, int64_t n, int64_t own_first, int64_t own_count,
+               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     const int64_t s = (int64_t)blockIdx.x * RO_THREADS + threadIdx.x;
     if (s >= n) return;
     const KeyIdx e = sorted[s];
@@ -32,7 +36,7 @@ reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
     const float3 p = load_f3(pos, e.idx), v = load_f3(vel, e.idx);
     const float3 q = advect_pos(p, v, c);
     x0[s] = make_float4(q.x, q.y, q.z, 0.f);
-    store_f3(pos0_out, s, p.x, p.y, p.z);
+    if (s >= own_first && s - own_first < own_count) store_f3(pos0_out, s - own_first, p.x, p.y, p.z);
     iid_sorted[s] = iid[e.idx];
     // Green-style range detection (reference computeGridRange)
     if (e.key != prev) {
@@ -44,14 +48,14 @@ reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
 
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                            float4* x0, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
-                           int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                           int64_t* launches) {
+                           int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
+                           const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     cudaError_t e = cudaMemsetAsync(cell_range, 0, sizeof(uint2) * (size_t)g.ncell, st);
     if (e != cudaSuccess) return e;
     if (launches) (*launches)++;
     if (n <= 0) return cudaSuccess;
     unsigned blocks = (unsigned)((n + RO_THREADS - 1) / RO_THREADS);
-    reorder_kernel<<<blocks, RO_THREADS, 0, st>>>(sorted, pos, vel, iid, x0, pos0_out, iid_sorted, cell_range, n, g, c);
+    reorder_kernel<<<blocks, RO_THREADS, 0, st>>>(sorted, pos, vel, iid, x0, pos0_out, iid_sorted, cell_range, n, own_first, own_count, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

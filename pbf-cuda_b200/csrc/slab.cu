@@ -1,0 +1,65 @@
+// slab.cu — device helpers of the multi-GPU x-slab decomposition (the reference is
+// single-GPU, so there is no reference code for this file — what it must preserve is the
+// reference's RESULT: every rank reproduces, for the particles it owns, the bits the single-GPU
+// step produces for them).
+//
+// Why x-slabs are plain ranges here: the sort key is the reference's x-major cell id
+// (Simulator.cu:45-53), so in the sorted arrays every cell plane x = const is one contiguous slot
+// range. A rank stores planes [xoff, xoff + nxl) = ghost | owned | ghost; after its local stable
+// sort the ghost particles sit at the two ends, the planes a neighbour needs as ITS ghosts are a
+// prefix / suffix of the owned range, and every halo refresh (lambda, positions, velocity+rho)
+// is a copy of one contiguous float4 range straight out of / into the solver's own arrays.
+#include "pbf_internal.h"
+
+namespace pbf {
+
+namespace {
+
+// plane_start[p] = first sorted slot whose key is >= p*dyz, p = 0..nxl. Keys ascend; the discard
+// key (== ncell == nxl*dyz) is behind every local cell, so plane_start[nxl] = particles kept.
+__global__ void plane_table_kernel(const KeyIdx* __restrict__ sorted, int64_t n,
+                                   int64_t* __restrict__ plane_start, int nxl, int dyz) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > nxl) return;
+    const uint32_t want = (uint32_t)p * (uint32_t)dyz;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted[mid].key < want) lo = mid + 1; else hi = mid;
+    }
+    plane_start[p] = lo;
+}
+
+__global__ void __launch_bounds__(256)
+gather_state_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
+                    const float* __restrict__ vel, const uint32_t* __restrict__ iid,
+                    float* __restrict__ npos, float* __restrict__ nvel, uint32_t* __restrict__ iid_out,
+                    int64_t n) {
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t j = sorted[s].idx;
+    npos[3 * s] = pos[3 * (int64_t)j]; npos[3 * s + 1] = pos[3 * (int64_t)j + 1]; npos[3 * s + 2] = pos[3 * (int64_t)j + 2];
+    nvel[3 * s] = vel[3 * (int64_t)j]; nvel[3 * s + 1] = vel[3 * (int64_t)j + 1]; nvel[3 * s + 2] = vel[3 * (int64_t)j + 2];
+    iid_out[s] = iid[j];
+}
+
+}  // namespace
+
+cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,
+                               cudaStream_t st, int64_t* launches) {
+    const int threads = 128;
+    plane_table_kernel<<<(g.nxl + 1 + threads - 1) / threads, threads, 0, st>>>(sorted, n, plane_start, g.nxl, g.dyz);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
+                                float* npos, float* nvel, uint32_t* iid_out, int64_t n, cudaStream_t st,
+                                int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    gather_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted, pos, vel, iid, npos, nvel, iid_out, n);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace pbf

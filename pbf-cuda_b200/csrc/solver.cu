@@ -65,8 +65,13 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
 #pragma unroll 1
     for (int dx = -1; dx <= 1; dx++) {
         const int cx = cc.x + dx;
+        const int lx = cx - g.xoff;  // plane in this handle's table (slab mode; lx == cx on one GPU)
         uint32_t base = 0xffffffffu;
-        if (cx >= 0 && cx < g.dim[0]) {
+        if (cx >= 0 && cx < g.dim[0] && (lx < 0 || lx >= g.nxl)) {
+            // the particle drifted so far from its stored cell that its search leaves the ghost
+            // planes: the result would silently miss neighbours, so say so
+            if (g.flags) atomicOr(g.flags, (uint32_t)PBF_SLAB_FLAG_GHOST);
+        } else if (cx >= 0 && cx < g.dim[0]) {
             uint16_t* tail = my_list;  // next free entry of this thread's list
             auto flush = [&]() {
 #pragma unroll 2
@@ -89,7 +94,7 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             for (int dy = -1; dy <= 1; dy++) {
                 const int cy = cc.y + dy;
                 if (cy < 0 || cy >= g.dim[1]) continue;
-                const int cbase = cx * g.dyz + cy * g.dim[2];
+                const int cbase = lx * g.dyz + cy * g.dim[2];
                 uint32_t start = 0, end = 0;
                 bool any = false;
                 for (int z = zlo; z <= zhi; z++) {
@@ -141,12 +146,13 @@ constexpr uint32_t PAIR_OVERFLOW = 1u << 31;
 template <bool EXACT_POW, bool SAVE_PAIRS>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __restrict__ rho_out,
-              const uint2* __restrict__ cell_range, int64_t n, uint32_t* __restrict__ pair_idx,
-              float2* __restrict__ pair_sw, uint32_t* __restrict__ pair_cnt,
+              const uint2* __restrict__ cell_range, int64_t first, int64_t n,
+              uint32_t* __restrict__ pair_idx, float2* __restrict__ pair_sw, uint32_t* __restrict__ pair_cnt,
               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
-    const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
-    if (i >= n) return;
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (t >= n) return;
+    const int64_t i = first + t;
     const float4 p = x[i];
     float rho = 0.f, gradj_l2 = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
     // the particle itself: r2 = 0 adds poly6(0) to rho at its place in the visiting order and
@@ -196,7 +202,7 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
     const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
     xl[i] = make_float4(p.x, p.y, p.z, lambda);
     rho_out[i] = rho;
-    if (SAVE_PAIRS) pair_cnt[i] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
+    if (SAVE_PAIRS) pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
 }
 
 // shared tail of the delta-p pass: divide, clamp to MAX_DP, add, clamp to the box (f64 like the reference)
@@ -214,17 +220,19 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
 template <bool EXACT_POW, bool USE_PAIRS>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
-               const uint2* __restrict__ cell_range, int64_t n, const uint32_t* __restrict__ pair_idx,
-               const float2* __restrict__ pair_sw, const uint32_t* __restrict__ pair_cnt,
-               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
+               const uint32_t* __restrict__ pair_idx, const float2* __restrict__ pair_sw,
+               const uint32_t* __restrict__ pair_cnt, const __grid_constant__ GridConsts g,
+               const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
-    const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
-    if (i >= n) return;
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (t >= n) return;
+    const int64_t i = first + t;
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     bool replayed = false;
     if (USE_PAIRS) {
-        const uint32_t cnt = pair_cnt[i];
+        const uint32_t cnt = pair_cnt[t];
         if (!(cnt & PAIR_OVERFLOW)) {
             replayed = true;
             const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
@@ -268,29 +276,31 @@ delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
 __global__ void __launch_bounds__(256)
 update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ rho,
                        float* __restrict__ pos_out, float* __restrict__ npos_io,
-                       float* __restrict__ vel_out, float4* __restrict__ v4, int64_t n,
+                       float* __restrict__ vel_out, float4* __restrict__ v4, int64_t first, int64_t n,
                        const __grid_constant__ SolverConsts c) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= n) return;
+    const int64_t i = first + t;
     const float4 q = x[i];
-    const float3 p0 = load_f3(npos_io, i);
+    const float3 p0 = load_f3(npos_io, t);
     const float vx = __fmul_rn(__fsub_rn(q.x, p0.x), c.inv_dt);
     const float vy = __fmul_rn(__fsub_rn(q.y, p0.y), c.inv_dt);
     const float vz = __fmul_rn(__fsub_rn(q.z, p0.z), c.inv_dt);
     v4[i] = make_float4(vx, vy, vz, rho[i]);
-    store_f3(vel_out, i, vx, vy, vz);
-    store_f3(pos_out, i, p0.x, p0.y, p0.z);
-    store_f3(npos_io, i, q.x, q.y, q.z);
+    store_f3(vel_out, t, vx, vy, vz);
+    store_f3(pos_out, t, p0.x, p0.y, p0.z);
+    store_f3(npos_io, t, q.x, q.y, q.z);
 }
 
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
-            const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t n,
+            const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
             const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
-    const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
-    if (i >= n) return;
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (t >= n) return;
+    const int64_t i = first + t;
     const float4 p = x[i];
     const float4 vi = v4[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
@@ -304,8 +314,8 @@ xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
         ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
         az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
     }, NoHooks());
-    store_f3(nvel_out, i, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
-    iid_out[i] = iid_sorted[i];
+    store_f3(nvel_out, t, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
+    iid_out[t] = iid_sorted[i];
 }
 
 __global__ void __launch_bounds__(GATHER_THREADS)
@@ -330,53 +340,53 @@ size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_byte
     return *idx_bytes + *sw_bytes + *cnt_bytes;
 }
 
-cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t n,
-                          const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                          int64_t* launches) {
+cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t first,
+                          int64_t n, const PairList& pl, const GridConsts& g, const SolverConsts& c,
+                          cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     const bool exact = c.exact_pow || c.n_corr != 4.0f;
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (!pl.idx)
-        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, nullptr, nullptr, nullptr, g, c);
+        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, g, c);
     else if (exact)
-        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
+        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
     else
-        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
+        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
-cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t n,
+cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t first, int64_t n,
                            const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
                            int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     const bool exact = c.exact_pow || c.n_corr != 4.0f;
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (pl.idx) {
-        if (exact) delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
-        else delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, pl.idx, pl.sw, pl.cnt, g, c);
+        if (exact) delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
+        else delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
     } else {
-        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, nullptr, nullptr, nullptr, g, c);
-        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, n, nullptr, nullptr, nullptr, g, c);
+        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, g, c);
+        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, g, c);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
-                                   float* vel_out, float4* v4, int64_t n, const SolverConsts& c,
-                                   cudaStream_t st, int64_t* launches) {
+                                   float* vel_out, float4* v4, int64_t first, int64_t n,
+                                   const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    update_velocity_kernel<<<nblocks(n, 256), 256, 0, st>>>(x, rho, pos_out, npos_io, vel_out, v4, n, c);
+    update_velocity_kernel<<<nblocks(n, 256), 256, 0, st>>>(x, rho, pos_out, npos_io, vel_out, v4, first, n, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,
-                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t n, const GridConsts& g,
-                        const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n,
+                        const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, v4, cell_range, nvel_out, iid_sorted, iid_out, n, g, c);
+    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -1,0 +1,426 @@
+"""slab.py — one scene on G GPUs: the x-slab decomposition of the PBF step.
+
+The reference is single-GPU (one `Simulator`, fluids/Simulator.h:7-61); this module is what makes G
+`Simulator` handles on G devices advance ONE scene so that every particle receives exactly the bits the
+single-GPU `pbf_step` gives it (tests/test_slab_*.py). One process per GPU; the transport is
+`torch.distributed` (NCCL send/recv over NVLink on the GPU box, gloo in the CPU tests); the per-rank work
+is the library's slab entry points (include/pbf.h "multi-GPU"). Three layers:
+
+  Planner        where the slab boundaries are (particle-count quantiles over cell planes), replicated:
+                 every rank holds every rank's per-plane particle counts (one small all-gather per step)
+                 and computes the same plan and the same message sizes — no size handshake on the wire.
+  SlabSimulator  the step protocol: raw-state exchange of the planes around each boundary, one local
+                 stable sort, then per Jacobi iteration a lambda halo and a position halo, a velocity
+                 halo before XSPH — each halo one contiguous float4 range per side.
+  engine         the per-rank compute behind the protocol: `GpuEngine` (libpbf_b200.so through the C-ABI;
+                 the product) — the CPU tests plug the oracle in instead (tests/_slab_cpu.py) to check the
+                 protocol itself at world_size 2 over gloo.
+
+Why the result is bit-identical to one GPU: keys are x-major (reference Simulator.cu:45-53), so a rank's
+planes are contiguous slot ranges; the within-cell order of the single-GPU stable sort is the previous
+global order, and a rank sorts [from left | own | from right], which IS the previous global order
+restricted to the particles it sees; ghosts are exact copies refreshed from their owner after every pass.
+"""
+import numpy as np
+
+from . import HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY, SLAB_FLAG_GHOST, SLAB_FLAG_MIGRATION, SlabStep
+
+
+class SlabError(RuntimeError):
+    pass
+
+
+# ---------------------------------------------------------------------------------------------------
+# planning (pure host logic, identical on every rank)
+# ---------------------------------------------------------------------------------------------------
+
+def plan_boundaries(plane_totals, world, min_width, old=None, reach=None):
+    """Slab boundaries b[0..world] (b[0] = 0, b[world] = planes) cutting `plane_totals` at particle-count
+    quantiles, every slab at least `min_width` planes wide. With `old` boundaries and a `reach`, boundary r
+    stays inside [old[r-1] + reach, old[r+1] - reach] so that everything a rank needs next step is held by
+    itself or an adjacent rank; returns `old` unchanged if that cannot be met."""
+    t = np.asarray(plane_totals, np.int64)
+    planes = len(t)
+    if world * min_width > planes:
+        raise SlabError("%d planes cannot hold %d slabs of >= %d planes" % (planes, world, min_width))
+    cum = np.concatenate([[0], np.cumsum(t)])
+    total = int(cum[-1])
+    b = [0]
+    for r in range(1, world):
+        target = total * r / world
+        x = int(np.searchsorted(cum, target, side="left"))
+        # the plane boundary closest to the quantile
+        if x > 0 and abs(cum[x - 1] - target) <= abs(cum[min(x, planes)] - target):
+            x -= 1
+        b.append(x)
+    b.append(planes)
+    lo = [0] + [r * min_width for r in range(1, world)] + [planes]
+    hi = [0] + [planes - (world - r) * min_width for r in range(1, world)] + [planes]
+    if old is not None and reach is not None:
+        for r in range(1, world):
+            lo[r] = max(lo[r], old[r - 1] + reach)
+            hi[r] = min(hi[r], old[r + 1] - reach)
+    for r in range(1, world):            # forward: clamp and keep the minimum width
+        b[r] = min(max(b[r], lo[r], b[r - 1] + min_width), hi[r])
+    for r in range(world - 1, 0, -1):    # backward
+        b[r] = max(min(b[r], b[r + 1] - min_width), lo[r])
+    ok = all(b[r + 1] - b[r] >= min_width for r in range(world)) and all(lo[r] <= b[r] <= hi[r] for r in range(1, world))
+    if not ok:
+        if old is not None:
+            return list(old)
+        raise SlabError("no valid slab plan for %d ranks over %d planes" % (world, planes))
+    return b
+
+
+def exchange_plan(counts, old, new, rank, reach):
+    """What rank `rank` sends and receives in the raw-state exchange. counts[r][x] = particles rank r owns in
+    plane x (previous step); old/new = boundaries of the previous / this step; reach = ghost + margin planes.
+    Returns dict(send_left_end, send_right_begin, m_left, m_right) in own-slot units. Every rank evaluates
+    the same formulas on the same replicated table, so sender and receiver agree without a handshake."""
+    world = len(old) - 1
+    own = counts[rank]
+    off = np.concatenate([[0], np.cumsum(own)])   # off[x] = first own slot of plane x
+
+    def clip(x, lo, hi):
+        return min(max(x, lo), hi)
+
+    n_own = int(off[-1])
+    send_left_end, send_right_begin, m_left, m_right = 0, n_own, 0, 0
+    if rank > 0:
+        # the left rank will store planes up to new[rank] + ghost; its particles come from <= margin further
+        send_left_end = int(off[clip(new[rank] + reach, old[rank], old[rank + 1])])
+        first = clip(new[rank] - reach, old[rank - 1], old[rank])
+        m_left = int(np.sum(counts[rank - 1][first:old[rank]]))
+        if new[rank] - reach < old[rank - 1]:
+            raise SlabError("plan moves boundary %d beyond the left neighbour's slab" % rank)
+    if rank < world - 1:
+        send_right_begin = int(off[clip(new[rank + 1] - reach, old[rank], old[rank + 1])])
+        last = clip(new[rank + 1] + reach, old[rank + 1], old[rank + 2])
+        m_right = int(np.sum(counts[rank + 1][old[rank + 1]:last]))
+        if new[rank + 1] + reach > old[rank + 2]:
+            raise SlabError("plan moves boundary %d beyond the right neighbour's slab" % (rank + 1))
+    return dict(send_left_end=send_left_end, send_right_begin=send_right_begin, m_left=m_left, m_right=m_right)
+
+
+# ---------------------------------------------------------------------------------------------------
+# transport
+# ---------------------------------------------------------------------------------------------------
+
+class TorchComm:
+    """Neighbour exchange + small all-gather over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, dist, device=None, group=None):
+        self.dist, self.device, self.group = dist, device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def exchange(self, sends, recvs):
+        """sends / recvs: {peer: [tensor, ...]} (empty tensors are skipped on both sides)."""
+        ops = []
+        for peer in sorted(set(sends) | set(recvs)):
+            for t in sends.get(peer, ()):
+                if t.numel():
+                    ops.append(self.dist.P2POp(self.dist.isend, t, peer, self.group))
+            for t in recvs.get(peer, ()):
+                if t.numel():
+                    ops.append(self.dist.P2POp(self.dist.irecv, t, peer, self.group))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def allgather_counts(self, counts):
+        import torch
+        mine = torch.from_numpy(np.ascontiguousarray(counts, np.int64))
+        if self.device is not None:
+            mine = mine.to(self.device)
+        out = torch.empty(self.world * mine.numel(), dtype=torch.int64, device=mine.device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.cpu().numpy().reshape(self.world, -1)
+
+
+class SingleComm:
+    """world == 1: nothing to exchange (the slab code path on one rank, for tests and N=1 runs)."""
+    rank, world = 0, 1
+
+    def exchange(self, sends, recvs):
+        assert not any(t.numel() for ts in sends.values() for t in ts)
+
+    def allgather_counts(self, counts):
+        return np.asarray(counts, np.int64)[None, :]
+
+
+class ThreadComm:
+    """`world` ranks as threads of ONE process sharing one device: the same protocol with in-process
+    mailboxes. Lets the one-GPU test box run the multi-rank path bit for bit (tests/test_slab_gpu.py)."""
+
+    class Hub:
+        def __init__(self, world):
+            import queue
+            import threading
+            self.world = world
+            self.box = {(a, b): queue.Queue() for a in range(world) for b in range(world)}
+            self.barrier = threading.Barrier(world)
+            self.gather = [None] * world
+            self.failed = threading.Event()   # a rank died: the others stop waiting for its messages
+
+        def abort(self):
+            self.failed.set()
+            self.barrier.abort()
+
+    def __init__(self, hub, rank):
+        self.hub, self.rank, self.world = hub, rank, hub.world
+
+    def exchange(self, sends, recvs):
+        for peer in sorted(sends):
+            for t in sends[peer]:
+                if t.numel():
+                    self.hub.box[(self.rank, peer)].put(t.clone())
+        for peer in sorted(recvs):
+            for t in recvs[peer]:
+                if t.numel():
+                    t.copy_(self._get(self.hub.box[(peer, self.rank)]))
+
+    def _get(self, box):
+        import queue
+        for _ in range(1200):
+            try:
+                return box.get(timeout=0.1)
+            except queue.Empty:
+                if self.hub.failed.is_set():
+                    raise SlabError("a peer rank failed")
+        raise SlabError("timed out waiting for a peer rank")
+
+    def allgather_counts(self, counts):
+        self.hub.gather[self.rank] = np.asarray(counts, np.int64).copy()
+        self.hub.barrier.wait(timeout=120)
+        out = np.stack(self.hub.gather)
+        self.hub.barrier.wait(timeout=120)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# the product's engine: libpbf_b200.so through the C-ABI
+# ---------------------------------------------------------------------------------------------------
+
+class _DevView:
+    """Zero-copy torch view of a library-owned device range (CUDA array interface)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class GpuEngine:
+    """Per-rank compute of the slab protocol on one GPU. Owns the five caller-side particle arrays
+    (capacity = max particles this rank may hold incl. received and ghost particles)."""
+
+    def __init__(self, pbf, params, ulim, llim, capacity, device_index=0, stream=None):
+        import torch
+        self.torch, self.pbf = torch, pbf
+        self.dev = torch.device("cuda", device_index)
+        self.capacity = int(capacity)
+        self.sim = pbf.Simulator(params, ulim, llim, self.capacity, device=device_index)
+        self.stream = stream
+        f3 = lambda: torch.zeros((self.capacity, 3), dtype=torch.float32, device=self.dev)
+        self.pos, self.npos, self.vel, self.nvel = f3(), f3(), f3(), f3()
+        self.iid = torch.zeros(self.capacity, dtype=torch.int32, device=self.dev)
+        self.n_own = 0
+        self.layout = None
+        self.planes = self.sim.grid_dim()[0]
+
+    # -- state
+    def load_state(self, pos, vel, iid, x_begin, x_end, has_left, has_right):
+        """Adopt `n` particles (device tensors, any order, all inside the owned planes) and cell-sort them."""
+        n = int(iid.shape[0])
+        if n > self.capacity:
+            raise SlabError("rank holds %d particles, capacity %d" % (n, self.capacity))
+        self.pos[:n].copy_(pos); self.vel[:n].copy_(vel); self.iid[:n].copy_(iid)
+        self.sim.slab_sort_state(x_begin, x_end, has_left, has_right, self.pos, self.npos, self.vel, self.nvel,
+                                 self.iid, n, self.stream)
+        self._swap()
+        self.n_own = n
+
+    def _swap(self):
+        self.pos, self.npos = self.npos, self.pos
+        self.vel, self.nvel = self.nvel, self.vel
+
+    def plane_counts(self):
+        return self.sim.slab_plane_counts(0, self.planes)
+
+    def raw_views(self, lo, hi):
+        return [self.pos[lo:hi], self.vel[lo:hi], self.iid[lo:hi]]
+
+    # -- the step
+    def begin(self, step):
+        n_in = step.n_own + step.m_left + step.m_right
+        if n_in > self.capacity:
+            raise SlabError("rank would hold %d particles, capacity %d" % (n_in, self.capacity))
+        self.sim.slab_begin(step, self.pos, self.npos, self.vel, self.nvel, self.iid, self.stream)
+
+    def grid(self):
+        self.sim.advect()
+        self.sim.buildGridHash()
+        self.layout = self.sim.slab_layout()
+        return self.layout
+
+    def lambda_pass(self): self.sim.computeLambda()
+    def delta_p_pass(self): self.sim.computeDeltaP()
+    def update_velocity(self): self.sim.updateVelocity()
+    def xsph(self): self.sim.correctVelocity()
+
+    def halo(self, what):
+        """([send_left], [recv_left], [send_right], [recv_right]) tensors viewing the solver's arrays."""
+        L = self.layout
+        ptrs = self.sim.slab_halo(what)
+        cnts = (L.send_left_count, L.recv_left_count, L.send_right_count, L.recv_right_count)
+        out = []
+        for p, c in zip(ptrs, cnts):
+            if c > 0:
+                out.append([self.torch.as_tensor(_DevView(p, (int(c), 4)), device=self.dev)])
+            else:
+                out.append([])
+        return out
+
+    def end(self):
+        self.sim.end()
+        self._swap()
+        self.n_own = int(self.layout.own_count)
+        return self.n_own
+
+    def flags(self):
+        return self.sim.slab_flags()
+
+    def state(self):
+        """(pos, vel, iid) of the owned particles after the last step (device tensors, views)."""
+        n = self.n_own
+        return self.pos[:n], self.vel[:n], self.iid[:n]
+
+    def close(self):
+        self.sim.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the protocol
+# ---------------------------------------------------------------------------------------------------
+
+class SlabSimulator:
+    """One rank of a G-rank run. `engine` does the rank's compute, `comm` moves the bytes.
+
+    ghost   ghost planes either side (2: a particle may drift one cell from its stored cell during the
+            Jacobi iterations — the reference re-derives the home cell from the current iterate,
+            Simulator_kernel.cuh:70,148,212 — and still find all 27 cells; violations raise)
+    margin  planes a particle may travel between two sorts (advection + drift); the raw-state exchange
+            covers ghost + margin planes either side of a boundary; violations raise
+    replan_every  re-cut the slabs at particle-count quantiles every k steps (0: keep the first plan)
+    """
+
+    def __init__(self, engine, comm, niter, planes, ghost=2, margin=4, replan_every=0):
+        self.e, self.c = engine, comm
+        self.rank, self.world = comm.rank, comm.world
+        self.niter, self.planes = int(niter), int(planes)
+        self.ghost, self.margin, self.reach = int(ghost), int(margin), int(ghost) + int(margin)
+        self.min_width = 2 * self.reach
+        self.replan_every = int(replan_every)
+        self.bounds = None
+        self.counts = None
+        self.steps = 0
+        self.messages = 0
+        self.bytes_sent = 0
+
+    # -- start-up
+    def plan_initial(self, plane_totals):
+        self.bounds = plan_boundaries(plane_totals, self.world, self.min_width if self.world > 1 else 1)
+        return self.bounds
+
+    def my_planes(self):
+        return self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    def load_owned(self, pos, vel, iid):
+        """pos/vel/iid: this rank's particles (all inside my_planes()), in the GLOBAL input order."""
+        x0, x1 = self.my_planes()
+        self.e.load_state(pos, vel, iid, x0, x1, self.rank > 0, self.rank < self.world - 1)
+        self.counts = self.c.allgather_counts(self.e.plane_counts())
+
+    # -- one step
+    def _xchg(self, left_send, left_recv, right_send, right_recv):
+        sends, recvs = {}, {}
+        if self.rank > 0:
+            sends[self.rank - 1], recvs[self.rank - 1] = left_send, left_recv
+        if self.rank < self.world - 1:
+            sends[self.rank + 1], recvs[self.rank + 1] = right_send, right_recv
+        for ts in sends.values():
+            for t in ts:
+                if t.numel():
+                    self.messages += 1
+                    self.bytes_sent += t.numel() * t.element_size()
+        self.c.exchange(sends, recvs)
+
+    def step(self):
+        e, r, w = self.e, self.rank, self.world
+        old = self.bounds
+        new = old
+        if self.replan_every and self.steps and self.steps % self.replan_every == 0 and w > 1:
+            new = plan_boundaries(self.counts.sum(axis=0), w, self.min_width, old=old, reach=self.reach)
+        xp = exchange_plan(self.counts, old, new, r, self.reach)
+        n_own = e.n_own
+        assert n_own == int(self.counts[r].sum())
+        m_l, m_r = xp["m_left"], xp["m_right"]
+        # 1. raw state of the planes around each boundary
+        self._xchg(e.raw_views(0, xp["send_left_end"]), e.raw_views(n_own, n_own + m_l),
+                   e.raw_views(xp["send_right_begin"], n_own), e.raw_views(n_own + m_l, n_own + m_l + m_r))
+        st = SlabStep(x_begin=new[r], x_end=new[r + 1], ghost=self.ghost, has_left=int(r > 0), has_right=int(r < w - 1),
+                      n_own=n_own, m_left=m_l, m_right=m_r, send_left_end=xp["send_left_end"],
+                      send_right_begin=xp["send_right_begin"])
+        # 2. keys, one stable sort, layout (the step's one host synchronisation). While the device is
+        #    still idle from it, replicate the new per-plane counts: they size the next step's messages
+        #    and feed the planner, and fetching them here keeps the END of the step free of any sync, so
+        #    the host runs ahead into the next step while the device works through the passes below.
+        e.begin(st)
+        lay = e.grid()
+        self.counts = self.c.allgather_counts(e.plane_counts())
+        self._raise_flags(lay.flags)
+        # 3. Jacobi iterations with ghost refreshes
+        for _ in range(self.niter):
+            e.lambda_pass()
+            self._halo(HALO_LAMBDA)
+            e.delta_p_pass()
+            self._halo(HALO_POSITION)
+        e.update_velocity()
+        self._halo(HALO_VELOCITY)
+        e.xsph()
+        e.end()
+        self.bounds = new
+        self.steps += 1
+
+    def _halo(self, what):
+        if self.world == 1:
+            return
+        sl, rl, sr, rr = self.e.halo(what)
+        self._xchg(sl, rl, sr, rr)
+
+    def finish(self):
+        """Synchronise and raise if any kernel of the steps so far reported a violated assumption. (During
+        a run the flags are looked at once per step, at the layout synchronisation, i.e. one step late for
+        the ghost check — without an extra synchronisation.)"""
+        self._raise_flags(self.e.flags())
+
+    def _raise_flags(self, f):
+        if f & SLAB_FLAG_MIGRATION:
+            raise SlabError("rank %d: a particle travelled more than margin=%d planes in one step; results are "
+                            "not exact — raise `margin`" % (self.rank, self.margin))
+        if f & SLAB_FLAG_GHOST:
+            raise SlabError("rank %d: a particle drifted beyond the %d ghost planes during the Jacobi iterations; "
+                            "results are not exact — raise `ghost`" % (self.rank, self.ghost))
+
+    def total_particles(self):
+        return int(self.counts.sum())
+
+
+def plane_of(x, llim_x, h, planes):
+    """Cell plane of x-coordinates exactly as the library computes it (reference getGridxyz,
+    Simulator.cu:30-35): trunc((x - llim) / h) in fp32, clamped. Works on numpy arrays and torch tensors."""
+    if isinstance(x, np.ndarray):
+        q = ((x.astype(np.float32) - np.float32(llim_x)) / np.float32(h)).astype(np.float32)
+        return np.clip(np.trunc(q).astype(np.int64), 0, planes - 1)
+    import torch
+    q = (x - torch.tensor(llim_x, dtype=torch.float32, device=x.device)) / torch.tensor(h, dtype=torch.float32, device=x.device)
+    return torch.clamp(torch.trunc(q).to(torch.int64), 0, planes - 1)
