@@ -256,6 +256,196 @@ def run_product(args, rank, world, dist):
     return out
 
 
+# ---- N > 1: one scene across the ranks (x-slab decomposition, pbf-cuda_b200/slab.py) ----------------
+
+def slab_scene(pbf, name, world, scaling):
+    """Block list and box of the multi-GPU workload. weak: the scene's single block and its box are
+    repeated `world` times along x (per-GPU work fixed: SURVEY.md 8d config 5 'weak'); strong: the named
+    scene as it is, cut into `world` slabs."""
+    sc = dict(pbf.SCENES[name])
+    if "blocks" not in sc:
+        raise SystemExit("scene %s has no block description; multi-GPU runs need a block scene" % name)
+    if scaling == "weak":
+        if len(sc["blocks"]) != 1 or "wall" in sc:
+            raise SystemExit("weak scaling is defined for single-block scenes without a moving wall")
+        (origin, n3), = sc["blocks"]
+        sc["blocks"] = [(origin, (n3[0] * world, n3[1], n3[2]))]
+        sc["ulim"] = (sc["ulim"][0] * world, sc["ulim"][1], sc["ulim"][2])
+    return sc
+
+
+def slab_generate(pbf, slab, torch, dev, sc, planes, layer_ranges, keep=None, chunk_layers=64):
+    """Generates lattice layers [a, b) of every block (layer_ranges[k] = (a, b)) on the device, in global
+    input order. keep = (x0, x1): only particles whose cell plane is in [x0, x1) are returned; keep = None:
+    only the per-plane histogram is returned."""
+    h, llx = 0.1, float(sc["llim"][0])
+    hist = torch.zeros(planes, dtype=torch.int64, device=dev)
+    parts, first_iid = [], 0
+    for (origin, n3), (a, b) in zip(sc["blocks"], layer_ranges):
+        per = int(n3[1]) * int(n3[2])
+        for ia in range(a, b, chunk_layers):
+            ib = min(b, ia + chunk_layers)
+            m = (ib - ia) * per
+            pos = torch.empty((m, 3), dtype=torch.float32, device=dev)
+            vel = torch.empty_like(pos)
+            iid = torch.empty(m, dtype=torch.int32, device=dev)
+            pbf.scene_block_slice_device(origin, n3, ia, ib, pos, vel, iid, first_iid=first_iid)
+            pl = slab.plane_of(pos[:, 0], llx, h, planes)
+            if keep is None:
+                hist += torch.bincount(pl, minlength=planes)
+            else:
+                msk = (pl >= keep[0]) & (pl < keep[1])
+                parts.append((pos[msk], vel[msk], iid[msk]))
+        first_iid += int(n3[0]) * per
+    if keep is None:
+        return hist
+    return tuple(torch.cat([q[i] for q in parts]) for i in range(3))
+
+
+def run_product_slab(args, rank, world, dist):
+    import torch
+    pbf = importlib.import_module("pbf-cuda_b200")   # raises if libpbf_b200.so is missing: no fallback
+    slab = importlib.import_module("pbf-cuda_b200.slab")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sc = slab_scene(pbf, args.scene, world, args.scaling)
+    params = pbf.default_params()
+    h = np.float32(0.1)
+    dims = [int(np.ceil(np.float32(np.float32(u) - np.float32(l)) / h)) for u, l in zip(sc["ulim"], sc["llim"])]
+    planes = dims[0]
+    n_total = sum(int(np.prod(b[1])) for b in sc["blocks"])
+    ghost, margin = args.ghost, args.margin
+    comm = slab.TorchComm(dist, device=dev)
+
+    # 1. per-plane histogram of the whole scene (every rank generates 1/world of the layers), the plan
+    shares = [(int(n3[0]) * rank // world, int(n3[0]) * (rank + 1) // world) for _, n3 in sc["blocks"]]
+    hist = slab_generate(pbf, slab, torch, dev, sc, planes, shares)
+    dist.all_reduce(hist)
+    hist = hist.cpu().numpy()
+    bounds = slab.plan_boundaries(hist, world, 2 * (ghost + margin))
+    x0, x1 = bounds[rank], bounds[rank + 1]
+    # 2. capacity: the rank's share with head-room for imbalance + the planes it receives and mirrors
+    per_rank = max(int(hist[bounds[r]:bounds[r + 1]].sum()) for r in range(world))
+    capacity = int(1.3 * per_rank) + 2 * (2 * ghost + margin) * int(hist.max()) + 4096
+    eng = slab.GpuEngine(pbf, params, sc["ulim"], sc["llim"], capacity, device_index=local,
+                         stream=torch.cuda.current_stream().cuda_stream)
+    sim = slab.SlabSimulator(eng, comm, params.niter, planes, ghost=ghost, margin=margin, replan_every=args.replan_every)
+    sim.bounds = bounds
+    # 3. the rank's own particles: the lattice layers that can reach its planes, filtered exactly
+    delta = 0.05
+    ranges = []
+    for origin, n3 in sc["blocks"]:
+        lo = int(np.floor((x0 * 0.1 + sc["llim"][0] - origin[0]) / delta - 0.7)) - 1
+        hi = int(np.ceil((x1 * 0.1 + sc["llim"][0] - origin[0]) / delta - 0.5)) + 1
+        ranges.append((min(max(lo, 0), int(n3[0])), min(max(hi, 0), int(n3[0]))))
+    pos, vel, iid = slab_generate(pbf, slab, torch, dev, sc, planes, ranges, keep=(x0, x1))
+    sim.load_owned(pos, vel, iid)
+    del pos, vel, iid
+    if sim.total_particles() != n_total:
+        raise SystemExit("slab initialisation lost particles: %d of %d" % (sim.total_particles(), n_total))
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    for _ in range(args.warmup):
+        sim.step()
+    sim.finish()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0, msgs0, bytes0 = eng.sim.launch_count(), sim.messages, sim.bytes_sent
+    dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        sim.step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sim.finish()
+    launches = eng.sim.launch_count() - launches0
+    msgs, sent = sim.messages - msgs0, sim.bytes_sent - bytes0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms, float(eng.n_own), -float(eng.n_own)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, n_max, n_min = float(t[0]), int(t[1]), int(-t[2])
+    value = n_total * args.steps / (total_ms * 1e-3)
+
+    # per-kernel device times on this rank for the roofline (same timers as the single-GPU run)
+    eng.sim.enable_stage_timing(True)
+    kacc, reps = {}, 3
+    for _ in range(reps):
+        flush.zero_()
+        sim.step()
+        for k, v in eng.sim.kernel_ms().items():
+            kacc[k] = kacc.get(k, 0.0) + v / reps
+    eng.sim.enable_stage_timing(False)
+    n_own = eng.n_own
+
+    # ---- end to end: every rank's state starts each step in pinned HOST memory and ends there ----------
+    e2e_steps = max(3, min(args.steps, 10))
+    cap = eng.capacity
+    hp = [torch.empty((cap, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    hi = torch.empty(cap, dtype=torch.int32).pin_memory()
+    n = eng.n_own
+    hp[0][:n].copy_(eng.pos[:n]); hp[1][:n].copy_(eng.vel[:n]); hi[:n].copy_(eng.iid[:n])
+    torch.cuda.synchronize()
+    dist.barrier()
+    up = down = 0
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.pos[:n].copy_(hp[0][:n], non_blocking=True); eng.vel[:n].copy_(hp[1][:n], non_blocking=True)
+        eng.iid[:n].copy_(hi[:n], non_blocking=True)
+        up += 28 * n
+        sim.step()
+        n = eng.n_own
+        hp[0][:n].copy_(eng.pos[:n], non_blocking=True); hp[1][:n].copy_(eng.vel[:n], non_blocking=True)
+        hi[:n].copy_(eng.iid[:n], non_blocking=True)
+        down += 28 * n
+        torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s, float(up), float(down)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sim.finish()
+    stats = eng.sim.stats(eng.pos, eng.vel, eng.n_own)
+    eng.close()
+    if rank != 0:
+        return None
+    peak, peak_src = hbm_peak()
+    dom = "lambda" if kacc["lambda"] >= kacc["delta_p"] else "delta_p"
+    achieved = ALG_BYTES[dom] * n_own / (kacc[dom] * 1e-3) / 1e9
+    step_gbs = ALG_BYTES_STEP * (value / world) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "kernel_ms": round(kacc[dom], 4), "algorithmic_bytes_per_particle": ALG_BYTES[dom],
+                "particles_on_this_rank": n_own,
+                "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved_per_gpu": round(step_gbs, 2),
+                               "frac": round(step_gbs / peak, 5)},
+                "note": "rank 0's kernels; the lambda / XSPH sweeps are FP32-issue bound, not HBM bound (DESIGN.md 5)"}
+    e2e = {"value": round(n_total * e2e_steps / float(t[0]), 1), "unit": "particle-steps/s", "steps": e2e_steps,
+           "h2d_bytes_per_step": int(float(t[1]) / e2e_steps), "d2h_bytes_per_step": int(float(t[2]) / e2e_steps),
+           "api": "every rank uploads its slab's pos/vel/iid from pinned host memory, SlabSimulator.step, downloads "
+                  "the result; bytes are the largest rank's"}
+    return {"metric": "particle-steps/s", "value": round(value, 1), "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.scene + (" x%d along x (weak)" % world if args.scaling == "weak" else ""), sc, n_total),
+                       "particles_total": n_total, "particles_per_gpu": {"min": n_min, "max": n_max},
+                       "parallelism": "x-slab decomposition over %d ranks (one scene), NCCL send/recv halo exchange: raw state of "
+                                      "%d planes per side per step + (2*niter+1) float4 ghost refreshes; ghost=%d margin=%d replan_every=%d"
+                                      % (world, ghost + margin, ghost, margin, args.replan_every),
+                       "slab_boundaries": [int(b) for b in sim.bounds],
+                       "messages_per_step_rank0": round(msgs / args.steps, 1), "bytes_sent_per_step_rank0": int(sent / args.steps),
+                       "l2": "flushed between timed steps (256 MB memset outside the event pairs)", "exact_pow": True,
+                       "kernel_ms_rank0": {k: round(v, 4) for k, v in kacc.items()},
+                       "stats_rank0": {k: round(v, 6) for k, v in stats.items()}},
+            "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "clocks": clocks}
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full`, dam_1m early state
 # (profiles/r01_gather_v5_ncu_summary.txt): the lambda pass writes the neighbour list the delta-p pass replays
 TRAFFIC = {"lambda": 594.66e6, "delta_p": 443.24e6}
@@ -368,6 +558,12 @@ def main():
     ap.add_argument("--scene", default="dam_1m")
     ap.add_argument("--cpu-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = the scene's block repeated N times along x; strong = the named scene cut in N slabs")
+    ap.add_argument("--replicas", action="store_true", help="N>1: N independent copies of the scene instead of one scene in slabs")
+    ap.add_argument("--ghost", type=int, default=2)
+    ap.add_argument("--margin", type=int, default=4)
+    ap.add_argument("--replan-every", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -381,7 +577,10 @@ def main():
             import torch.distributed as dist
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
             dist.init_process_group("nccl")
-        out = run_product(args, rank, world, dist)
+        if world > 1 and not args.replicas:
+            out = run_product_slab(args, rank, world, dist)
+        else:
+            out = run_product(args, rank, world, dist)
         if dist:
             dist.destroy_process_group()
     if rank == 0 and out is not None:

@@ -502,5 +502,7 @@ SCENES = {
                      wall=dict(a_ulim=(4.8, 0.0, 0.0), a_llim=(0.0, 0.0, 0.0), w=0.05), ulim_max=(24.0, 6.8, 9.6)),
     "double_dam_16m": dict(ulim=(38.4, 38.4, 9.6), llim=(0.0, 0.0, 0.0),
                            blocks=[((0.2, 25.4, 0.2), (256, 256, 128)), ((25.4, 0.2, 0.2), (256, 256, 128))]),
+    # per-GPU block of the 64M weak-scaling run (SURVEY.md 8d config 5 "weak": box x-extent 9.6 per GPU)
+    "dam_8m": dict(ulim=(9.6, 26.0, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (128, 512, 128))]),
     "dam_64m": dict(ulim=(76.8, 26.0, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (1024, 512, 128))]),
 }

@@ -175,3 +175,18 @@ def test_scene_block_slice_matches_full_block(pbf, torch):
     torch.cuda.synchronize()
     assert np.array_equal(d_pos.cpu().numpy(), sp) and np.array_equal(d_iid.cpu().numpy().view(np.uint32), si)
     assert float(d_vel.abs().max()) == 0.0
+
+
+def test_slab_over_nccl_equals_single_gpu(pbf, torch):
+    """The same comparison through the real transport (one process per GPU, NCCL send/recv); needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the one-GPU box covers the protocol with thread-emulated ranks)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = min(4, torch.cuda.device_count())
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "slab_nccl_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "BIT-EXACT" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
