@@ -247,6 +247,7 @@ def run_product(args, rank, world, dist):
                       "parallelism": "single GPU" if world == 1 else "replicas x%d (one independent scene per GPU)" % world,
                       "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
                       "ms_per_step_back_to_back": round(b2b_ms, 5), "exact_pow": True,
+                      "ms_per_step_series": [round(a.elapsed_time(b), 2) for a, b in ev],
                       "stage_ms": {k: round(v, 4) for k, v in sacc.items()},
                       "kernel_ms": {k: round(v, 4) for k, v in kacc.items()},
                       "stats_after_run": {k: round(v, 6) for k, v in stats.items()}},
@@ -357,9 +358,12 @@ def run_product_slab(args, rank, world, dist):
     launches0, msgs0, bytes0 = eng.sim.launch_count(), sim.messages, sim.bytes_sent
     dist.barrier()
     torch.cuda.synchronize()
+    trace = os.environ.get("PBF_BENCH_TRACE") == "1"
     for k in range(args.steps):
         flush.zero_()
         ev[k][0].record()
+        if trace:
+            print("TRACE rank %d step %d begins %.4f" % (rank, k, time.time()), flush=True)
         sim.step()
         ev[k][1].record()
     torch.cuda.synchronize()
@@ -384,6 +388,19 @@ def run_product_slab(args, rank, world, dist):
             kacc[k] = kacc.get(k, 0.0) + v / reps
     eng.sim.enable_stage_timing(False)
     n_own = eng.n_own
+    # where a step's device time goes on every rank (phase stamps on the stream), and who is slowest
+    phases = {}
+    for _ in range(reps):
+        flush.zero_()
+        for k, v in sim.profile_step().items():
+            phases[k] = phases.get(k, 0.0) + v / reps
+    names = ["raw_exchange", "keys_sort_layout", "count_allgather", "lambda", "delta_p", "update_velocity", "xsph", "halo"]
+    pt = torch.tensor([phases.get(k, 0.0) for k in names] + [sum(a.elapsed_time(b) for a, b in ev) / args.steps, float(eng.n_own)],
+                      dtype=torch.float64, device=dev)
+    allp = [torch.zeros_like(pt) for _ in range(world)]
+    dist.all_gather(allp, pt)
+    per_rank = [{**{k: round(float(q[i]), 3) for i, k in enumerate(names)}, "ms_per_step": round(float(q[-2]), 3),
+                 "particles": int(q[-1])} for q in allp]
 
     # ---- end to end: every rank's state starts each step in pinned HOST memory and ends there ----------
     e2e_steps = max(3, min(args.steps, 10))
@@ -442,6 +459,8 @@ def run_product_slab(args, rank, world, dist):
                        "messages_per_step_rank0": round(msgs / args.steps, 1), "bytes_sent_per_step_rank0": int(sent / args.steps),
                        "l2": "flushed between timed steps (256 MB memset outside the event pairs)", "exact_pow": True,
                        "kernel_ms_rank0": {k: round(v, 4) for k, v in kacc.items()},
+                       "phase_ms_per_rank": per_rank,
+                       "ms_per_step_series_rank0": [round(a.elapsed_time(b), 2) for a, b in ev],
                        "stats_rank0": {k: round(v, 6) for k, v in stats.items()}},
             "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "clocks": clocks}
 
@@ -561,8 +580,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the scene's block repeated N times along x; strong = the named scene cut in N slabs")
     ap.add_argument("--replicas", action="store_true", help="N>1: N independent copies of the scene instead of one scene in slabs")
-    ap.add_argument("--ghost", type=int, default=2)
-    ap.add_argument("--margin", type=int, default=4)
+    ap.add_argument("--ghost", type=int, default=5,
+                    help="ghost planes per side; niter+1 is the guaranteed bound (MAX_DP = one cell per iteration)")
+    ap.add_argument("--margin", type=int, default=6, help="planes a particle may travel between two sorts")
     ap.add_argument("--replan-every", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

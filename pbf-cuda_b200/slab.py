@@ -127,6 +127,16 @@ class TorchComm:
             for req in self.dist.batch_isend_irecv(ops):
                 req.wait()
 
+    def connect(self, peers):
+        """Exchanges one word with every peer in BOTH directions. NCCL sets a send/recv connection up on
+        first use per direction (~0.2 s); a dam break may not send anything leftwards for many steps, so
+        without this the set-up lands in the middle of a timed run."""
+        import torch
+        dev = self.device if self.device is not None else "cpu"
+        tx = {p: [torch.zeros(1, dtype=torch.float32, device=dev)] for p in peers}
+        rx = {p: [torch.zeros(1, dtype=torch.float32, device=dev)] for p in peers}
+        self.exchange(tx, rx)
+
     def allgather_counts(self, counts):
         import torch
         mine = torch.from_numpy(np.ascontiguousarray(counts, np.int64))
@@ -143,6 +153,9 @@ class SingleComm:
 
     def exchange(self, sends, recvs):
         assert not any(t.numel() for ts in sends.values() for t in ts)
+
+    def connect(self, peers):
+        pass
 
     def allgather_counts(self, counts):
         return np.asarray(counts, np.int64)[None, :]
@@ -178,6 +191,9 @@ class ThreadComm:
             for t in recvs[peer]:
                 if t.numel():
                     t.copy_(self._get(self.hub.box[(peer, self.rank)]))
+
+    def connect(self, peers):
+        pass
 
     def _get(self, box):
         import queue
@@ -289,6 +305,12 @@ class GpuEngine:
     def flags(self):
         return self.sim.slab_flags()
 
+    def mark(self):
+        """A CUDA event on the stream the step runs on (phase timing of SlabSimulator.profile_step)."""
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
     def state(self):
         """(pos, vel, iid) of the owned particles after the last step (device tensors, views)."""
         n = self.n_own
@@ -337,6 +359,7 @@ class SlabSimulator:
     def load_owned(self, pos, vel, iid):
         """pos/vel/iid: this rank's particles (all inside my_planes()), in the GLOBAL input order."""
         x0, x1 = self.my_planes()
+        self.c.connect([p for p in (self.rank - 1, self.rank + 1) if 0 <= p < self.world])
         self.e.load_state(pos, vel, iid, x0, x1, self.rank > 0, self.rank < self.world - 1)
         self.counts = self.c.allgather_counts(self.e.plane_counts())
 
@@ -354,6 +377,28 @@ class SlabSimulator:
                     self.bytes_sent += t.numel() * t.element_size()
         self.c.exchange(sends, recvs)
 
+    def profile_step(self):
+        """One step with device-time stamps at the phase boundaries: returns {phase: ms} for this rank
+        (raw exchange, keys+sort+layout, count all-gather, passes, halos). Synchronises; not for timed runs."""
+        marks = []
+        self._mark = lambda name: marks.append((name, self.e.mark()))
+        self._mark("start")
+        try:
+            self.step()
+        finally:
+            self._mark = None
+        marks[-1][1].synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(marks, marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+    _mark = None
+
+    def _m(self, name):
+        if self._mark:
+            self._mark(name)
+
     def step(self):
         e, r, w = self.e, self.rank, self.world
         old = self.bounds
@@ -367,6 +412,7 @@ class SlabSimulator:
         # 1. raw state of the planes around each boundary
         self._xchg(e.raw_views(0, xp["send_left_end"]), e.raw_views(n_own, n_own + m_l),
                    e.raw_views(xp["send_right_begin"], n_own), e.raw_views(n_own + m_l, n_own + m_l + m_r))
+        self._m("raw_exchange")
         st = SlabStep(x_begin=new[r], x_end=new[r + 1], ghost=self.ghost, has_left=int(r > 0), has_right=int(r < w - 1),
                       n_own=n_own, m_left=m_l, m_right=m_r, send_left_end=xp["send_left_end"],
                       send_right_begin=xp["send_right_begin"])
@@ -376,17 +422,26 @@ class SlabSimulator:
         #    the host runs ahead into the next step while the device works through the passes below.
         e.begin(st)
         lay = e.grid()
+        self._m("keys_sort_layout")
         self.counts = self.c.allgather_counts(e.plane_counts())
+        self._m("count_allgather")
         self._raise_flags(lay.flags)
         # 3. Jacobi iterations with ghost refreshes
         for _ in range(self.niter):
             e.lambda_pass()
+            self._m("lambda")
             self._halo(HALO_LAMBDA)
+            self._m("halo")
             e.delta_p_pass()
+            self._m("delta_p")
             self._halo(HALO_POSITION)
+            self._m("halo")
         e.update_velocity()
+        self._m("update_velocity")
         self._halo(HALO_VELOCITY)
+        self._m("halo")
         e.xsph()
+        self._m("xsph")
         e.end()
         self.bounds = new
         self.steps += 1
