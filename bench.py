@@ -331,7 +331,8 @@ def run_product_slab(args, rank, world, dist):
     capacity = int(1.3 * per_rank) + 2 * (2 * ghost + margin) * int(hist.max()) + 4096
     eng = slab.GpuEngine(pbf, params, sc["ulim"], sc["llim"], capacity, device_index=local,
                          stream=torch.cuda.current_stream().cuda_stream)
-    sim = slab.SlabSimulator(eng, comm, params.niter, planes, ghost=ghost, margin=margin, replan_every=args.replan_every)
+    sim = slab.SlabSimulator(eng, comm, params.niter, planes, ghost=ghost, margin=margin, replan_every=args.replan_every,
+                             fused_halo=args.halo == "fused")
     sim.bounds = bounds
     # 3. the rank's own particles: the lattice layers that can reach its planes, filtered exactly
     delta = 0.05
@@ -429,6 +430,8 @@ def run_product_slab(args, rank, world, dist):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sim.finish()
     stats = eng.sim.stats(eng.pos, eng.vel, eng.n_own)
+    torch.cuda.synchronize()
+    dist.barrier()     # nobody frees arrays a neighbour may still be pushing ghost values into
     eng.close()
     if rank != 0:
         return None
@@ -452,9 +455,12 @@ def run_product_slab(args, rank, world, dist):
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.scene + (" x%d along x (weak)" % world if args.scaling == "weak" else ""), sc, n_total),
                        "particles_total": n_total, "particles_per_gpu": {"min": n_min, "max": n_max},
-                       "parallelism": "x-slab decomposition over %d ranks (one scene), NCCL send/recv halo exchange: raw state of "
-                                      "%d planes per side per step + (2*niter+1) float4 ghost refreshes; ghost=%d margin=%d replan_every=%d"
-                                      % (world, ghost + margin, ghost, margin, args.replan_every),
+                       "parallelism": "x-slab decomposition over %d ranks (one scene): per step one NCCL send/recv of the raw state of "
+                                      "%d planes per side, then (2*niter+1) ghost refreshes %s; ghost=%d margin=%d replan_every=%d"
+                                      % (world, ghost + margin,
+                                         "FUSED into the pass kernels (stores into the neighbour's ghost slots over NVLink peer memory "
+                                         "+ a flag handshake, no collective)" if args.halo == "fused" else "as NCCL send/recv of float4 ranges",
+                                         ghost, margin, args.replan_every),
                        "slab_boundaries": [int(b) for b in sim.bounds],
                        "messages_per_step_rank0": round(msgs / args.steps, 1), "bytes_sent_per_step_rank0": int(sent / args.steps),
                        "l2": "flushed between timed steps (256 MB memset outside the event pairs)", "exact_pow": True,
@@ -584,6 +590,8 @@ def main():
                     help="ghost planes per side; niter+1 is the guaranteed bound (MAX_DP = one cell per iteration)")
     ap.add_argument("--margin", type=int, default=6, help="planes a particle may travel between two sorts")
     ap.add_argument("--replan-every", type=int, default=20)
+    ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],
+                    help="N>1 ghost refreshes: fused = peer-memory stores from inside the kernels; nccl = send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -38,11 +38,12 @@ EXPORTS = (
     "pbf_scene_block_device", "pbf_scene_block_host", "pbf_last_error", "pbf_version",
     "pbf_slab_begin", "pbf_slab_get_layout", "pbf_slab_plane_counts", "pbf_stage_lambda", "pbf_stage_delta_p",
     "pbf_slab_halo", "pbf_slab_flags", "pbf_slab_sort_state", "pbf_scene_block_slice_device",
-    "pbf_scene_block_slice_host",
+    "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach", "pbf_slab_peer_set_offset",
+    "pbf_slab_halo_sync",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
-SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST = 1, 2
+SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST, SLAB_FLAG_TIMEOUT = 1, 2, 4
 
 
 class PbfError(RuntimeError):
@@ -76,6 +77,12 @@ class SlabLayout(C.Structure):
     _fields_ = [("n_local", C.c_int64), ("own_first", C.c_int64), ("own_count", C.c_int64),
                 ("send_left_count", C.c_int64), ("send_right_count", C.c_int64),
                 ("recv_left_count", C.c_int64), ("recv_right_count", C.c_int64), ("flags", C.c_uint32)]
+
+
+class SlabPeerInfo(C.Structure):
+    """pbf_slab_peer_info (include/pbf.h): a rank's solver arrays as CUDA IPC handles / raw pointers."""
+    _fields_ = [("ipc", (C.c_ubyte * 64) * 4), ("ptr", C.c_uint64 * 4), ("pid", C.c_int64), ("device", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -135,6 +142,10 @@ _lib.pbf_scene_block_slice_device.argtypes = [_f3, C.POINTER(C.c_int32), C.c_flo
                                               C.c_int32, _vp, _vp, _vp, _vp]
 _lib.pbf_scene_block_slice_host.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, C.c_int32,
                                             C.c_int32, _vp, _vp, _vp]
+_lib.pbf_slab_peer_export.argtypes = [_vp, C.POINTER(SlabPeerInfo)]
+_lib.pbf_slab_peer_attach.argtypes = [_vp, C.c_int, C.POINTER(SlabPeerInfo)]
+_lib.pbf_slab_peer_set_offset.argtypes = [_vp, _i64]
+_lib.pbf_slab_halo_sync.argtypes = [_vp]
 _lib.pbf_last_error.restype = C.c_char_p
 _lib.pbf_version.restype = C.c_char_p
 
@@ -319,6 +330,24 @@ class Simulator:
         p = [_vp() for _ in range(4)]
         _check(_lib.pbf_slab_halo(self._h, int(what), *[C.byref(q) for q in p]))
         return tuple(q.value or 0 for q in p)
+
+    def slab_peer_export(self):
+        info = SlabPeerInfo()
+        _check(_lib.pbf_slab_peer_export(self._h, C.byref(info)))
+        return bytes(info)
+
+    def slab_peer_attach(self, side, info_bytes):
+        if info_bytes is None:
+            _check(_lib.pbf_slab_peer_attach(self._h, int(side), None))
+        else:
+            info = SlabPeerInfo.from_buffer_copy(info_bytes)
+            _check(_lib.pbf_slab_peer_attach(self._h, int(side), C.byref(info)))
+
+    def slab_peer_set_offset(self, left_peer_first_right_ghost_slot):
+        _check(_lib.pbf_slab_peer_set_offset(self._h, int(left_peer_first_right_ghost_slot)))
+
+    def slab_halo_sync(self):
+        _check(_lib.pbf_slab_halo_sync(self._h))
 
     def slab_flags(self):
         f = C.c_uint32()

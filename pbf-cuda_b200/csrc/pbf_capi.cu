@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <new>
 
@@ -109,6 +110,19 @@ struct pbf_sim {
     uint32_t* flags_dev = nullptr;
     pbf_slab_layout layout{};
     bool layout_valid = false;
+    // fused halo over peer memory
+    struct Peer {
+        bool on = false;
+        float4* x[2] = {nullptr, nullptr};
+        float4* xl = nullptr;
+        uint32_t* sync = nullptr;
+        void* ipc_base[4] = {nullptr, nullptr, nullptr, nullptr};  // opened IPC mappings to close
+    } peer[2];
+    uint32_t* sync_words = nullptr;   // device: [0] raised by the left neighbour, [1] by the right one
+    int64_t peer_left_offset = 0;
+    bool peer_offset_valid = false;
+    uint32_t halo_seq = 0;
+    uint64_t halo_timeout_ns = 10ull * 1000 * 1000 * 1000;
 
     int64_t launches = 0;
     bool timing = false;
@@ -218,6 +232,10 @@ void free_all(pbf_sim* s) {
     cudaFree(s->plane_dev);
     if (s->plane_host) cudaFreeHost(s->plane_host);
     if (s->flags_host) cudaFreeHost(s->flags_host);
+    for (auto& pr : s->peer)
+        for (void* b : pr.ipc_base)
+            if (b) cudaIpcCloseMemHandle(b);
+    cudaFree(s->sync_words);
     if (s->ev_valid) {
         for (auto& e : s->ev) cudaEventDestroy(e);
         for (auto& e : s->kev) cudaEventDestroy(e);
@@ -305,6 +323,9 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->plane_host, (size_t)s->plane_capacity * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->flags_host, sizeof(uint32_t), cudaHostAllocMapped);
     if (e == cudaSuccess) { *s->flags_host = 0; e = cudaHostGetDevicePointer((void**)&s->flags_dev, s->flags_host, 0); }
+    A((void**)&s->sync_words, 8 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->sync_words, 0, 8 * sizeof(uint32_t));
+    if (const char* to = getenv("PBF_HALO_TIMEOUT_MS")) s->halo_timeout_ns = (uint64_t)atoll(to) * 1000000ull;
     if (e != cudaSuccess) {
         free_all(s);
         delete s;
@@ -432,6 +453,24 @@ static int slab_learn_layout(pbf_sim* s) {
     return PBF_OK;
 }
 
+// Where the boundary values of the pass writing array `a` (x[0], x[1] or xl of this handle) go on
+// the attached neighbours. Empty when no neighbour is attached: the caller's transport does it.
+static int make_push(pbf_sim* s, const float4* a, HaloPush* hp) {
+    *hp = HaloPush();
+    if (!s->slab_on || (!s->peer[0].on && !s->peer[1].on)) return PBF_OK;
+    if (!s->layout_valid || !s->peer_offset_valid)
+        return fail(PBF_ERR_STATE, "fused halo: pbf_slab_peer_set_offset must follow pbf_slab_get_layout every step");
+    const pbf_slab_layout& L = s->layout;
+    for (int side = 0; side < 2; side++) {
+        const pbf_sim::Peer& pr = s->peer[side];
+        if (!pr.on) continue;
+        float4* dst = a == s->x[0] ? pr.x[0] : a == s->x[1] ? pr.x[1] : pr.xl;
+        if (side == 0 && L.send_left_count > 0) { hp->left = dst + s->peer_left_offset; hp->left_count = L.send_left_count; }
+        if (side == 1 && L.send_right_count > 0) { hp->right = dst; hp->right_first = L.own_count - L.send_right_count; }
+    }
+    return PBF_OK;
+}
+
 int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n,
                     void* stream) {
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
@@ -449,6 +488,7 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
     s->si.n_own = n;
     s->n_local = n; s->own_first = 0; s->own_count = n;
     s->layout_valid = false;
+    s->peer_offset_valid = false;
     s->cur = 0;
     s->iters_done = 0;
     s->pos0_in_npos = false;
@@ -493,14 +533,20 @@ int pbf_stage_build_grid(pbf_sim* s) {
 int pbf_stage_lambda(pbf_sim* s) {
     if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "lambda: build_grid first");
     // (each iteration overwrites the slot: the timers report the LAST iteration of the step)
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, s->g, s->c, s->stream, &s->launches));
+    HaloPush hp;
+    int prc = make_push(s, s->xl, &hp);
+    if (prc) return prc;
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_LAMBDA;
     return PBF_OK;
 }
 
 int pbf_stage_delta_p(pbf_sim* s) {
     if (!s || s->stage != ST_LAMBDA) return fail(PBF_ERR_STATE, "delta_p: lambda first");
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, s->g, s->c, s->stream, &s->launches));
+    HaloPush hp;
+    int prc = make_push(s, s->x[s->cur ^ 1], &hp);
+    if (prc) return prc;
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;
@@ -519,7 +565,10 @@ int pbf_stage_update_velocity(pbf_sim* s) {
     int rc = stage_event(s, 3);
     if (rc) return rc;
     // xl is dead after the last delta-p pass: reuse it for (velocity, rho)
-    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, s->c, s->stream, &s->launches));
+    HaloPush hp;
+    int prc = make_push(s, s->xl, &hp);
+    if (prc) return prc;
+    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, hp, s->c, s->stream, &s->launches));
     s->pos0_in_npos = false;
     s->stage = ST_VELOCITY;
     return stage_event(s, 4);
@@ -645,6 +694,77 @@ int pbf_slab_halo(pbf_sim* s, int what, void** send_left, void** recv_left, void
     *send_left = a + L.own_first;
     *send_right = a + L.own_first + L.own_count - L.send_right_count;
     *recv_right = a + L.own_first + L.own_count;
+    return PBF_OK;
+}
+
+int pbf_slab_peer_export(pbf_sim* s, pbf_slab_peer_info* out) {
+    if (!s || !out) return fail(PBF_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    memset(out, 0, sizeof(*out));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "pbf_slab_peer_info::ipc holds CUDA IPC handles");
+    void* arr[4] = {s->x[0], s->x[1], s->xl, s->sync_words};
+    for (int k = 0; k < 4; k++) {
+        out->ptr[k] = (uint64_t)(uintptr_t)arr[k];
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, arr[k]) == cudaSuccess) memcpy(out->ipc[k], &h, 64);
+        else cudaGetLastError();   // no IPC on this platform: same-process neighbours still work
+    }
+    out->pid = (int64_t)getpid();
+    out->device = s->device;
+    return PBF_OK;
+}
+
+int pbf_slab_peer_attach(pbf_sim* s, int side, const pbf_slab_peer_info* peer) {
+    if (!s || side < 0 || side > 1) return fail(PBF_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    pbf_sim::Peer& pr = s->peer[side];
+    for (void*& b : pr.ipc_base)
+        if (b) { cudaIpcCloseMemHandle(b); b = nullptr; }
+    pr = pbf_sim::Peer();
+    if (!peer) return PBF_OK;   // detach
+    void* arr[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (peer->pid == (int64_t)getpid()) {
+        if (peer->device != s->device) {   // another device of this process: plain peer access
+            cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(PBF_ERR_CUDA, "no peer access from device %d to %d: %s", s->device, peer->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        for (int k = 0; k < 4; k++) arr[k] = (void*)(uintptr_t)peer->ptr[k];
+    } else {
+        for (int k = 0; k < 4; k++) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, peer->ipc[k], 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&arr[k], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int j = 0; j < k; j++) { cudaIpcCloseMemHandle(arr[j]); pr.ipc_base[j] = nullptr; }
+                return fail(PBF_ERR_CUDA, "cudaIpcOpenMemHandle failed for the neighbour's array %d: %s", k, cudaGetErrorString(e));
+            }
+            pr.ipc_base[k] = arr[k];
+        }
+    }
+    pr.x[0] = (float4*)arr[0]; pr.x[1] = (float4*)arr[1]; pr.xl = (float4*)arr[2]; pr.sync = (uint32_t*)arr[3];
+    pr.on = true;
+    return PBF_OK;
+}
+
+int pbf_slab_peer_set_offset(pbf_sim* s, int64_t left_peer_first_right_ghost_slot) {
+    if (!s || left_peer_first_right_ghost_slot < 0) return fail(PBF_ERR_INVALID, "bad argument");
+    if (!s->slab_on || !s->layout_valid) return fail(PBF_ERR_STATE, "no slab layout: pbf_slab_begin .. pbf_stage_build_grid first");
+    s->peer_left_offset = left_peer_first_right_ghost_slot;
+    s->peer_offset_valid = true;
+    return PBF_OK;
+}
+
+int pbf_slab_halo_sync(pbf_sim* s) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    if (!s->peer[0].on && !s->peer[1].on) return PBF_OK;
+    s->halo_seq++;
+    // I am my left neighbour's RIGHT neighbour: raise its word [1]; and my right neighbour's word [0]
+    CUDA_TRY(launch_halo_signal(s->peer[0].on ? s->peer[0].sync + 1 : nullptr, s->peer[1].on ? s->peer[1].sync + 0 : nullptr,
+                                s->halo_seq, s->stream, &s->launches));
+    CUDA_TRY(launch_halo_wait(s->peer[0].on ? s->sync_words + 0 : nullptr, s->peer[1].on ? s->sync_words + 1 : nullptr,
+                              s->halo_seq, s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
     return PBF_OK;
 }
 

@@ -85,6 +85,22 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 
+// Fused halo push (slab mode with attached peers): the pass that produces a float4 per owned
+// particle also stores it — for the particles of the first / last ghost-width planes — straight
+// into the neighbour rank's ghost slots over NVLink (peer-mapped memory), so that a halo refresh
+// needs no copy kernel and no NCCL call, only a flag handshake (slab.cu). `t` below is the
+// particle's index among the owned slots.
+struct HaloPush {
+    float4* left = nullptr;    // left peer's array, already offset to its first right-ghost slot
+    float4* right = nullptr;   // right peer's array, offset to its first left-ghost slot (slot 0)
+    int64_t left_count = 0;    // owned t in [0, left_count) are mirrored by the left peer
+    int64_t right_first = 0;   // owned t in [right_first, n) are mirrored by the right peer
+};
+__device__ __forceinline__ void halo_push(const HaloPush& hp, int64_t t, const float4 v) {
+    if (hp.left && t < hp.left_count) hp.left[t] = v;
+    if (hp.right && t >= hp.right_first) hp.right[t - hp.right_first] = v;
+}
+
 // ---- launchers (each returns the CUDA error of its launches) ---------------------------
 
 // advect + cell key + per-pass digit histograms, in input order (advect_key.cu)
@@ -117,7 +133,7 @@ cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* 
 // Neighbour list the lambda pass saves for the delta-p pass of the same iteration (null = off).
 struct PairList {
     uint32_t* idx = nullptr;  // slot of the k-th in-range neighbour
-    float2* sw = nullptr;     // (spiky scale, poly6^n_corr) of that pair
+    float2* sw = nullptr;     // (spiky scale, poly6 weight) of that pair
     uint32_t* cnt = nullptr;  // per particle: number of entries, or the overflow flag
 };
 size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_bytes, size_t* cnt_bytes);
@@ -125,14 +141,21 @@ size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_byte
 // read neighbours from every slot. Internal arrays (x, xl, rho, v4, iid_sorted) are indexed by
 // slot; caller-facing arrays (pos/npos/vel/nvel/iid) and the pair list by slot - first.
 cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                          int64_t n, const PairList& pl, const GridConsts& g, const SolverConsts& c,
-                          cudaStream_t st, int64_t* launches);
+                          int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
+                          const SolverConsts& c, cudaStream_t st, int64_t* launches);
 cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t first, int64_t n,
-                           const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                           int64_t* launches);
+                           const PairList& pl, const HaloPush& hp, const GridConsts& g, const SolverConsts& c,
+                           cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
-                                   float* vel_out, float4* v4, int64_t first, int64_t n,
+                                   float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
                                    const SolverConsts& c, cudaStream_t st, int64_t* launches);
+// slab.cu: flag handshake of a fused halo refresh. signal: store `seq` (release, system scope) to
+// a word in a peer's memory; wait: spin until the local word reaches `seq`, give up after
+// `timeout_ns` and raise PBF_SLAB_FLAG_TIMEOUT instead of hanging the device.
+cudaError_t launch_halo_signal(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq, cudaStream_t st,
+                               int64_t* launches);
+cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
+                             uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches);
 cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,
                         const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n,
                         const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);

@@ -43,7 +43,62 @@ gather_state_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__
     iid_out[s] = iid[j];
 }
 
+// ---- flag handshake of the fused halo refresh ------------------------------------------------
+// After a pass whose kernel pushed its boundary values into the neighbours' ghost slots, a rank
+// tells both neighbours "my pushes of refresh #seq are complete" and waits for theirs. Both are
+// one-thread kernels in stream order: the signal runs after the pushing kernel has retired (its
+// remote stores are performed), the wait blocks the stream until the neighbours' words arrive.
+__global__ void halo_signal_kernel(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq) {
+    __threadfence_system();
+    if (peer_word_left) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_word_left), "r"(seq) : "memory");
+    if (peer_word_right) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_word_right), "r"(seq) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// (int32 difference: the sequence number may wrap)
+__global__ void halo_wait_kernel(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
+                                 uint64_t timeout_ns, uint32_t* flags) {
+    const uint64_t t0 = global_ns();
+    for (int side = 0; side < 2; side++) {
+        const uint32_t* w = side == 0 ? word_left : word_right;
+        if (!w) continue;
+        while ((int32_t)(ld_acquire_sys(w) - seq) < 0) {
+            if (global_ns() - t0 > timeout_ns) {   // a dead neighbour must not hang the device
+                if (flags) atomicOr(flags, (uint32_t)PBF_SLAB_FLAG_TIMEOUT);
+                return;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_halo_signal(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq, cudaStream_t st,
+                               int64_t* launches) {
+    if (!peer_word_left && !peer_word_right) return cudaSuccess;
+    halo_signal_kernel<<<1, 1, 0, st>>>(peer_word_left, peer_word_right, seq);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
+                             uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches) {
+    if (!word_left && !word_right) return cudaSuccess;
+    halo_wait_kernel<<<1, 1, 0, st>>>(word_left, word_right, seq, timeout_ns, flags);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,
                                cudaStream_t st, int64_t* launches) {

@@ -135,9 +135,10 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
 // computeLambda and computetpos on the same dc_npos, Simulator.cu:222-245), so their in-range
 // neighbour sets and the per-pair kernel values coincide. The lambda pass therefore saves, per
 // particle and in visiting order, the slot offset of every in-range neighbour plus the two values
-// the delta-p pass needs from the pair geometry: the spiky scale s and w^n_corr. The delta-p pass
-// replays the list: no cull, no sqrt, no division, no pow — and produces the same bits, because it
-// consumes the very values its own evaluation would have produced.
+// the delta-p pass needs from the pair geometry: the spiky scale s and the poly6 weight w. The
+// delta-p pass replays the list: no cull, no sqrt, no division — only w^n_corr, which it can
+// afford (it is HBM bound) — and produces the same bits, because it consumes the very values its
+// own evaluation would have produced.
 // Layout (block b of 128 threads, entry k, thread t): [(b*PAIR_CAP + k)*128 + t] — a warp's k-th
 // entries are contiguous (4 B slot + 8 B (s, w^n)). A particle with more than PAIR_CAP neighbours
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
@@ -148,7 +149,8 @@ __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
               uint32_t* __restrict__ pair_idx, float2* __restrict__ pair_sw, uint32_t* __restrict__ pair_cnt,
-              const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+              const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
+              const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (t >= n) return;
@@ -178,14 +180,10 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
             giy = __fadd_rn(giy, gy);
             giz = __fadd_rn(giz, gz);
             gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
-            if (SAVE_PAIRS) {
-                if (EXACT_POW) {
-                    pw = powf(w, c.n_corr);
-                } else {  // n_corr == 4
-                    const float w2 = __fmul_rn(w, w);
-                    pw = __fmul_rn(w2, w2);
-                }
-            }
+            // The delta-p pass needs w^n_corr of this pair. The lambda pass is FP32-issue bound and the
+            // delta-p replay is HBM bound with idle issue slots, so the ~45-instruction powf is left to
+            // the replay: the list carries w itself, and powf(w, n) there yields the reference's bits.
+            pw = w;
         }
         // (the self entry is saved with s = pw = 0: the delta-p pass then adds an exact zero)
         if (SAVE_PAIRS) {
@@ -200,7 +198,9 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
     if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
     const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
     const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
-    xl[i] = make_float4(p.x, p.y, p.z, lambda);
+    const float4 out = make_float4(p.x, p.y, p.z, lambda);
+    xl[i] = out;
+    halo_push(hp, t, out);
     rho_out[i] = rho;
     if (SAVE_PAIRS) pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
 }
@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n,
                const uint32_t* __restrict__ pair_idx, const float2* __restrict__ pair_sw,
-               const uint32_t* __restrict__ pair_cnt, const __grid_constant__ GridConsts g,
-               const __grid_constant__ SolverConsts c) {
+               const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
+               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (t >= n) return;
@@ -242,7 +242,14 @@ delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                 const uint32_t j = __ldg(&pair_idx[e]);
                 const float2 sw = __ldg(&pair_sw[e]);
                 const float4 q = __ldg(&xl[j]);
-                const float sc = __fmaf_rn(c.coef_corr, sw.y, __fadd_rn(p.w, q.w));
+                float pw;  // sw.y = poly6(r2) of the pair, saved by the lambda pass
+                if (EXACT_POW) {
+                    pw = powf(sw.y, c.n_corr);
+                } else {  // n_corr == 4
+                    const float w2 = __fmul_rn(sw.y, sw.y);
+                    pw = __fmul_rn(w2, w2);
+                }
+                const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
                 ax = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.x, q.x), sw.x), ax);
                 ay = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.y, q.y), sw.x), ay);
                 az = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.z, q.z), sw.x), az);
@@ -268,7 +275,9 @@ delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
             az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
         }, NoHooks());
     }
-    x_out[i] = delta_p_finish(p, ax, ay, az, c);
+    const float4 out = delta_p_finish(p, ax, ay, az, c);
+    x_out[i] = out;
+    halo_push(hp, t, out);
 }
 
 // vel = (npos - pos) * inv_dt, plus everything the caller-facing buffers need from this point:
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(256)
 update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ rho,
                        float* __restrict__ pos_out, float* __restrict__ npos_io,
                        float* __restrict__ vel_out, float4* __restrict__ v4, int64_t first, int64_t n,
-                       const __grid_constant__ SolverConsts c) {
+                       const __grid_constant__ HaloPush hp, const __grid_constant__ SolverConsts c) {
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= n) return;
     const int64_t i = first + t;
@@ -286,7 +295,9 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
     const float vx = __fmul_rn(__fsub_rn(q.x, p0.x), c.inv_dt);
     const float vy = __fmul_rn(__fsub_rn(q.y, p0.y), c.inv_dt);
     const float vz = __fmul_rn(__fsub_rn(q.z, p0.z), c.inv_dt);
-    v4[i] = make_float4(vx, vy, vz, rho[i]);
+    const float4 out = make_float4(vx, vy, vz, rho[i]);
+    v4[i] = out;
+    halo_push(hp, t, out);
     store_f3(vel_out, t, vx, vy, vz);
     store_f3(pos_out, t, p0.x, p0.y, p0.z);
     store_f3(npos_io, t, q.x, q.y, q.z);
@@ -341,43 +352,43 @@ size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_byte
 }
 
 cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                          int64_t n, const PairList& pl, const GridConsts& g, const SolverConsts& c,
-                          cudaStream_t st, int64_t* launches) {
+                          int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
+                          const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     const bool exact = c.exact_pow || c.n_corr != 4.0f;
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (!pl.idx)
-        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, g, c);
+        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
     else if (exact)
-        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
+        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
     else
-        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
+        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t first, int64_t n,
-                           const PairList& pl, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                           int64_t* launches) {
+                           const PairList& pl, const HaloPush& hp, const GridConsts& g, const SolverConsts& c,
+                           cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     const bool exact = c.exact_pow || c.n_corr != 4.0f;
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (pl.idx) {
-        if (exact) delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
-        else delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, g, c);
+        if (exact) delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
+        else delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
     } else {
-        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, g, c);
-        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, g, c);
+        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
+        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
-                                   float* vel_out, float4* v4, int64_t first, int64_t n,
+                                   float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
                                    const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    update_velocity_kernel<<<nblocks(n, 256), 256, 0, st>>>(x, rho, pos_out, npos_io, vel_out, v4, first, n, c);
+    update_velocity_kernel<<<nblocks(n, 256), 256, 0, st>>>(x, rho, pos_out, npos_io, vel_out, v4, first, n, hp, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -23,7 +23,9 @@ restricted to the particles it sees; ghosts are exact copies refreshed from thei
 """
 import numpy as np
 
-from . import HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY, SLAB_FLAG_GHOST, SLAB_FLAG_MIGRATION, SlabStep
+from . import (HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY, SLAB_FLAG_GHOST, SLAB_FLAG_MIGRATION, SLAB_FLAG_TIMEOUT,
+               SlabPeerInfo, SlabStep)
+import ctypes as _C
 
 
 class SlabError(RuntimeError):
@@ -183,14 +185,25 @@ class ThreadComm:
         self.hub, self.rank, self.world = hub, rank, hub.world
 
     def exchange(self, sends, recvs):
+        # ranks may run on different CUDA streams of the one device: the copy is ordered behind the
+        # sender's clone with an event
         for peer in sorted(sends):
             for t in sends[peer]:
                 if t.numel():
-                    self.hub.box[(self.rank, peer)].put(t.clone())
+                    c, ev = t.clone(), None
+                    if c.is_cuda:
+                        import torch
+                        ev = torch.cuda.Event()
+                        ev.record()
+                    self.hub.box[(self.rank, peer)].put((c, ev))
         for peer in sorted(recvs):
             for t in recvs[peer]:
                 if t.numel():
-                    t.copy_(self._get(self.hub.box[(peer, self.rank)]))
+                    c, ev = self._get(self.hub.box[(peer, self.rank)])
+                    if ev is not None:
+                        import torch
+                        torch.cuda.current_stream().wait_event(ev)
+                    t.copy_(c)
 
     def connect(self, peers):
         pass
@@ -302,6 +315,29 @@ class GpuEngine:
         self.n_own = int(self.layout.own_count)
         return self.n_own
 
+    # -- fused halo over peer memory (the kernels push their boundary values into the neighbours' ghost slots)
+    peer_info_bytes = _C.sizeof(SlabPeerInfo)
+
+    def peer_export(self):
+        t = self.torch.frombuffer(bytearray(self.sim.slab_peer_export()), dtype=self.torch.uint8)
+        return t.to(self.dev)
+
+    def peer_buffer(self):
+        return self.torch.zeros(self.peer_info_bytes, dtype=self.torch.uint8, device=self.dev)
+
+    def peer_attach(self, side, info_tensor):
+        self.sim.slab_peer_attach(side, None if info_tensor is None else bytes(info_tensor.cpu().numpy().tobytes()))
+
+    def peer_set_offset(self, slot):
+        self.sim.slab_peer_set_offset(slot)
+
+    def halo_sync(self):
+        self.sim.slab_halo_sync()
+
+    def layout_tail(self):
+        L = self.layout
+        return [0, self.n_own] if L is None else [int(L.own_first), int(L.own_count)]
+
     def flags(self):
         return self.sim.slab_flags()
 
@@ -335,13 +371,17 @@ class SlabSimulator:
     replan_every  re-cut the slabs at particle-count quantiles every k steps (0: keep the first plan)
     """
 
-    def __init__(self, engine, comm, niter, planes, ghost=2, margin=4, replan_every=0):
+    def __init__(self, engine, comm, niter, planes, ghost=2, margin=4, replan_every=0, fused_halo=False):
         self.e, self.c = engine, comm
         self.rank, self.world = comm.rank, comm.world
         self.niter, self.planes = int(niter), int(planes)
         self.ghost, self.margin, self.reach = int(ghost), int(margin), int(ghost) + int(margin)
         self.min_width = 2 * self.reach
         self.replan_every = int(replan_every)
+        # fused_halo: the ghost refreshes are peer-memory stores issued by the pass kernels themselves plus a
+        # flag handshake (include/pbf.h "Fused halo refresh"); otherwise one send/recv pair per side through comm
+        self.fused = bool(fused_halo) and comm.world > 1
+        self.left_peer_tail = None
         self.bounds = None
         self.counts = None
         self.steps = 0
@@ -360,8 +400,30 @@ class SlabSimulator:
         """pos/vel/iid: this rank's particles (all inside my_planes()), in the GLOBAL input order."""
         x0, x1 = self.my_planes()
         self.c.connect([p for p in (self.rank - 1, self.rank + 1) if 0 <= p < self.world])
+        if self.fused:
+            self._attach_peers()
         self.e.load_state(pos, vel, iid, x0, x1, self.rank > 0, self.rank < self.world - 1)
-        self.counts = self.c.allgather_counts(self.e.plane_counts())
+        self._gather_counts()
+
+    def _attach_peers(self):
+        e, r, w = self.e, self.rank, self.world
+        mine = e.peer_export()
+        peers = [p for p in (r - 1, r + 1) if 0 <= p < w]
+        got = {p: e.peer_buffer() for p in peers}
+        self.c.exchange({p: [mine] for p in peers}, {p: [got[p]] for p in peers})
+        if r > 0:
+            e.peer_attach(0, got[r - 1])
+        if r < w - 1:
+            e.peer_attach(1, got[r + 1])
+
+    def _gather_counts(self):
+        """Replicates every rank's per-plane counts, and (two more words) where its owned slots are: a rank's
+        left neighbour's own_first + own_count is where that neighbour's right-ghost slots begin."""
+        tail = getattr(self.e, "layout_tail", lambda: [0, 0])()
+        allv = self.c.allgather_counts(np.concatenate([np.asarray(self.e.plane_counts(), np.int64), np.asarray(tail, np.int64)]))
+        self.counts = allv[:, :-2]
+        if self.rank > 0:
+            self.left_peer_tail = int(allv[self.rank - 1, -2] + allv[self.rank - 1, -1])
 
     # -- one step
     def _xchg(self, left_send, left_recv, right_send, right_recv):
@@ -423,7 +485,9 @@ class SlabSimulator:
         e.begin(st)
         lay = e.grid()
         self._m("keys_sort_layout")
-        self.counts = self.c.allgather_counts(e.plane_counts())
+        self._gather_counts()
+        if self.fused:
+            e.peer_set_offset(self.left_peer_tail if r > 0 else 0)
         self._m("count_allgather")
         self._raise_flags(lay.flags)
         # 3. Jacobi iterations with ghost refreshes
@@ -449,6 +513,9 @@ class SlabSimulator:
     def _halo(self, what):
         if self.world == 1:
             return
+        if self.fused:      # the pass kernel already stored the values into the neighbours' ghost slots
+            self.e.halo_sync()
+            return
         sl, rl, sr, rr = self.e.halo(what)
         self._xchg(sl, rl, sr, rr)
 
@@ -462,6 +529,8 @@ class SlabSimulator:
         if f & SLAB_FLAG_MIGRATION:
             raise SlabError("rank %d: a particle travelled more than margin=%d planes in one step; results are "
                             "not exact — raise `margin`" % (self.rank, self.margin))
+        if f & SLAB_FLAG_TIMEOUT:
+            raise SlabError("rank %d: a neighbour's halo completion flag did not arrive (fused halo handshake timed out)" % self.rank)
         if f & SLAB_FLAG_GHOST:
             raise SlabError("rank %d: a particle drifted beyond the %d ghost planes during the Jacobi iterations; "
                             "results are not exact — raise `ghost`" % (self.rank, self.ghost))

@@ -26,6 +26,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     replan = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    fused = (sys.argv[3] == "fused") if len(sys.argv) > 3 else False
     origin, n3 = (0.2, 0.2, 0.2), (128, 32, 64)
     ulim, llim = np.asarray((12.8, 2.0, 4.8), np.float32), np.zeros(3, np.float32)
     pos, vel, iid = pbf.scene_block_host(origin, n3)
@@ -36,7 +37,8 @@ def main():
     gpos, gvel, giid, gplane = pos[order].copy(), vel[order].copy(), iid[order].copy(), c[0][order]
 
     eng = slab.GpuEngine(pbf, p, ulim, llim, len(giid), device_index=local)
-    sim = slab.SlabSimulator(eng, slab.TorchComm(dist, device=dev), p.niter, dims[0], ghost=2, margin=4, replan_every=replan)
+    sim = slab.SlabSimulator(eng, slab.TorchComm(dist, device=dev), p.niter, dims[0], ghost=2, margin=4, replan_every=replan,
+                             fused_halo=fused)
     sim.plan_initial(np.bincount(gplane, minlength=dims[0]))
     if replan:
         sim.bounds = [0] + [sim.min_width * r for r in range(1, world)] + [dims[0]]   # lopsided on purpose
@@ -71,8 +73,8 @@ def main():
         torch.cuda.synchronize()
         ok = (np.array_equal(got[2], d_iid.cpu().numpy()) and np.array_equal(got[0], d[0].cpu().numpy())
               and np.array_equal(got[1], d[2].cpu().numpy()))
-        print("slab_nccl_check world=%d steps=%d particles=%d per-rank=%s bounds %s -> %s messages/step=%.1f : %s"
-              % (world, steps, n, n_all, first_bounds, list(sim.bounds), sim.messages / steps, "BIT-EXACT" if ok else "MISMATCH"), flush=True)
+        print("slab_nccl_check halo=%s world=%d steps=%d particles=%d per-rank=%s bounds %s -> %s messages/step=%.1f : %s"
+              % ("fused-p2p" if fused else "nccl", world, steps, n, n_all, first_bounds, list(sim.bounds), sim.messages / steps, "BIT-EXACT" if ok else "MISMATCH"), flush=True)
         rc = 0 if ok else 1
     else:
         dist.send(sp.contiguous(), 0); dist.send(sv.contiguous(), 0); dist.send(si.contiguous(), 0)
