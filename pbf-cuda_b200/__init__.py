@@ -38,8 +38,8 @@ EXPORTS = (
     "pbf_scene_block_device", "pbf_scene_block_host", "pbf_last_error", "pbf_version",
     "pbf_slab_begin", "pbf_slab_get_layout", "pbf_slab_plane_counts", "pbf_stage_lambda", "pbf_stage_delta_p",
     "pbf_slab_halo", "pbf_slab_flags", "pbf_slab_sort_state", "pbf_scene_block_slice_device",
-    "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach", "pbf_slab_peer_set_offset",
-    "pbf_slab_halo_sync",
+    "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
+    "pbf_slab_halo_sync", "pbf_slab_register_state",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
@@ -69,7 +69,7 @@ class SlabStep(C.Structure):
     """pbf_slab_step (include/pbf.h): one rank's view of one step of the x-slab decomposition."""
     _fields_ = [("x_begin", C.c_int32), ("x_end", C.c_int32), ("ghost", C.c_int32), ("has_left", C.c_int32),
                 ("has_right", C.c_int32), ("n_own", C.c_int64), ("m_left", C.c_int64), ("m_right", C.c_int64),
-                ("send_left_end", C.c_int64), ("send_right_begin", C.c_int64)]
+                ("send_left_end", C.c_int64), ("send_right_begin", C.c_int64), ("pull_left_first", C.c_int64)]
 
 
 class SlabLayout(C.Structure):
@@ -81,8 +81,8 @@ class SlabLayout(C.Structure):
 
 class SlabPeerInfo(C.Structure):
     """pbf_slab_peer_info (include/pbf.h): a rank's solver arrays as CUDA IPC handles / raw pointers."""
-    _fields_ = [("ipc", (C.c_ubyte * 64) * 4), ("ptr", C.c_uint64 * 4), ("pid", C.c_int64), ("device", C.c_int32),
-                ("reserved", C.c_int32)]
+    _fields_ = [("ipc", (C.c_ubyte * 64) * 9), ("ptr", C.c_uint64 * 9), ("pid", C.c_int64), ("device", C.c_int32),
+                ("has_state", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -142,9 +142,9 @@ _lib.pbf_scene_block_slice_device.argtypes = [_f3, C.POINTER(C.c_int32), C.c_flo
                                               C.c_int32, _vp, _vp, _vp, _vp]
 _lib.pbf_scene_block_slice_host.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, C.c_int32,
                                             C.c_int32, _vp, _vp, _vp]
+_lib.pbf_slab_register_state.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
 _lib.pbf_slab_peer_export.argtypes = [_vp, C.POINTER(SlabPeerInfo)]
 _lib.pbf_slab_peer_attach.argtypes = [_vp, C.c_int, C.POINTER(SlabPeerInfo)]
-_lib.pbf_slab_peer_set_offset.argtypes = [_vp, _i64]
 _lib.pbf_slab_halo_sync.argtypes = [_vp]
 _lib.pbf_last_error.restype = C.c_char_p
 _lib.pbf_version.restype = C.c_char_p
@@ -331,6 +331,9 @@ class Simulator:
         _check(_lib.pbf_slab_halo(self._h, int(what), *[C.byref(q) for q in p]))
         return tuple(q.value or 0 for q in p)
 
+    def slab_register_state(self, pos_a, pos_b, vel_a, vel_b, iid):
+        _check(_lib.pbf_slab_register_state(self._h, _ptr(pos_a), _ptr(pos_b), _ptr(vel_a), _ptr(vel_b), _ptr(iid)))
+
     def slab_peer_export(self):
         info = SlabPeerInfo()
         _check(_lib.pbf_slab_peer_export(self._h, C.byref(info)))
@@ -342,9 +345,6 @@ class Simulator:
         else:
             info = SlabPeerInfo.from_buffer_copy(info_bytes)
             _check(_lib.pbf_slab_peer_attach(self._h, int(side), C.byref(info)))
-
-    def slab_peer_set_offset(self, left_peer_first_right_ghost_slot):
-        _check(_lib.pbf_slab_peer_set_offset(self._h, int(left_peer_first_right_ghost_slot)))
 
     def slab_halo_sync(self):
         _check(_lib.pbf_slab_halo_sync(self._h))

@@ -116,11 +116,15 @@ struct pbf_sim {
         float4* x[2] = {nullptr, nullptr};
         float4* xl = nullptr;
         uint32_t* sync = nullptr;
-        void* ipc_base[4] = {nullptr, nullptr, nullptr, nullptr};  // opened IPC mappings to close
+        float* state[4] = {nullptr, nullptr, nullptr, nullptr};    // pos A, pos B, vel A, vel B (if registered)
+        uint32_t* iid = nullptr;
+        void* ipc_base[9] = {};                                    // opened IPC mappings to close
     } peer[2];
-    uint32_t* sync_words = nullptr;   // device: [0] raised by the left neighbour, [1] by the right one
-    int64_t peer_left_offset = 0;
-    bool peer_offset_valid = false;
+    float* state[4] = {nullptr, nullptr, nullptr, nullptr};        // my registered pos A, pos B, vel A, vel B
+    uint32_t* state_iid = nullptr;
+    uint32_t state_seq = 0;          // handshake number of my neighbours' "state complete" signal to wait for
+    uint32_t* sync_words = nullptr;   // device: [0] raised by the left neighbour, [1] by the right one,
+                                      // [2..3] int64 published by the left neighbour: its first right-ghost slot
     uint32_t halo_seq = 0;
     uint64_t halo_timeout_ns = 10ull * 1000 * 1000 * 1000;
 
@@ -245,6 +249,8 @@ void free_all(pbf_sim* s) {
 }  // namespace
 
 extern "C" {
+
+static int peers_signal(pbf_sim* s);
 
 const char* pbf_last_error(void) { return g_err; }
 const char* pbf_version(void) { return "pbf-cuda_b200 0.1 (sm_100a)"; }
@@ -431,8 +437,20 @@ static int slab_learn_layout(pbf_sim* s) {
     if (g.nxl + 1 > s->plane_capacity) return fail(PBF_ERR_CAPACITY, "slab stores %d planes, handle holds %lld", g.nxl, (long long)s->plane_capacity - 1);
     CUDA_TRY(launch_plane_table(s->pairs[s->sorted_buf], s->n, s->plane_dev, g, s->stream, &s->launches));
     CUDA_TRY(cudaMemcpyAsync(s->plane_host, s->plane_dev, (size_t)(g.nxl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
     const pbf_slab_step& sl = s->slab;
+    if (s->peer[0].on || s->peer[1].on) {
+        // fused halo: device to device, tell the right neighbour where my right-ghost slots begin (the
+        // first slot behind my owned planes) — its lambda pass pushes there — and exchange a handshake so
+        // that nobody pushes before the word has arrived. No host is involved.
+        s->halo_seq++;
+        CUDA_TRY(launch_halo_publish(s->plane_dev + s->ghost_left + (sl.x_end - sl.x_begin),
+                                     s->peer[1].on ? (int64_t*)(s->peer[1].sync + 2) : nullptr,
+                                     s->peer[0].on ? s->peer[0].sync + 1 : nullptr, s->peer[1].on ? s->peer[1].sync + 0 : nullptr,
+                                     s->halo_seq, s->stream, &s->launches));
+        CUDA_TRY(launch_halo_wait(s->peer[0].on ? s->sync_words + 0 : nullptr, s->peer[1].on ? s->sync_words + 1 : nullptr,
+                                  s->halo_seq, s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     const int64_t* ps = s->plane_host;
     const int gl = s->ghost_left, nx = sl.x_end - sl.x_begin;
     const int gw_l = sl.has_left ? (sl.ghost < nx ? sl.ghost : nx) : 0;   // owned planes a neighbour mirrors
@@ -458,14 +476,17 @@ static int slab_learn_layout(pbf_sim* s) {
 static int make_push(pbf_sim* s, const float4* a, HaloPush* hp) {
     *hp = HaloPush();
     if (!s->slab_on || (!s->peer[0].on && !s->peer[1].on)) return PBF_OK;
-    if (!s->layout_valid || !s->peer_offset_valid)
-        return fail(PBF_ERR_STATE, "fused halo: pbf_slab_peer_set_offset must follow pbf_slab_get_layout every step");
+    if (!s->layout_valid) return fail(PBF_ERR_STATE, "fused halo: no slab layout");
     const pbf_slab_layout& L = s->layout;
     for (int side = 0; side < 2; side++) {
         const pbf_sim::Peer& pr = s->peer[side];
         if (!pr.on) continue;
         float4* dst = a == s->x[0] ? pr.x[0] : a == s->x[1] ? pr.x[1] : pr.xl;
-        if (side == 0 && L.send_left_count > 0) { hp->left = dst + s->peer_left_offset; hp->left_count = L.send_left_count; }
+        if (side == 0 && L.send_left_count > 0) {
+            hp->left = dst;
+            hp->left_tail = (const int64_t*)(s->sync_words + 2);
+            hp->left_count = L.send_left_count;
+        }
         if (side == 1 && L.send_right_count > 0) { hp->right = dst; hp->right_first = L.own_count - L.send_right_count; }
     }
     return PBF_OK;
@@ -488,7 +509,6 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
     s->si.n_own = n;
     s->n_local = n; s->own_first = 0; s->own_count = n;
     s->layout_valid = false;
-    s->peer_offset_valid = false;
     s->cur = 0;
     s->iters_done = 0;
     s->pos0_in_npos = false;
@@ -584,6 +604,12 @@ int pbf_stage_correct_velocity(pbf_sim* s) {
 int pbf_stage_end(pbf_sim* s) {
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
     s->stage = ST_IDLE;
+    // fused mode: tell the neighbours that this step's state is complete — they pull from it next step
+    if (s->slab_on && s->state_iid && (s->peer[0].on || s->peer[1].on)) {
+        int rc = peers_signal(s);
+        if (rc) return rc;
+        s->state_seq = s->halo_seq;
+    }
     return PBF_OK;
 }
 
@@ -651,6 +677,26 @@ int pbf_slab_begin(pbf_sim* s, const pbf_slab_step* st, float* pos, float* npos,
     si.need_left_below = st->has_left ? st->x_begin + st->ghost : INT32_MIN;
     si.need_right_from = st->has_right ? st->x_end - st->ghost : INT32_MAX;
     si.flags = s->flags_dev;
+    // fused mode: pull the neighbours' raw particles out of their state arrays (peer memory)
+    if (s->state_iid && (s->peer[0].on || s->peer[1].on) && (st->m_left > 0 || st->m_right > 0)) {
+        const int which = pos == s->state[0] ? 0 : pos == s->state[1] ? 1 : -1;
+        if (which < 0 || vel != s->state[2 + which] || iid != s->state_iid)
+            return fail(PBF_ERR_INVALID, "fused slab step: pos / vel / iid are not the registered state arrays");
+        CUDA_TRY(launch_halo_wait(s->peer[0].on && st->m_left > 0 ? s->sync_words + 0 : nullptr,
+                                  s->peer[1].on && st->m_right > 0 ? s->sync_words + 1 : nullptr, s->state_seq,
+                                  s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
+        struct { int side; int64_t src, dst, cnt; } pull[2] = {{0, st->pull_left_first, st->n_own, st->m_left},
+                                                                {1, 0, st->n_own + st->m_left, st->m_right}};
+        for (auto& q : pull) {
+            if (q.cnt <= 0) continue;
+            const pbf_sim::Peer& pr = s->peer[q.side];
+            if (!pr.on || !pr.iid) return fail(PBF_ERR_STATE, "fused slab step: neighbour %d has no registered state attached", q.side);
+            CUDA_TRY(cudaMemcpyAsync(pos + 3 * q.dst, pr.state[which] + 3 * q.src, (size_t)q.cnt * 12, cudaMemcpyDefault, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(vel + 3 * q.dst, pr.state[2 + which] + 3 * q.src, (size_t)q.cnt * 12, cudaMemcpyDefault, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(iid + q.dst, pr.iid + q.src, (size_t)q.cnt * 4, cudaMemcpyDefault, s->stream));
+            s->launches += 3;
+        }
+    }
     return PBF_OK;
 }
 
@@ -697,13 +743,21 @@ int pbf_slab_halo(pbf_sim* s, int what, void** send_left, void** recv_left, void
     return PBF_OK;
 }
 
+int pbf_slab_register_state(pbf_sim* s, float* pos_a, float* pos_b, float* vel_a, float* vel_b, uint32_t* iid) {
+    if (!s || !pos_a || !pos_b || !vel_a || !vel_b || !iid) return fail(PBF_ERR_INVALID, "null argument");
+    s->state[0] = pos_a; s->state[1] = pos_b; s->state[2] = vel_a; s->state[3] = vel_b;
+    s->state_iid = iid;
+    return PBF_OK;
+}
+
 int pbf_slab_peer_export(pbf_sim* s, pbf_slab_peer_info* out) {
     if (!s || !out) return fail(PBF_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(s->device));
     memset(out, 0, sizeof(*out));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "pbf_slab_peer_info::ipc holds CUDA IPC handles");
-    void* arr[4] = {s->x[0], s->x[1], s->xl, s->sync_words};
-    for (int k = 0; k < 4; k++) {
+    void* arr[9] = {s->x[0], s->x[1], s->xl, s->sync_words, s->state[0], s->state[1], s->state[2], s->state[3], s->state_iid};
+    out->has_state = s->state_iid != nullptr;
+    for (int k = 0; k < (out->has_state ? 9 : 4); k++) {
         out->ptr[k] = (uint64_t)(uintptr_t)arr[k];
         cudaIpcMemHandle_t h;
         if (cudaIpcGetMemHandle(&h, arr[k]) == cudaSuccess) memcpy(out->ipc[k], &h, 64);
@@ -722,7 +776,8 @@ int pbf_slab_peer_attach(pbf_sim* s, int side, const pbf_slab_peer_info* peer) {
         if (b) { cudaIpcCloseMemHandle(b); b = nullptr; }
     pr = pbf_sim::Peer();
     if (!peer) return PBF_OK;   // detach
-    void* arr[4] = {nullptr, nullptr, nullptr, nullptr};
+    const int na = peer->has_state ? 9 : 4;
+    void* arr[9] = {};
     if (peer->pid == (int64_t)getpid()) {
         if (peer->device != s->device) {   // another device of this process: plain peer access
             cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
@@ -730,9 +785,9 @@ int pbf_slab_peer_attach(pbf_sim* s, int side, const pbf_slab_peer_info* peer) {
                 return fail(PBF_ERR_CUDA, "no peer access from device %d to %d: %s", s->device, peer->device, cudaGetErrorString(e));
             cudaGetLastError();
         }
-        for (int k = 0; k < 4; k++) arr[k] = (void*)(uintptr_t)peer->ptr[k];
+        for (int k = 0; k < na; k++) arr[k] = (void*)(uintptr_t)peer->ptr[k];
     } else {
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < na; k++) {
             cudaIpcMemHandle_t h;
             memcpy(&h, peer->ipc[k], 64);
             cudaError_t e = cudaIpcOpenMemHandle(&arr[k], h, cudaIpcMemLazyEnablePeerAccess);
@@ -744,25 +799,26 @@ int pbf_slab_peer_attach(pbf_sim* s, int side, const pbf_slab_peer_info* peer) {
         }
     }
     pr.x[0] = (float4*)arr[0]; pr.x[1] = (float4*)arr[1]; pr.xl = (float4*)arr[2]; pr.sync = (uint32_t*)arr[3];
+    for (int k = 0; k < 4; k++) pr.state[k] = (float*)arr[4 + k];
+    pr.iid = (uint32_t*)arr[8];
     pr.on = true;
     return PBF_OK;
 }
 
-int pbf_slab_peer_set_offset(pbf_sim* s, int64_t left_peer_first_right_ghost_slot) {
-    if (!s || left_peer_first_right_ghost_slot < 0) return fail(PBF_ERR_INVALID, "bad argument");
-    if (!s->slab_on || !s->layout_valid) return fail(PBF_ERR_STATE, "no slab layout: pbf_slab_begin .. pbf_stage_build_grid first");
-    s->peer_left_offset = left_peer_first_right_ghost_slot;
-    s->peer_offset_valid = true;
+// "everything I enqueued so far is complete" to both neighbours, under a fresh handshake number
+static int peers_signal(pbf_sim* s) {
+    s->halo_seq++;
+    // I am my left neighbour's RIGHT neighbour: raise its word [1]; and my right neighbour's word [0]
+    CUDA_TRY(launch_halo_signal(s->peer[0].on ? s->peer[0].sync + 1 : nullptr, s->peer[1].on ? s->peer[1].sync + 0 : nullptr,
+                                s->halo_seq, s->stream, &s->launches));
     return PBF_OK;
 }
 
 int pbf_slab_halo_sync(pbf_sim* s) {
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
     if (!s->peer[0].on && !s->peer[1].on) return PBF_OK;
-    s->halo_seq++;
-    // I am my left neighbour's RIGHT neighbour: raise its word [1]; and my right neighbour's word [0]
-    CUDA_TRY(launch_halo_signal(s->peer[0].on ? s->peer[0].sync + 1 : nullptr, s->peer[1].on ? s->peer[1].sync + 0 : nullptr,
-                                s->halo_seq, s->stream, &s->launches));
+    int rc = peers_signal(s);
+    if (rc) return rc;
     CUDA_TRY(launch_halo_wait(s->peer[0].on ? s->sync_words + 0 : nullptr, s->peer[1].on ? s->sync_words + 1 : nullptr,
                               s->halo_seq, s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
     return PBF_OK;
@@ -808,6 +864,10 @@ int pbf_slab_sort_state(pbf_sim* s, int32_t x_begin, int32_t x_end, int32_t has_
                     (long long)(n - s->layout.own_count), (long long)n, x_begin, x_end);
     CUDA_TRY(launch_gather_state(s->pairs[s->sorted_buf], pos, vel, iid, npos, nvel, s->iid_sorted, n, s->stream, &s->launches));
     CUDA_TRY(cudaMemcpyAsync(iid, s->iid_sorted, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->stream));
+    if (s->state_iid && (s->peer[0].on || s->peer[1].on)) {   // fused mode: the sorted state is what neighbours pull from
+        if ((rc = peers_signal(s))) return rc;
+        s->state_seq = s->halo_seq;
+    }
     return PBF_OK;
 }
 

@@ -91,13 +91,15 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 // needs no copy kernel and no NCCL call, only a flag handshake (slab.cu). `t` below is the
 // particle's index among the owned slots.
 struct HaloPush {
-    float4* left = nullptr;    // left peer's array, already offset to its first right-ghost slot
-    float4* right = nullptr;   // right peer's array, offset to its first left-ghost slot (slot 0)
+    float4* left = nullptr;    // left peer's array (its slot 0)
+    float4* right = nullptr;   // right peer's array: its left-ghost slots start at slot 0
+    const int64_t* left_tail = nullptr;  // local word the left peer publishes after its sort: the slot
+                                         // where its right-ghost particles begin (own_first + own_count)
     int64_t left_count = 0;    // owned t in [0, left_count) are mirrored by the left peer
     int64_t right_first = 0;   // owned t in [right_first, n) are mirrored by the right peer
 };
 __device__ __forceinline__ void halo_push(const HaloPush& hp, int64_t t, const float4 v) {
-    if (hp.left && t < hp.left_count) hp.left[t] = v;
+    if (hp.left && t < hp.left_count) hp.left[*hp.left_tail + t] = v;
     if (hp.right && t >= hp.right_first) hp.right[t - hp.right_first] = v;
 }
 
@@ -154,6 +156,10 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
 // `timeout_ns` and raise PBF_SLAB_FLAG_TIMEOUT instead of hanging the device.
 cudaError_t launch_halo_signal(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq, cudaStream_t st,
                                int64_t* launches);
+// the same signal, after first publishing *tail_src (a device word: where this rank's right-ghost
+// slots begin) into the right neighbour's memory
+cudaError_t launch_halo_publish(const int64_t* tail_src, int64_t* peer_right_tail, uint32_t* peer_word_left,
+                                uint32_t* peer_word_right, uint32_t seq, cudaStream_t st, int64_t* launches);
 cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
                              uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches);
 cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,

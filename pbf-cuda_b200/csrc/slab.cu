@@ -48,7 +48,9 @@ gather_state_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__
 // tells both neighbours "my pushes of refresh #seq are complete" and waits for theirs. Both are
 // one-thread kernels in stream order: the signal runs after the pushing kernel has retired (its
 // remote stores are performed), the wait blocks the stream until the neighbours' words arrive.
-__global__ void halo_signal_kernel(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq) {
+__global__ void halo_signal_kernel(const int64_t* tail_src, int64_t* peer_right_tail, uint32_t* peer_word_left,
+                                   uint32_t* peer_word_right, uint32_t seq) {
+    if (peer_right_tail) *(volatile int64_t*)peer_right_tail = *tail_src;
     __threadfence_system();
     if (peer_word_left) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_word_left), "r"(seq) : "memory");
     if (peer_word_right) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_word_right), "r"(seq) : "memory");
@@ -87,7 +89,15 @@ __global__ void halo_wait_kernel(const uint32_t* word_left, const uint32_t* word
 cudaError_t launch_halo_signal(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq, cudaStream_t st,
                                int64_t* launches) {
     if (!peer_word_left && !peer_word_right) return cudaSuccess;
-    halo_signal_kernel<<<1, 1, 0, st>>>(peer_word_left, peer_word_right, seq);
+    halo_signal_kernel<<<1, 1, 0, st>>>(nullptr, nullptr, peer_word_left, peer_word_right, seq);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_publish(const int64_t* tail_src, int64_t* peer_right_tail, uint32_t* peer_word_left,
+                                uint32_t* peer_word_right, uint32_t seq, cudaStream_t st, int64_t* launches) {
+    if (!peer_word_left && !peer_word_right) return cudaSuccess;
+    halo_signal_kernel<<<1, 1, 0, st>>>(tail_src, peer_right_tail, peer_word_left, peer_word_right, seq);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

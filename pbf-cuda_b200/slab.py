@@ -101,7 +101,13 @@ def exchange_plan(counts, old, new, rank, reach):
         m_right = int(np.sum(counts[rank + 1][old[rank + 1]:last]))
         if new[rank + 1] + reach > old[rank + 2]:
             raise SlabError("plan moves boundary %d beyond the right neighbour's slab" % (rank + 1))
-    return dict(send_left_end=send_left_end, send_right_begin=send_right_begin, m_left=m_left, m_right=m_right)
+    # (fused mode pulls instead of receiving: the left neighbour's range starts at ITS send_right_begin)
+    pull_left_first = 0
+    if rank > 0:
+        off_l = np.concatenate([[0], np.cumsum(counts[rank - 1])])
+        pull_left_first = int(off_l[clip(new[rank] - reach, old[rank - 1], old[rank])])
+    return dict(send_left_end=send_left_end, send_right_begin=send_right_begin, m_left=m_left, m_right=m_right,
+                pull_left_first=pull_left_first)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -142,11 +148,22 @@ class TorchComm:
     def allgather_counts(self, counts):
         import torch
         mine = torch.from_numpy(np.ascontiguousarray(counts, np.int64))
-        if self.device is not None:
-            mine = mine.to(self.device)
-        out = torch.empty(self.world * mine.numel(), dtype=torch.int64, device=mine.device)
-        self.dist.all_gather_into_tensor(out, mine, group=self.group)
-        return out.cpu().numpy().reshape(self.world, -1)
+        if self.device is None:
+            out = torch.empty(self.world * mine.numel(), dtype=torch.int64)
+            self.dist.all_gather_into_tensor(out, mine, group=self.group)
+            return out.numpy().reshape(self.world, -1)
+        # on a stream of its own: the collective and the host's wait for it do not queue behind the pass
+        # kernels already enqueued on the compute stream
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._side):
+            mine = mine.to(self.device, non_blocking=True)
+            out = torch.empty(self.world * mine.numel(), dtype=torch.int64, device=self.device)
+            self.dist.all_gather_into_tensor(out, mine, group=self.group)
+            host = out.cpu()
+        return host.numpy().reshape(self.world, -1)
+
+    _side = None
 
 
 class SingleComm:
@@ -249,9 +266,16 @@ class GpuEngine:
         self.capacity = int(capacity)
         self.sim = pbf.Simulator(params, ulim, llim, self.capacity, device=device_index)
         self.stream = stream
-        f3 = lambda: torch.zeros((self.capacity, 3), dtype=torch.float32, device=self.dev)
-        self.pos, self.npos, self.vel, self.nvel = f3(), f3(), f3(), f3()
-        self.iid = torch.zeros(self.capacity, dtype=torch.int32, device=self.dev)
+        # the five state arrays are plain cudaMalloc allocations (not sub-blocks of torch's caching allocator):
+        # as allocation bases they can be handed to neighbour processes through CUDA IPC (fused mode)
+        self._bufs = [pbf.DeviceBuffer(self.capacity * 12, device_index) for _ in range(4)] + \
+                     [pbf.DeviceBuffer(self.capacity * 4, device_index)]
+        v3 = lambda b: torch.as_tensor(_DevView(b.ptr, (self.capacity, 3)), device=self.dev)
+        self.pos, self.npos, self.vel, self.nvel = (v3(b) for b in self._bufs[:4])
+        self.iid = torch.as_tensor(_DevView(self._bufs[4].ptr, (self.capacity,), "<i4"), device=self.dev)
+        for t in (self.pos, self.npos, self.vel, self.nvel, self.iid):
+            t.zero_()
+        self.sim.slab_register_state(self.pos, self.npos, self.vel, self.nvel, self.iid)
         self.n_own = 0
         self.layout = None
         self.planes = self.sim.grid_dim()[0]
@@ -328,15 +352,8 @@ class GpuEngine:
     def peer_attach(self, side, info_tensor):
         self.sim.slab_peer_attach(side, None if info_tensor is None else bytes(info_tensor.cpu().numpy().tobytes()))
 
-    def peer_set_offset(self, slot):
-        self.sim.slab_peer_set_offset(slot)
-
     def halo_sync(self):
         self.sim.slab_halo_sync()
-
-    def layout_tail(self):
-        L = self.layout
-        return [0, self.n_own] if L is None else [int(L.own_first), int(L.own_count)]
 
     def flags(self):
         return self.sim.slab_flags()
@@ -354,6 +371,8 @@ class GpuEngine:
 
     def close(self):
         self.sim.close()
+        for b in self._bufs:
+            b.free()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -381,7 +400,6 @@ class SlabSimulator:
         # fused_halo: the ghost refreshes are peer-memory stores issued by the pass kernels themselves plus a
         # flag handshake (include/pbf.h "Fused halo refresh"); otherwise one send/recv pair per side through comm
         self.fused = bool(fused_halo) and comm.world > 1
-        self.left_peer_tail = None
         self.bounds = None
         self.counts = None
         self.steps = 0
@@ -417,13 +435,9 @@ class SlabSimulator:
             e.peer_attach(1, got[r + 1])
 
     def _gather_counts(self):
-        """Replicates every rank's per-plane counts, and (two more words) where its owned slots are: a rank's
-        left neighbour's own_first + own_count is where that neighbour's right-ghost slots begin."""
-        tail = getattr(self.e, "layout_tail", lambda: [0, 0])()
-        allv = self.c.allgather_counts(np.concatenate([np.asarray(self.e.plane_counts(), np.int64), np.asarray(tail, np.int64)]))
-        self.counts = allv[:, :-2]
-        if self.rank > 0:
-            self.left_peer_tail = int(allv[self.rank - 1, -2] + allv[self.rank - 1, -1])
+        """Replicates every rank's per-plane particle counts (sizes of the next step's raw exchange, input of
+        the planner)."""
+        self.counts = self.c.allgather_counts(np.asarray(self.e.plane_counts(), np.int64))
 
     # -- one step
     def _xchg(self, left_send, left_recv, right_send, right_recv):
@@ -471,35 +485,40 @@ class SlabSimulator:
         n_own = e.n_own
         assert n_own == int(self.counts[r].sum())
         m_l, m_r = xp["m_left"], xp["m_right"]
-        # 1. raw state of the planes around each boundary
-        self._xchg(e.raw_views(0, xp["send_left_end"]), e.raw_views(n_own, n_own + m_l),
-                   e.raw_views(xp["send_right_begin"], n_own), e.raw_views(n_own + m_l, n_own + m_l + m_r))
-        self._m("raw_exchange")
+        # 1. raw state of the planes around each boundary: sent / received through comm — or, fused, pulled by
+        #    pbf_slab_begin straight out of the neighbours' state arrays (peer-memory copies, no collective)
+        if not self.fused:
+            self._xchg(e.raw_views(0, xp["send_left_end"]), e.raw_views(n_own, n_own + m_l),
+                       e.raw_views(xp["send_right_begin"], n_own), e.raw_views(n_own + m_l, n_own + m_l + m_r))
+            self._m("raw_exchange")
         st = SlabStep(x_begin=new[r], x_end=new[r + 1], ghost=self.ghost, has_left=int(r > 0), has_right=int(r < w - 1),
                       n_own=n_own, m_left=m_l, m_right=m_r, send_left_end=xp["send_left_end"],
-                      send_right_begin=xp["send_right_begin"])
-        # 2. keys, one stable sort, layout (the step's one host synchronisation). While the device is
-        #    still idle from it, replicate the new per-plane counts: they size the next step's messages
-        #    and feed the planner, and fetching them here keeps the END of the step free of any sync, so
-        #    the host runs ahead into the next step while the device works through the passes below.
+                      send_right_begin=xp["send_right_begin"], pull_left_first=xp["pull_left_first"])
+        # 2. keys, one stable sort, layout (the step's one host synchronisation on the compute stream)
         e.begin(st)
+        if self.fused:
+            self._m("raw_exchange")
         lay = e.grid()
         self._m("keys_sort_layout")
-        self._gather_counts()
-        if self.fused:
-            e.peer_set_offset(self.left_peer_tail if r > 0 else 0)
-        self._m("count_allgather")
         self._raise_flags(lay.flags)
-        # 3. Jacobi iterations with ghost refreshes
-        for _ in range(self.niter):
+        # 3. Jacobi iterations with ghost refreshes. Behind the FIRST lambda pass — so that the device has
+        #    work while the host waits — the new per-plane counts are replicated (on the transport's own
+        #    stream): they size the next step's raw exchange and feed the planner. Fetching them here keeps
+        #    the END of the step free of any synchronisation: the host runs ahead into the next step.
+        for it in range(self.niter):
             e.lambda_pass()
             self._m("lambda")
+            if it == 0:
+                self._gather_counts()
+                self._m("count_allgather")
             self._halo(HALO_LAMBDA)
             self._m("halo")
             e.delta_p_pass()
             self._m("delta_p")
             self._halo(HALO_POSITION)
             self._m("halo")
+        if self.niter == 0:
+            self._gather_counts()
         e.update_velocity()
         self._m("update_velocity")
         self._halo(HALO_VELOCITY)
