@@ -216,8 +216,8 @@ def run_product(args, rank, world, dist):
                 "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved": round(step_gbs, 2),
                                "frac": round(step_gbs / peak, 5)},
                 "note": "the lambda / XSPH sweeps are FP32-issue bound, not HBM bound (SURVEY.md App. D, DESIGN.md 5): "
-                        "ncu shows ~81% issue-slot utilisation at 15% DRAM throughput; the delta-p pass replays the "
-                        "lambda pass's neighbour list and IS HBM bound (see delta_p below)",
+                        "ncu shows 74% issue-slot utilisation at 19% DRAM throughput; the delta-p pass replays the "
+                        "lambda pass's neighbour list (and evaluates the exact powf): 53% issue, 27% DRAM (see delta_p below)",
                 "delta_p": {"kernel_ms": round(kacc["delta_p"], 4), "traffic": TRAFFIC["delta_p"],
                             "dram_GBps_from_traffic": round(TRAFFIC["delta_p"] / (kacc["delta_p"] * 1e-3) / 1e9, 1)}}
 
