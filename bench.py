@@ -459,7 +459,8 @@ def run_product_slab(args, rank, world, dist):
                                       "%d planes per side, then (2*niter+1) ghost refreshes %s; ghost=%d margin=%d replan_every=%d"
                                       % (world, ghost + margin,
                                          "FUSED into the pass kernels (stores into the neighbour's ghost slots over NVLink peer memory "
-                                         "+ a flag handshake, no collective)" if args.halo == "fused" else "as NCCL send/recv of float4 ranges",
+                                         "+ a flag handshake, no collective)" if sim.fused else "as NCCL send/recv of float4 ranges" +
+                                         (" [%s]" % sim.fused_note if sim.fused_note else ""),
                                          ghost, margin, args.replan_every),
                        "slab_boundaries": [int(b) for b in sim.bounds],
                        "messages_per_step_rank0": round(msgs / args.steps, 1), "bytes_sent_per_step_rank0": int(sent / args.steps),

@@ -39,7 +39,8 @@ EXPORTS = (
     "pbf_slab_begin", "pbf_slab_get_layout", "pbf_slab_plane_counts", "pbf_stage_lambda", "pbf_stage_delta_p",
     "pbf_slab_halo", "pbf_slab_flags", "pbf_slab_sort_state", "pbf_scene_block_slice_device",
     "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
-    "pbf_slab_halo_sync", "pbf_slab_register_state",
+    "pbf_slab_halo_sync", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
+    "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
@@ -142,6 +143,13 @@ _lib.pbf_scene_block_slice_device.argtypes = [_f3, C.POINTER(C.c_int32), C.c_flo
                                               C.c_int32, _vp, _vp, _vp, _vp]
 _lib.pbf_scene_block_slice_host.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float, C.c_uint32, C.c_uint32, C.c_int32,
                                             C.c_int32, _vp, _vp, _vp]
+_lib.pbf_slab_adopt_state.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _i64,
+                                      C.POINTER(_i64), _vp]
+_lib.pbf_stream_create.argtypes = [C.c_int, C.POINTER(_vp)]
+_lib.pbf_stream_destroy.argtypes = [C.c_int, _vp]
+_lib.pbf_stream_sync.argtypes = [C.c_int, _vp]
+_lib.pbf_copy_d2h_async.argtypes = [_vp, _vp, _i64, _vp]
+_lib.pbf_device_count.argtypes = [C.POINTER(C.c_int)]
 _lib.pbf_slab_register_state.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
 _lib.pbf_slab_peer_export.argtypes = [_vp, C.POINTER(SlabPeerInfo)]
 _lib.pbf_slab_peer_attach.argtypes = [_vp, C.c_int, C.POINTER(SlabPeerInfo)]
@@ -330,6 +338,13 @@ class Simulator:
         p = [_vp() for _ in range(4)]
         _check(_lib.pbf_slab_halo(self._h, int(what), *[C.byref(q) for q in p]))
         return tuple(q.value or 0 for q in p)
+
+    def slab_adopt_state(self, x_begin, x_end, has_left, has_right, pos, npos, vel, nvel, iid, n, stream=None):
+        """Like slab_sort_state, but particles outside planes [x_begin, x_end) are dropped; returns the count kept."""
+        kept = _i64()
+        _check(_lib.pbf_slab_adopt_state(self._h, int(x_begin), int(x_end), int(bool(has_left)), int(bool(has_right)),
+                                         _ptr(pos), _ptr(npos), _ptr(vel), _ptr(nvel), _ptr(iid), int(n), C.byref(kept), stream))
+        return int(kept.value)
 
     def slab_register_state(self, pos_a, pos_b, vel_a, vel_b, iid):
         _check(_lib.pbf_slab_register_state(self._h, _ptr(pos_a), _ptr(pos_b), _ptr(vel_a), _ptr(vel_b), _ptr(iid)))

@@ -59,6 +59,16 @@ advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
     }
 }
 
+// Lazy module loading (the CUDA default) loads a kernel at its first launch, and that load can wait for
+// running kernels to finish: if the running kernel is a neighbour rank's flag wait (several ranks in one
+// process), the two deadlock until the time-out. pbf_create therefore loads every kernel up front.
+cudaError_t preload_advect_key() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, advect_key_kernel);
+    return e;
+}
+
 cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist,
                               int64_t n, int npass, const SlabInput& si, const GridConsts& g,
                               const SolverConsts& c, cudaStream_t st, int64_t* launches) {

@@ -285,6 +285,16 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (prop.major != 10) return fail(PBF_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CUDA_TRY(cudaSetDevice(device));
 
+    {   // once per device: load all kernels now, not at their first launch (preload_solver, solver.cu)
+        static bool loaded[64] = {};
+        if (device < 64 && !loaded[device]) {
+            cudaFuncAttributes fa;
+            CUDA_TRY(cudaFuncGetAttributes(&fa, extract_words_kernel));
+            CUDA_TRY(preload_advect_key()); CUDA_TRY(preload_sort()); CUDA_TRY(preload_reorder()); CUDA_TRY(preload_scene());
+            CUDA_TRY(preload_slab()); CUDA_TRY(preload_solver()); CUDA_TRY(preload_stats());
+            loaded[device] = true;
+        }
+    }
     pbf_sim* s = new (std::nothrow) pbf_sim;
     if (!s) return fail(PBF_ERR_INVALID, "out of host memory");
     s->device = device;
@@ -331,6 +341,9 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (e == cudaSuccess) { *s->flags_host = 0; e = cudaHostGetDevicePointer((void**)&s->flags_dev, s->flags_host, 0); }
     A((void**)&s->sync_words, 8 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(s->sync_words, 0, 8 * sizeof(uint32_t));
+    // (the memset runs on the legacy stream; a neighbour's first flag store comes from a non-blocking
+    //  stream and must not be overtaken by it)
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (const char* to = getenv("PBF_HALO_TIMEOUT_MS")) s->halo_timeout_ns = (uint64_t)atoll(to) * 1000000ull;
     if (e != cudaSuccess) {
         free_all(s);
@@ -443,6 +456,7 @@ static int slab_learn_layout(pbf_sim* s) {
         // first slot behind my owned planes) — its lambda pass pushes there — and exchange a handshake so
         // that nobody pushes before the word has arrived. No host is involved.
         s->halo_seq++;
+        if (getenv("PBF_HALO_TRACE")) fprintf(stderr, "[halo %p] publish+wait %u\n", (void*)s, s->halo_seq);
         CUDA_TRY(launch_halo_publish(s->plane_dev + s->ghost_left + (sl.x_end - sl.x_begin),
                                      s->peer[1].on ? (int64_t*)(s->peer[1].sync + 2) : nullptr,
                                      s->peer[0].on ? s->peer[0].sync + 1 : nullptr, s->peer[1].on ? s->peer[1].sync + 0 : nullptr,
@@ -682,6 +696,7 @@ int pbf_slab_begin(pbf_sim* s, const pbf_slab_step* st, float* pos, float* npos,
         const int which = pos == s->state[0] ? 0 : pos == s->state[1] ? 1 : -1;
         if (which < 0 || vel != s->state[2 + which] || iid != s->state_iid)
             return fail(PBF_ERR_INVALID, "fused slab step: pos / vel / iid are not the registered state arrays");
+        if (getenv("PBF_HALO_TRACE")) fprintf(stderr, "[halo %p] pull wait %u (m_left %lld m_right %lld)\n", (void*)s, s->state_seq, (long long)st->m_left, (long long)st->m_right);
         CUDA_TRY(launch_halo_wait(s->peer[0].on && st->m_left > 0 ? s->sync_words + 0 : nullptr,
                                   s->peer[1].on && st->m_right > 0 ? s->sync_words + 1 : nullptr, s->state_seq,
                                   s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
@@ -808,6 +823,7 @@ int pbf_slab_peer_attach(pbf_sim* s, int side, const pbf_slab_peer_info* peer) {
 // "everything I enqueued so far is complete" to both neighbours, under a fresh handshake number
 static int peers_signal(pbf_sim* s) {
     s->halo_seq++;
+    if (getenv("PBF_HALO_TRACE")) fprintf(stderr, "[halo %p] signal %u\n", (void*)s, s->halo_seq);
     // I am my left neighbour's RIGHT neighbour: raise its word [1]; and my right neighbour's word [0]
     CUDA_TRY(launch_halo_signal(s->peer[0].on ? s->peer[0].sync + 1 : nullptr, s->peer[1].on ? s->peer[1].sync + 0 : nullptr,
                                 s->halo_seq, s->stream, &s->launches));
@@ -833,8 +849,9 @@ int pbf_slab_flags(pbf_sim* s, uint32_t* out) {
     return PBF_OK;
 }
 
-int pbf_slab_sort_state(pbf_sim* s, int32_t x_begin, int32_t x_end, int32_t has_left, int32_t has_right,
-                        float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
+static int slab_sort_state_impl(pbf_sim* s, int32_t x_begin, int32_t x_end, int32_t has_left, int32_t has_right,
+                                float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n,
+                                int64_t* n_kept, void* stream) {
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
     pbf_slab_step st{};
     st.x_begin = x_begin; st.x_end = x_end; st.ghost = 1;
@@ -859,16 +876,33 @@ int pbf_slab_sort_state(pbf_sim* s, int32_t x_begin, int32_t x_end, int32_t has_
     CUDA_TRY(launch_sort(s->keys, sc, s->n, s->npass, s->si, &s->sorted_buf, s->stream, &s->launches));
     if ((rc = slab_learn_layout(s))) return rc;
     s->stage = ST_IDLE;
-    if (s->layout.own_count != n || s->layout.own_first != 0)
+    if (!n_kept && (s->layout.own_count != n || s->layout.own_first != 0))
         return fail(PBF_ERR_INVALID, "sort_state: %lld of %lld particles lie outside planes [%d, %d)",
                     (long long)(n - s->layout.own_count), (long long)n, x_begin, x_end);
-    CUDA_TRY(launch_gather_state(s->pairs[s->sorted_buf], pos, vel, iid, npos, nvel, s->iid_sorted, n, s->stream, &s->launches));
-    CUDA_TRY(cudaMemcpyAsync(iid, s->iid_sorted, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->stream));
+    const int64_t kept = s->layout.own_count;
+    if (n_kept) *n_kept = kept;
+    // (adopt: the owned particles are the slots [own_first, own_first + kept) of the sort; what follows
+    //  describes a state that holds exactly them, as a step's result would)
+    CUDA_TRY(launch_gather_state(s->pairs[s->sorted_buf] + s->layout.own_first, pos, vel, iid, npos, nvel, s->iid_sorted, kept, s->stream, &s->launches));
+    CUDA_TRY(cudaMemcpyAsync(iid, s->iid_sorted, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s->stream));
+    n = kept;
     if (s->state_iid && (s->peer[0].on || s->peer[1].on)) {   // fused mode: the sorted state is what neighbours pull from
         if ((rc = peers_signal(s))) return rc;
         s->state_seq = s->halo_seq;
     }
     return PBF_OK;
+}
+
+int pbf_slab_sort_state(pbf_sim* s, int32_t x_begin, int32_t x_end, int32_t has_left, int32_t has_right,
+                        float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
+    return slab_sort_state_impl(s, x_begin, x_end, has_left, has_right, pos, npos, vel, nvel, iid, n, nullptr, stream);
+}
+
+int pbf_slab_adopt_state(pbf_sim* s, int32_t x_begin, int32_t x_end, int32_t has_left, int32_t has_right,
+                         float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, int64_t* n_kept,
+                         void* stream) {
+    if (!n_kept) return fail(PBF_ERR_INVALID, "null argument");
+    return slab_sort_state_impl(s, x_begin, x_end, has_left, has_right, pos, npos, vel, nvel, iid, n, n_kept, stream);
 }
 
 int pbf_scene_block_slice_device(const float origin[3], const int32_t n[3], float spacing, uint32_t seed,
@@ -1012,6 +1046,34 @@ int pbf_copy_d2h(void* dst, const void* src, int64_t bytes) {
 int pbf_device_sync(int device) {
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaDeviceSynchronize());
+    return PBF_OK;
+}
+
+int pbf_stream_create(int device, void** stream_out) {
+    if (!stream_out) return fail(PBF_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream_out = (void*)st;
+    return PBF_OK;
+}
+int pbf_stream_destroy(int device, void* stream) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamDestroy((cudaStream_t)stream));
+    return PBF_OK;
+}
+int pbf_stream_sync(int device, void* stream) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return PBF_OK;
+}
+int pbf_copy_d2h_async(void* dst, const void* src, int64_t bytes, void* stream) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return PBF_OK;
+}
+int pbf_device_count(int* count) {
+    if (!count) return fail(PBF_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaGetDeviceCount(count));
     return PBF_OK;
 }
 

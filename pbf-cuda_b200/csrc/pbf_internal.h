@@ -176,6 +176,15 @@ cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const fl
 cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
                                   const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 
+// force-load every kernel of a translation unit (see the comment at preload_solver in solver.cu)
+cudaError_t preload_advect_key();
+cudaError_t preload_sort();
+cudaError_t preload_reorder();
+cudaError_t preload_scene();
+cudaError_t preload_slab();
+cudaError_t preload_solver();
+cudaError_t preload_stats();
+
 // scene + stats (scene.cu, stats.cu)
 cudaError_t launch_scene_block(const float origin[3], const int32_t n3[3], float spacing, uint32_t seed,
                                uint32_t first_iid, int32_t ix_begin, int32_t ix_end, float* pos, float* vel,

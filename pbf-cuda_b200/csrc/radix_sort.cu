@@ -197,6 +197,18 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
 
 }  // namespace
 
+// Lazy module loading (the CUDA default) loads a kernel at its first launch, and that load can wait for
+// running kernels to finish: if the running kernel is a neighbour rank's flag wait (several ranks in one
+// process), the two deadlock until the time-out. pbf_create therefore loads every kernel up front.
+cudaError_t preload_sort() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hist_scan_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<false>);
+    return e;
+}
+
 size_t sort_scratch_zero_bytes(int64_t n, int npass) {
     int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
     return sizeof(uint32_t) * ((size_t)MAX_PASSES * RADIX + MAX_PASSES + (size_t)npass * tiles * RADIX);

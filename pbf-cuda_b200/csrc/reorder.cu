@@ -46,6 +46,16 @@ reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
     if (s == n - 1) cell_range[e.key].y = (uint32_t)n;
 }
 
+// Lazy module loading (the CUDA default) loads a kernel at its first launch, and that load can wait for
+// running kernels to finish: if the running kernel is a neighbour rank's flag wait (several ranks in one
+// process), the two deadlock until the time-out. pbf_create therefore loads every kernel up front.
+cudaError_t preload_reorder() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, reorder_kernel);
+    return e;
+}
+
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                            float4* x0, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
                            int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,

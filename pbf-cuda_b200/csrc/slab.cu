@@ -9,6 +9,8 @@
 // sort the ghost particles sit at the two ends, the planes a neighbour needs as ITS ghosts are a
 // prefix / suffix of the owned range, and every halo refresh (lambda, positions, velocity+rho)
 // is a copy of one contiguous float4 range straight out of / into the solver's own arrays.
+#include <stdio.h>
+
 #include "pbf_internal.h"
 
 namespace pbf {
@@ -77,6 +79,7 @@ __global__ void halo_wait_kernel(const uint32_t* word_left, const uint32_t* word
         while ((int32_t)(ld_acquire_sys(w) - seq) < 0) {
             if (global_ns() - t0 > timeout_ns) {   // a dead neighbour must not hang the device
                 if (flags) atomicOr(flags, (uint32_t)PBF_SLAB_FLAG_TIMEOUT);
+                printf("pbf halo wait timed out: side %d, waiting for handshake %u, word holds %u\n", side, seq, ld_acquire_sys(w));
                 return;
             }
             __nanosleep(64);
@@ -85,6 +88,19 @@ __global__ void halo_wait_kernel(const uint32_t* word_left, const uint32_t* word
 }
 
 }  // namespace
+
+// Lazy module loading (the CUDA default) loads a kernel at its first launch, and that load can wait for
+// running kernels to finish: if the running kernel is a neighbour rank's flag wait (several ranks in one
+// process), the two deadlock until the time-out. pbf_create therefore loads every kernel up front.
+cudaError_t preload_slab() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, plane_table_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, gather_state_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, halo_signal_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, halo_wait_kernel);
+    return e;
+}
 
 cudaError_t launch_halo_signal(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq, cudaStream_t st,
                                int64_t* launches) {

@@ -341,6 +341,25 @@ neighbor_count_kernel(const float4* __restrict__ x, const uint2* __restrict__ ce
     count[i] = cnt;
 }
 
+// Lazy module loading (the CUDA default) loads a kernel at its first launch, and that load can wait for
+// running kernels to finish: if the running kernel is a neighbour rank's flag wait (several ranks in one
+// process), the two deadlock until the time-out. pbf_create therefore loads every kernel up front.
+cudaError_t preload_solver() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<true, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, update_velocity_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, neighbor_count_kernel);
+    return e;
+}
+
 static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_bytes, size_t* cnt_bytes) {

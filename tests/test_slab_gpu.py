@@ -199,3 +199,32 @@ def test_slab_over_nccl_equals_single_gpu(pbf, torch):
                             "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "slab_nccl_check.py"),
                             "8", "3", mode], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "BIT-EXACT" in r.stdout, mode + r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cpp_slab_harness_matches_single_gpu(pbf, torch, tmp_path):
+    """host/SlabSimulator.h (C++, one thread per rank, fused transport between handles of one process): 1, 2 and
+    3 ranks write the same bytes, and they are the bytes of pbf_step on the cell-sorted scene."""
+    import os
+    import subprocess
+    slab = importlib.import_module("pbf-cuda_b200.slab")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "pbf-cuda_b200", "pbf_slab_headless")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "pbf-cuda_b200"), "harness"], stdout=subprocess.DEVNULL)
+    steps, dumps = 6, {}
+    for ranks in (1, 2, 3):
+        out = str(tmp_path / ("r%d.bin" % ranks))
+        r = subprocess.run([exe, "--scene", "small", "--ranks", str(ranks), "--steps", str(steps), "--warmup", "0", "--ghost", "2",
+                            "--margin", "2", "--replan", "2", "--dump", out], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        dumps[ranks] = open(out, "rb").read()
+    assert dumps[1] == dumps[2] == dumps[3]
+    n = int(np.frombuffer(dumps[1][:4], np.int32)[0])
+    body = np.frombuffer(dumps[1][4:], np.float32)
+    pos, vel = body[:3 * n].reshape(n, 3), body[3 * n:6 * n].reshape(n, 3)
+    iid = np.frombuffer(dumps[1][4 + 24 * n:], np.uint32)
+    scene = _scene("small")
+    gpos, gvel, giid, _, _ = _sorted_state(pbf, slab, *scene, pbf.default_params().h)
+    ref = _single_gpu(pbf, torch, gpos, gvel, giid, scene[3], scene[4], steps)
+    assert n == len(giid)
+    assert np.array_equal(iid, ref[2]) and np.array_equal(pos, ref[0]) and np.array_equal(vel, ref[1])
