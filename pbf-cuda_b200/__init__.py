@@ -40,7 +40,7 @@ EXPORTS = (
     "pbf_slab_halo", "pbf_slab_flags", "pbf_slab_sort_state", "pbf_scene_block_slice_device",
     "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
     "pbf_slab_halo_sync", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
-    "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count",
+    "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count", "pbf_get_const_div_interval",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
@@ -145,6 +145,7 @@ _lib.pbf_scene_block_slice_host.argtypes = [_f3, C.POINTER(C.c_int32), C.c_float
                                             C.c_int32, _vp, _vp, _vp]
 _lib.pbf_slab_adopt_state.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _i64,
                                       C.POINTER(_i64), _vp]
+_lib.pbf_get_const_div_interval.argtypes = [_vp, _f3, _f3]
 _lib.pbf_stream_create.argtypes = [C.c_int, C.POINTER(_vp)]
 _lib.pbf_stream_destroy.argtypes = [C.c_int, _vp]
 _lib.pbf_stream_sync.argtypes = [C.c_int, _vp]
@@ -285,6 +286,11 @@ class Simulator:
 
     def set_exact_pow(self, on):
         _check(_lib.pbf_set_option_exact_pow(self._h, int(bool(on))))
+
+    def const_div_interval(self):
+        lo, hi = C.c_float(), C.c_float()
+        _check(_lib.pbf_get_const_div_interval(self._h, C.byref(lo), C.byref(hi)))
+        return float(lo.value), float(hi.value)
 
     def grid_dim(self):
         d = (C.c_int32 * 3)()

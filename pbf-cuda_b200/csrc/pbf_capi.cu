@@ -128,6 +128,10 @@ struct pbf_sim {
     uint32_t halo_seq = 0;
     uint64_t halo_timeout_ns = 10ull * 1000 * 1000 * 1000;
 
+    // verified constant division (refresh_consts)
+    bool div_verified = false;
+    float div_d = 0.f, div_rcp = 0.f, div_lo = 1.f, div_hi = 0.f;
+
     int64_t launches = 0;
     bool timing = false;
     cudaEvent_t ev[6] = {};
@@ -223,6 +227,28 @@ int refresh_consts(pbf_sim* s) {
         c.lim_lo[a] = (double)s->llim[a] + 1e-3;
     }
     c.exact_pow = s->exact_pow;
+    // division by pho0 as a verified reciprocal sequence (pbf_math.cuh div_pho0); re-verified on the
+    // device whenever pho0 changes, plain division if anything is off
+    if (!(s->div_verified && s->div_d == p.pho0)) {
+        s->div_verified = false;
+        s->div_lo = 1.f; s->div_hi = 0.f;   // empty interval: always the plain division
+        s->div_rcp = (float)(1.0 / (double)p.pho0);
+        const char* off = getenv("PBF_NO_CONST_DIV");
+        if (!(off && off[0] == '1') && p.pho0 > 0.f && p.pho0 < 3.0e38f && cudaSetDevice(s->device) == cudaSuccess) {
+            float lo = 1.f, hi = 0.f;
+            if (verify_const_div(p.pho0, s->div_rcp, &lo, &hi, nullptr) == cudaSuccess) {
+                // use it only if the verified interval is comfortably wide around the values that occur
+                if (lo <= 1e-30f && hi >= 1e30f) { s->div_lo = lo; s->div_hi = hi; }
+            } else {
+                cudaGetLastError();
+            }
+        }
+        s->div_d = p.pho0;
+        s->div_verified = true;
+    }
+    c.pho0_rcp = s->div_rcp;
+    c.div_lo = s->div_lo;
+    c.div_hi = s->div_hi;
     return PBF_OK;
 }
 
@@ -414,6 +440,11 @@ int pbf_get_lim(const pbf_sim* s, float ulim[3], float llim[3]) {
     if (!s || !ulim || !llim) return fail(PBF_ERR_INVALID, "null argument");
     memcpy(ulim, s->ulim, sizeof(float) * 3);
     memcpy(llim, s->llim, sizeof(float) * 3);
+    return PBF_OK;
+}
+int pbf_get_const_div_interval(const pbf_sim* s, float* lo, float* hi) {
+    if (!s || !lo || !hi) return fail(PBF_ERR_INVALID, "null argument");
+    *lo = s->div_lo; *hi = s->div_hi;
     return PBF_OK;
 }
 int pbf_get_grid_dim(const pbf_sim* s, int32_t dim[3]) {

@@ -70,6 +70,10 @@ struct SolverConsts {
     double lim_hi[3];  // (double)ulim - LIM_EPS            (Simulator_kernel.cuh:190-192)
     double lim_lo[3];  // (double)llim + LIM_EPS
     int32_t exact_pow; // 1: powf(w, n_corr) like the reference; 0: (w*w)^2 when n_corr == 4
+    // division by the constant pho0 without the divide sequence (pbf_math.cuh div_pho0): valid for
+    // |a| in [div_lo, div_hi], an interval VERIFIED exhaustively on the device against div.rn
+    float pho0_rcp;    // RN(1 / pho0)
+    float div_lo, div_hi;
 };
 
 // (key, source index) pair the radix sort moves; one 8-byte transaction per element.
@@ -175,6 +179,10 @@ cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const fl
                                 int64_t* launches);
 cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
                                   const GridConsts& g, const SolverConsts& c, cudaStream_t st);
+
+// stats.cu: exhaustive check of the reciprocal division sequence for divisor d over all 2^32 bit
+// patterns of the dividend; returns the verified interval of |a| around 1 (lo > hi: none)
+cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStream_t st);
 
 // force-load every kernel of a translation unit (see the comment at preload_solver in solver.cu)
 cudaError_t preload_advect_key();

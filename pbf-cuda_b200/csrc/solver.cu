@@ -173,9 +173,8 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
             const float w = poly6(r2, c);
             rho = __fadd_rn(rho, w);
             s = spiky_scale(r2, c);
-            const float gx = __fdiv_rn(__fmul_rn(dx, s), c.pho0);
-            const float gy = __fdiv_rn(__fmul_rn(dy, s), c.pho0);
-            const float gz = __fdiv_rn(__fmul_rn(dz, s), c.pho0);
+            float gx = __fmul_rn(dx, s), gy = __fmul_rn(dy, s), gz = __fmul_rn(dz, s);
+            div3_pho0(gx, gy, gz, c);
             gix = __fadd_rn(gix, gx);
             giy = __fadd_rn(giy, gy);
             giz = __fadd_rn(giz, gz);
@@ -208,9 +207,10 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
 // shared tail of the delta-p pass: divide, clamp to MAX_DP, add, clamp to the box (f64 like the reference)
 __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float ay, float az, const SolverConsts& c) {
     const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
-    const float vx = fmaxf(fminf(__fdiv_rn(ax, c.pho0), max_dp), -max_dp);
-    const float vy = fmaxf(fminf(__fdiv_rn(ay, c.pho0), max_dp), -max_dp);
-    const float vz = fmaxf(fminf(__fdiv_rn(az, c.pho0), max_dp), -max_dp);
+    div3_pho0(ax, ay, az, c);
+    const float vx = fmaxf(fminf(ax, max_dp), -max_dp);
+    const float vy = fmaxf(fminf(ay, max_dp), -max_dp);
+    const float vz = fmaxf(fminf(az, max_dp), -max_dp);
     const float qx = (float)fmax(fmin((double)__fadd_rn(p.x, vx), c.lim_hi[0]), c.lim_lo[0]);
     const float qy = (float)fmax(fmin((double)__fadd_rn(p.y, vy), c.lim_hi[1]), c.lim_lo[1]);
     const float qz = (float)fmax(fmin((double)__fadd_rn(p.z, vz), c.lim_hi[2]), c.lim_lo[2]);

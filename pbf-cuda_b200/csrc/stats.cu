@@ -2,6 +2,8 @@
 // The reference has no diagnostics (SURVEY.md section 5 "Metrics / logging: printf only"); the
 // 1000-step comparison BASELINE.json asks for needs them. Deterministic: fixed block count, fixed
 // tree order, f64 accumulation; the host adds the per-block partials in index order.
+#include <string.h>
+
 #include "pbf_internal.h"
 
 namespace pbf {
@@ -41,9 +43,55 @@ stats_kernel(const float* __restrict__ rho, const float* __restrict__ npos, cons
         for (int k = 0; k < 5; k++) partial[blockIdx.x * 5 + k] = s[k][0];
 }
 
+// ---- exhaustive verification of the constant-divisor sequence (pbf_math.cuh div_pho0) ------------------
+// Every float bit pattern a: does fma(fma(-a*y, d, a), y, a*y) equal a / d (div.rn) bit for bit? Mismatches are
+// reduced to: the largest |a| < 1 that fails and the smallest |a| >= 1 that fails (as positive-float bit
+// patterns, which order like the values). The verified interval is what lies strictly between them.
+__global__ void __launch_bounds__(256) const_div_check_kernel(float d, float y, uint32_t* fail_below, uint32_t* fail_above) {
+    uint32_t lo = 0, hi = 0xffffffffu;
+    for (uint64_t b = (uint64_t)blockIdx.x * 256 + threadIdx.x; b < (1ull << 32); b += (uint64_t)gridDim.x * 256) {
+        const float a = __uint_as_float((uint32_t)b);
+        const float q = __fmul_rn(a, y);
+        const float fast = __fmaf_rn(__fmaf_rn(-q, d, a), y, q);
+        const float exact = __fdiv_rn(a, d);
+        if (__float_as_uint(fast) != __float_as_uint(exact)) {
+            const uint32_t m = (uint32_t)b & 0x7fffffffu;
+            if (m < 0x3f800000u) lo = max(lo, m); else hi = min(hi, m);
+        }
+    }
+    if (lo) atomicMax(fail_below, lo);
+    if (hi != 0xffffffffu) atomicMin(fail_above, hi);
+}
+
+cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStream_t st) {
+    uint32_t* dev = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dev, 8);
+    if (e != cudaSuccess) return e;
+    const uint32_t init[2] = {0u, 0xffffffffu};
+    uint32_t out[2] = {0, 0};
+    e = cudaMemcpyAsync(dev, init, 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const_div_check_kernel<<<148 * 16, 256, 0, st>>>(d, rcp, dev, dev + 1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dev, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) return e;
+    // strictly inside the failures; +0 (pattern 0) "fails below" only if 0/d mismatched, which it does not,
+    // but zero is excluded anyway: lo is at least the smallest normal number
+    uint32_t lo_bits = out[0] + 1, hi_bits = out[1] == 0xffffffffu ? 0x7f7fffffu : out[1] - 1;
+    if (lo_bits < 0x00800000u) lo_bits = 0x00800000u;
+    if (hi_bits > 0x7f7fffffu) hi_bits = 0x7f7fffffu;
+    memcpy(lo, &lo_bits, 4);
+    memcpy(hi, &hi_bits, 4);
+    return cudaSuccess;
+}
+
 cudaError_t preload_stats() {
     cudaFuncAttributes a;
-    return cudaFuncGetAttributes(&a, stats_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&a, const_div_check_kernel);
+    return e != cudaSuccess ? e : cudaFuncGetAttributes(&a, stats_kernel);
 }
 
 cudaError_t launch_stats(const float* rho, const float* npos, const float* nvel, int64_t n, float pho0,

@@ -107,3 +107,19 @@ def test_cpp_shim_builds_and_fails_loudly_without_gpu(pbf):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "1"], capture_output=True, text=True)
         assert r.returncode == 1 and "PBF error at" in r.stderr and "pbf_create" in r.stderr
+
+
+def test_scene_block_slice_is_a_slice_of_the_block(pbf):
+    """pbf_scene_block_slice_host (what lets every rank generate only its part of a scene): lattice layers
+    [a, b) carry exactly the bits of the full block's particles, and match the oracle's generator."""
+    import _oracle as O
+    origin, n3 = (0.2, 0.2, 0.2), (24, 6, 10)
+    fp, fv, fi = pbf.scene_block_host(origin, n3)
+    op, ov, oi = O.scene_block(origin, n3, 0.05, 27, 0)
+    assert np.array_equal(fp, op) and np.array_equal(fi, oi)
+    per = n3[1] * n3[2]
+    for a, b in ((0, 24), (5, 17), (23, 24), (7, 7)):
+        sp, sv, si = pbf.scene_block_slice_host(origin, n3, a, b)
+        assert np.array_equal(sp, fp[a * per:b * per]) and np.array_equal(si, fi[a * per:b * per]) and not sv.any()
+    with pytest.raises(pbf.PbfError):
+        pbf.scene_block_slice_host(origin, n3, 3, 25)
