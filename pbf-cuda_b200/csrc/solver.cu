@@ -217,64 +217,81 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
     return make_float4(qx, qy, qz, 0.f);
 }
 
-template <bool EXACT_POW, bool USE_PAIRS>
+// The delta-p pass comes as two kernels. The REPLAY kernel walks the neighbour list the lambda pass saved:
+// no cell table, no shared-memory list, few registers — it is latency / HBM bound, so it is compiled for
+// 16 CTAs per SM instead of 8 (32 registers, no spills; measured 0.28 -> 0.20 ms in the compressed state). Particles whose list overflowed
+// (more than PAIR_CAP neighbours) are left to the GATHER kernel, which re-runs the full two-phase gather
+// for them only (ONLY_OVERFLOW) — or for everybody when there is no list at all.
+#ifndef PBF_REPLAY_MINBLOCKS
+#define PBF_REPLAY_MINBLOCKS 16
+#endif
+template <bool EXACT_POW>
+__global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
+delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, int64_t first, int64_t n,
+                      const uint32_t* __restrict__ pair_idx, const float2* __restrict__ pair_sw,
+                      const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
+                      const __grid_constant__ SolverConsts c) {
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t cnt = pair_cnt[t];
+    if (cnt & PAIR_OVERFLOW) return;   // the gather kernel's particle
+    const int64_t i = first + t;
+    const float4 p = xl[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
+#pragma unroll 4
+    for (uint32_t k = 0; k < cnt; k++) {
+        const size_t e = pair0 + (size_t)k * GATHER_THREADS;
+        const uint32_t j = __ldg(&pair_idx[e]);
+        const float2 sw = __ldg(&pair_sw[e]);
+        const float4 q = __ldg(&xl[j]);
+        float pw;  // sw.y = poly6(r2) of the pair, saved by the lambda pass
+        if (EXACT_POW) {
+            pw = powf(sw.y, c.n_corr);
+        } else {  // n_corr == 4
+            const float w2 = __fmul_rn(sw.y, sw.y);
+            pw = __fmul_rn(w2, w2);
+        }
+        const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+        ax = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.x, q.x), sw.x), ax);
+        ay = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.y, q.y), sw.x), ay);
+        az = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.z, q.z), sw.x), az);
+    }
+    const float4 out = delta_p_finish(p, ax, ay, az, c);
+    x_out[i] = out;
+    halo_push(hp, t, out);
+}
+
+template <bool EXACT_POW, bool ONLY_OVERFLOW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-               const uint32_t* __restrict__ pair_idx, const float2* __restrict__ pair_sw,
                const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint16_t s_list[];
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (t >= n) return;
+    if (ONLY_OVERFLOW && !(pair_cnt[t] & PAIR_OVERFLOW)) return;
     const int64_t i = first + t;
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    bool replayed = false;
-    if (USE_PAIRS) {
-        const uint32_t cnt = pair_cnt[t];
-        if (!(cnt & PAIR_OVERFLOW)) {
-            replayed = true;
-            const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
-#pragma unroll 4
-            for (uint32_t k = 0; k < cnt; k++) {
-                const size_t e = pair0 + (size_t)k * GATHER_THREADS;
-                const uint32_t j = __ldg(&pair_idx[e]);
-                const float2 sw = __ldg(&pair_sw[e]);
-                const float4 q = __ldg(&xl[j]);
-                float pw;  // sw.y = poly6(r2) of the pair, saved by the lambda pass
-                if (EXACT_POW) {
-                    pw = powf(sw.y, c.n_corr);
-                } else {  // n_corr == 4
-                    const float w2 = __fmul_rn(sw.y, sw.y);
-                    pw = __fmul_rn(w2, w2);
-                }
-                const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-                ax = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.x, q.x), sw.x), ax);
-                ay = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.y, q.y), sw.x), ay);
-                az = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.z, q.z), sw.x), az);
-            }
+    gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4 q, int) {
+        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+        const float r2 = sumsq(dx, dy, dz);
+        const float w = poly6(r2, c);
+        float pw;
+        if (EXACT_POW) {
+            pw = powf(w, c.n_corr);
+        } else {  // n_corr == 4
+            const float w2 = __fmul_rn(w, w);
+            pw = __fmul_rn(w2, w2);
         }
-    }
-    if (!replayed) {
-        gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4 q, int) {
-            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-            const float r2 = sumsq(dx, dy, dz);
-            const float w = poly6(r2, c);
-            float pw;
-            if (EXACT_POW) {
-                pw = powf(w, c.n_corr);
-            } else {  // n_corr == 4
-                const float w2 = __fmul_rn(w, w);
-                pw = __fmul_rn(w2, w2);
-            }
-            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-            const float s = spiky_scale(r2, c);
-            ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
-            ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
-            az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
-        }, NoHooks());
-    }
+        const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+        const float s = spiky_scale(r2, c);
+        ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
+        ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
+        az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
+    }, NoHooks());
     const float4 out = delta_p_finish(p, ax, ay, az, c);
     x_out[i] = out;
     halo_push(hp, t, out);
@@ -350,6 +367,8 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<true, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<false, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<true, false>);
@@ -393,11 +412,17 @@ cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_ra
     const bool exact = c.exact_pow || c.n_corr != 4.0f;
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (pl.idx) {
-        if (exact) delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
-        else delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
+        if (exact) {
+            delta_p_replay_kernel<true><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.idx, pl.sw, pl.cnt, hp, c);
+            delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.cnt, hp, g, c);
+        } else {
+            delta_p_replay_kernel<false><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.idx, pl.sw, pl.cnt, hp, c);
+            delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.cnt, hp, g, c);
+        }
+        if (launches) (*launches)++;
     } else {
-        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
-        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
+        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, hp, g, c);
+        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, hp, g, c);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();
