@@ -351,9 +351,10 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     A((void**)&s->sort_zero, s->sort_zero_capacity);
     A((void**)&s->pairs[0], n * sizeof(KeyIdx));
     A((void**)&s->pairs[1], n * sizeof(KeyIdx));
-    A((void**)&s->x[0], n * sizeof(float4));
-    A((void**)&s->x[1], n * sizeof(float4));
-    A((void**)&s->xl, n * sizeof(float4));
+    // (+8: the cull of the neighbour sweeps reads runs in groups of four, up to 3 slots past their end)
+    A((void**)&s->x[0], (n + 8) * sizeof(float4));
+    A((void**)&s->x[1], (n + 8) * sizeof(float4));
+    A((void**)&s->xl, (n + 8) * sizeof(float4));
     A((void**)&s->rho, n * 4);
     A((void**)&s->iid_sorted, n * 4);
     A((void**)&s->cell_range, (size_t)cap * sizeof(uint2));

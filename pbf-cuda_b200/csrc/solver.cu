@@ -22,112 +22,121 @@ namespace pbf {
 #ifndef PBF_GATHER_MINBLOCKS
 #define PBF_GATHER_MINBLOCKS 8
 #endif
-#ifndef PBF_LIST_CAP
-#define PBF_LIST_CAP 32
+#ifndef PBF_WORD_CAP
+#define PBF_WORD_CAP 8
+#endif
+#ifndef PBF_FLUSH_PER_SLAB
+#define PBF_FLUSH_PER_SLAB 1
 #endif
 #ifndef PBF_PAIR_CAP
 #define PBF_PAIR_CAP 96
 #endif
 constexpr int GATHER_THREADS = 128;
-constexpr int LIST_CAP = PBF_LIST_CAP;
-constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pass can hand to the delta-p pass  // in-range neighbours buffered per thread and x-slab before a flush
-constexpr size_t LIST_SMEM = (size_t)LIST_CAP * GATHER_THREADS * sizeof(uint16_t);  // 8 KB per CTA
+constexpr int WORD_CAP = PBF_WORD_CAP;  // hit words (32 candidates each) buffered per thread before a flush
+constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pass can hand to the delta-p pass
+constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2);  // 8 KB per CTA
 
 // Two-phase gather of one particle (one thread), the core of all three neighbour sweeps.
 //
 // Phase 1 (cull) walks the candidates in the reference's visiting order — dx, dy, dz nested,
 // ascending slot inside a cell; the three dz cells of a column are consecutive keys, hence ONE
-// contiguous slot run per (dx, dy), and the three runs of one dx are ascending too — with one
-// 16-byte load and 7 flops per candidate, branch-free: the slot offset is always stored to the
-// tail of a per-thread list in shared memory (entry k of thread t at [k][t]: conflict-free) and
-// the tail only advances when `r2 < limit`. Phase 2 (`heavy`) then runs the expensive exact
-// arithmetic over the list only, every lane busy, still in visiting order. Without the list a
-// warp executes the heavy path for nearly every candidate, because some lane is almost always
-// in range (~15 % of the candidates are), at ~15 % lane utilisation.
-// The list is flushed after each dx slab (3 runs, ~11 neighbours) and whenever it is nearly
-// full, so any neighbour count stays correct and ordered; entries are 16-bit offsets from the
-// slab's first slot (re-based if a slab ever spans more than 65535 slots), which keeps the
-// shared-memory footprint at 8 KB per CTA and leaves the rest of the 256 KB for L1.
-struct NoHooks {
-    __device__ __forceinline__ void slab_done(int, uint32_t, int) {}
-    __device__ __forceinline__ void rebased() {}
-};
+// contiguous slot run per (dx, dy), and the runs are visited in ascending slot order — with one
+// 16-byte load, 7 flops and one funnel shift per candidate and nothing else: the sign bit of
+// RN(r2 - limit) (set exactly when r2 < limit; IEEE subtraction with denormals never rounds a
+// non-zero difference to zero) is shifted into a hit word, 32 candidates per word, first
+// candidate in the top bit. Non-empty words go to a per-thread list in shared memory as
+// (first slot, hits) (entry k of thread t at [k][t]: conflict-free). Runs are read in groups of
+// four, up to three slots past their end (the arrays are padded); those bits are masked off.
+// Phase 2 (`heavy`) then runs the expensive exact arithmetic over the set bits only — count
+// leading zeros, clear, next word when empty — every lane busy, still in visiting order.
+// Without the split a warp executes the heavy path for nearly every candidate, because some
+// lane is almost always in range (~15 % of the candidates are), at ~15 % lane utilisation.
+// The list is drained after each dx slab (3 runs, ~11 neighbours) and whenever it is full, so
+// any neighbour count stays correct and ordered at 8 KB of shared memory per CTA, which leaves
+// the rest of the 256 KB for L1.
+__device__ __forceinline__ uint32_t push_hit(uint32_t hits, const float4 p, const float4 q, const float limit) {
+    const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
+    return __funnelshift_l(__float_as_uint(__fsub_rn(r2, limit)), hits, 1);
+}
 
-template <bool SKIP_SELF, typename Heavy, typename Hooks>
+template <bool SKIP_SELF, typename Heavy>
 __device__ __forceinline__ void gather(const float4 p, const uint32_t self, const float limit,
                                        const float4* __restrict__ x, const uint2* __restrict__ cell_range,
-                                       const GridConsts& g, uint16_t* __restrict__ my_list, Heavy&& heavy,
-                                       Hooks&& hooks) {
+                                       const GridConsts& g, uint2* __restrict__ my_words, Heavy&& heavy) {
     const int3 cc = cell_of(p.x, p.y, p.z, g);
     const int zlo = max(cc.z - 1, 0), zhi = min(cc.z + 1, g.dim[2] - 1);
-    uint16_t* const list_full = my_list + (LIST_CAP - 4) * GATHER_THREADS;
-    int k_total = 0;  // in-range neighbours handed to `heavy` so far (its third argument)
+    uint2* const words_end = my_words + WORD_CAP * GATHER_THREADS;
+    uint2* tail = my_words;  // next free entry of this thread's list
+    int k_total = 0;         // in-range neighbours handed to `heavy` so far (its third argument)
+    auto flush = [&]() {
+        const uint2* e = my_words;
+        uint32_t first = 0, hits = 0;
+        for (;;) {
+            if (hits == 0) {
+                if (e == tail) break;
+                const uint2 w = *e;
+                e += GATHER_THREADS;
+                first = w.x;
+                hits = w.y;
+            }
+            const int lead = __clz((int)hits);
+            hits &= ~(0x80000000u >> lead);
+            const uint32_t j = first + (uint32_t)lead;
+            if (SKIP_SELF && j == self) continue;
+            heavy(j, __ldg(&x[j]), k_total);
+            k_total++;
+        }
+        tail = my_words;
+    };
 #pragma unroll 1
     for (int dx = -1; dx <= 1; dx++) {
         const int cx = cc.x + dx;
         const int lx = cx - g.xoff;  // plane in this handle's table (slab mode; lx == cx on one GPU)
-        uint32_t base = 0xffffffffu;
-        if (cx >= 0 && cx < g.dim[0] && (lx < 0 || lx >= g.nxl)) {
+        if (cx < 0 || cx >= g.dim[0]) continue;
+        if (lx < 0 || lx >= g.nxl) {
             // the particle drifted so far from its stored cell that its search leaves the ghost
             // planes: the result would silently miss neighbours, so say so
             if (g.flags) atomicOr(g.flags, (uint32_t)PBF_SLAB_FLAG_GHOST);
-        } else if (cx >= 0 && cx < g.dim[0]) {
-            uint16_t* tail = my_list;  // next free entry of this thread's list
-            auto flush = [&]() {
-#pragma unroll 2
-                for (const uint16_t* e = my_list; e < tail; e += GATHER_THREADS) {
-                    const uint32_t j = base + *e;
-                    heavy(j, __ldg(&x[j]), k_total);
-                    k_total++;
-                }
-                tail = my_list;
-            };
-            // branch-free append: always store the offset, advance the tail only on a hit
-            auto test = [&](const uint32_t j, const float4 q) {
-                const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
-                bool pass = r2 < limit;
-                if (SKIP_SELF) pass &= (j != self);
-                *tail = (uint16_t)(j - base);
-                tail += pass ? GATHER_THREADS : 0;
-            };
+            continue;
+        }
 #pragma unroll 1
-            for (int dy = -1; dy <= 1; dy++) {
-                const int cy = cc.y + dy;
-                if (cy < 0 || cy >= g.dim[1]) continue;
-                const int cbase = lx * g.dyz + cy * g.dim[2];
-                uint32_t start = 0, end = 0;
-                bool any = false;
-                for (int z = zlo; z <= zhi; z++) {
-                    const uint2 r = __ldg(&cell_range[cbase + z]);
-                    if (r.y > r.x) {
-                        if (!any) { start = r.x; any = true; }
-                        end = r.y;
-                    }
-                }
-                if (!any) continue;
-                if (base == 0xffffffffu) base = start;
-                uint32_t j = start;
-                while (j < end) {
-                    if (end - base > 0xffffu) {  // offsets would not fit 16 bits: drain and re-base (rare)
-                        flush();
-                        base = j;
-                        hooks.rebased();
-                    }
-                    const uint32_t stop = min(end, base + 0xffffu);
-                    for (; j + 4 <= stop; j += 4) {  // four independent loads in flight, tested in order
-                        const float4* xp = x + j;
-                        const float4 q0 = __ldg(xp), q1 = __ldg(xp + 1), q2 = __ldg(xp + 2), q3 = __ldg(xp + 3);
-                        test(j, q0); test(j + 1, q1); test(j + 2, q2); test(j + 3, q3);
-                        if (tail > list_full) flush();
-                    }
-                    for (; j < stop; j++) test(j, __ldg(&x[j]));
-                    if (tail > list_full) flush();
+        for (int dy = -1; dy <= 1; dy++) {
+            const int cy = cc.y + dy;
+            if (cy < 0 || cy >= g.dim[1]) continue;
+            const int cbase = lx * g.dyz + cy * g.dim[2];
+            uint32_t start = 0, end = 0;
+            bool any = false;
+            for (int z = zlo; z <= zhi; z++) {
+                const uint2 r = __ldg(&cell_range[cbase + z]);
+                if (r.y > r.x) {
+                    if (!any) { start = r.x; any = true; }
+                    end = r.y;
                 }
             }
-            flush();
+#pragma unroll 1
+            for (uint32_t b = start; b < end; b += 32) {
+                const uint32_t cnt = min(end - b, 32u);   // candidates of this word
+                const uint32_t groups = (cnt + 3) >> 2;
+                const float4* xp = x + b;
+                uint32_t hits = 0;
+#pragma unroll 1
+                for (uint32_t gi = 0; gi < groups; gi++, xp += 4) {  // four independent loads in flight
+                    const float4 q0 = __ldg(xp), q1 = __ldg(xp + 1), q2 = __ldg(xp + 2), q3 = __ldg(xp + 3);
+                    hits = push_hit(hits, p, q0, limit);
+                    hits = push_hit(hits, p, q1, limit);
+                    hits = push_hit(hits, p, q2, limit);
+                    hits = push_hit(hits, p, q3, limit);
+                }
+                // first candidate to the top bit; drop what was read past the end of the run
+                hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt));
+                *tail = make_uint2(b, hits);
+                tail += hits ? GATHER_THREADS : 0;
+                if (tail == words_end) flush();
+            }
         }
-        hooks.slab_done(dx + 1, base, k_total);
+        if (PBF_FLUSH_PER_SLAB) flush();
     }
+    if (!PBF_FLUSH_PER_SLAB) flush();
 }
 
 // ---- neighbour-list reuse between the two passes of one Jacobi iteration ------------------------
@@ -151,7 +160,7 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
               uint32_t* __restrict__ pair_idx, float2* __restrict__ pair_sw, uint32_t* __restrict__ pair_cnt,
               const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
               const __grid_constant__ SolverConsts c) {
-    extern __shared__ uint16_t s_list[];
+    extern __shared__ uint2 s_words[];
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (t >= n) return;
     const int64_t i = first + t;
@@ -163,7 +172,7 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
     const float w_self = poly6_in(0.f, c);
     const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
     int n_pairs = 0;
-    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q, int k) {
+    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int k) {
         float s = 0.f, pw = 0.f;
         if (j == (uint32_t)i) {
             rho = __fadd_rn(rho, w_self);
@@ -193,7 +202,7 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
             }
             n_pairs = k + 1;
         }
-    }, NoHooks());
+    });
     if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
     const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
     const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
@@ -268,14 +277,14 @@ delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n,
                const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
-    extern __shared__ uint16_t s_list[];
+    extern __shared__ uint2 s_words[];
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (t >= n) return;
     if (ONLY_OVERFLOW && !(pair_cnt[t] & PAIR_OVERFLOW)) return;
     const int64_t i = first + t;
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4 q, int) {
+    gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
         const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
         const float r2 = sumsq(dx, dy, dz);
         const float w = poly6(r2, c);
@@ -291,7 +300,7 @@ delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
         ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
         ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
         az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
-    }, NoHooks());
+    });
     const float4 out = delta_p_finish(p, ax, ay, az, c);
     x_out[i] = out;
     halo_push(hp, t, out);
@@ -325,14 +334,14 @@ xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
             const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
-    extern __shared__ uint16_t s_list[];
+    extern __shared__ uint2 s_words[];
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 p = x[i];
     const float4 vi = v4[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<false>(p, (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t j, float4 q, int) {
+    gather<false>(p, (uint32_t)i, c.h2, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
         const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
         const float4 vj = __ldg(&v4[j]);
         const float w = poly6_in(r2, c);
@@ -341,7 +350,7 @@ xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
         ax = __fadd_rn(ax, __fdiv_rn(__fmul_rn(__fadd_rn(tx, tx), w), den));
         ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
         az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
-    }, NoHooks());
+    });
     store_f3(nvel_out, t, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
     iid_out[t] = iid_sorted[i];
 }
@@ -350,11 +359,11 @@ __global__ void __launch_bounds__(GATHER_THREADS)
 neighbor_count_kernel(const float4* __restrict__ x, const uint2* __restrict__ cell_range,
                       uint32_t* __restrict__ count, int64_t n, const __grid_constant__ GridConsts g,
                       const __grid_constant__ SolverConsts c) {
-    extern __shared__ uint16_t s_list[];
+    extern __shared__ uint2 s_words[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
     uint32_t cnt = 0;
-    gather<false>(x[i], (uint32_t)i, c.h2, x, cell_range, g, s_list + threadIdx.x, [&](uint32_t, float4, int) { cnt++; }, NoHooks());
+    gather<false>(x[i], (uint32_t)i, c.h2, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4, int) { cnt++; });
     count[i] = cnt;
 }
 
