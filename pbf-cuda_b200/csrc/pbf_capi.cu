@@ -255,7 +255,7 @@ int refresh_consts(pbf_sim* s) {
 void free_all(pbf_sim* s) {
     cudaFree(s->keys); cudaFree(s->sort_zero); cudaFree(s->pairs[0]); cudaFree(s->pairs[1]);
     cudaFree(s->x[0]); cudaFree(s->x[1]); cudaFree(s->xl); cudaFree(s->rho); cudaFree(s->iid_sorted);
-    cudaFree(s->pairs_list.idx); cudaFree(s->pairs_list.sw); cudaFree(s->pairs_list.cnt);
+    cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt);
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
     if (s->stats_host) cudaFreeHost(s->stats_host);
@@ -377,19 +377,18 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
         delete s;
         return fail(PBF_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e));
     }
-    // Neighbour-list reuse between the lambda and delta-p passes: ~1.1 KB per particle of scratch.
+    // Neighbour-list reuse between the lambda and delta-p passes: ~0.77 KB per particle of scratch.
     // Taken only if it fits comfortably (<= 40 % of the free memory); PBF_NO_PAIR_REUSE=1 disables it.
     {
         const char* np = getenv("PBF_NO_PAIR_REUSE");
-        size_t ib, sb, cb, free_b = 0, total_b = 0;
-        const size_t need = pair_list_bytes(max_particles, &ib, &sb, &cb);
+        size_t jb, cb, free_b = 0, total_b = 0;
+        const size_t need = pair_list_bytes(max_particles, &jb, &cb);
         cudaMemGetInfo(&free_b, &total_b);
         if (!(np && np[0] == '1') && need <= free_b / 10 * 4) {
-            cudaError_t pe = cudaMalloc((void**)&s->pairs_list.idx, ib);
-            if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.sw, sb);
+            cudaError_t pe = cudaMalloc((void**)&s->pairs_list.js, jb);
             if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.cnt, cb);
             if (pe != cudaSuccess) {
-                cudaFree(s->pairs_list.idx); cudaFree(s->pairs_list.sw); cudaFree(s->pairs_list.cnt);
+                cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt);
                 s->pairs_list = PairList();
                 cudaGetLastError();
             }

@@ -138,11 +138,10 @@ cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* 
 // solver passes (solver.cu)
 // Neighbour list the lambda pass saves for the delta-p pass of the same iteration (null = off).
 struct PairList {
-    uint32_t* idx = nullptr;  // slot of the k-th in-range neighbour
-    float2* sw = nullptr;     // (spiky scale, poly6 weight) of that pair
+    uint2* js = nullptr;      // (slot of the k-th in-range neighbour, spiky scale of that pair as bits)
     uint32_t* cnt = nullptr;  // per particle: number of entries, or the overflow flag
 };
-size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_bytes, size_t* cnt_bytes);
+size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes);
 // The passes compute slots [first, first + n) (slab mode: the owned slots; single GPU: 0, n) and
 // read neighbours from every slot. Internal arrays (x, xl, rho, v4, iid_sorted) are indexed by
 // slot; caller-facing arrays (pos/npos/vel/nvel/iid) and the pair list by slot - first.

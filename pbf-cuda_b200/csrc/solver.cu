@@ -23,10 +23,10 @@ namespace pbf {
 #define PBF_GATHER_MINBLOCKS 8
 #endif
 #ifndef PBF_WORD_CAP
-#define PBF_WORD_CAP 8
+#define PBF_WORD_CAP 15
 #endif
 #ifndef PBF_FLUSH_PER_SLAB
-#define PBF_FLUSH_PER_SLAB 1
+#define PBF_FLUSH_PER_SLAB 0
 #endif
 #ifndef PBF_PAIR_CAP
 #define PBF_PAIR_CAP 96
@@ -59,6 +59,30 @@ __device__ __forceinline__ uint32_t push_hit(uint32_t hits, const float4 p, cons
     return __funnelshift_l(__float_as_uint(__fsub_rn(r2, limit)), hits, 1);
 }
 
+// Four consecutive candidates. sm_100 has 256-bit global loads (LDG.E.256): two of them instead of four
+// LDG.128 halve the L1 tag look-ups and data wavefronts of the cull, which is what bounds the later Jacobi
+// iterations (lanes whose home cell drifted apart read different lines: 8.5 tags per warp load, ncu).
+// `xp` is 32-byte aligned: words start at even slots.
+#ifndef PBF_CULL_LD256
+#define PBF_CULL_LD256 1
+#endif
+#ifndef PBF_CULL_PIPE
+#define PBF_CULL_PIPE 0
+#endif
+#ifndef PBF_HEAVY_PREFETCH
+#define PBF_HEAVY_PREFETCH 0
+#endif
+__device__ __forceinline__ void load4(const float4* __restrict__ xp, float4& q0, float4& q1, float4& q2, float4& q3) {
+#if PBF_CULL_LD256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "l"(xp));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w) : "l"(xp + 2));
+#else
+    q0 = __ldg(xp); q1 = __ldg(xp + 1); q2 = __ldg(xp + 2); q3 = __ldg(xp + 3);
+#endif
+}
+
 template <bool SKIP_SELF, typename Heavy>
 __device__ __forceinline__ void gather(const float4 p, const uint32_t self, const float limit,
                                        const float4* __restrict__ x, const uint2* __restrict__ cell_range,
@@ -71,9 +95,9 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
     auto flush = [&]() {
         const uint2* e = my_words;
         uint32_t first = 0, hits = 0;
-        for (;;) {
+        auto next = [&](uint32_t& j) -> bool {  // next set bit of the list, in order
             if (hits == 0) {
-                if (e == tail) break;
+                if (e == tail) return false;
                 const uint2 w = *e;
                 e += GATHER_THREADS;
                 first = w.x;
@@ -81,11 +105,34 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             }
             const int lead = __clz((int)hits);
             hits &= ~(0x80000000u >> lead);
-            const uint32_t j = first + (uint32_t)lead;
+            j = first + (uint32_t)lead;
+            return true;
+        };
+#if PBF_HEAVY_PREFETCH
+        // the neighbour after the current one is loaded before the current one's arithmetic
+        uint32_t j = 0, jn = 0;
+        float4 q = p, qn = p;
+        bool have = next(j);
+        if (have) q = __ldg(&x[j]);
+        while (have) {
+            const bool have_n = next(jn);
+            if (have_n) qn = __ldg(&x[jn]);
+            if (!(SKIP_SELF && j == self)) {
+                heavy(j, q, k_total);
+                k_total++;
+            }
+            j = jn;
+            q = qn;
+            have = have_n;
+        }
+#else
+        uint32_t j;
+        while (next(j)) {
             if (SKIP_SELF && j == self) continue;
             heavy(j, __ldg(&x[j]), k_total);
             k_total++;
         }
+#endif
         tail = my_words;
     };
 #pragma unroll 1
@@ -114,21 +161,47 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
                 }
             }
 #pragma unroll 1
-            for (uint32_t b = start; b < end; b += 32) {
-                const uint32_t cnt = min(end - b, 32u);   // candidates of this word
+            for (uint32_t b = start & ~1u; b < end; b += 32) {   // words start at even slots (load4)
+                const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
                 const uint32_t groups = (cnt + 3) >> 2;
                 const float4* xp = x + b;
                 uint32_t hits = 0;
+#if PBF_CULL_PIPE
+                // software pipeline: the next group's loads are issued before this group's arithmetic
+                // (two register sets A / B in ping-pong, so no register is moved)
+                float4 a0, a1, a2, a3, b0, b1, b2, b3;
+                load4(xp, a0, a1, a2, a3);
+                uint32_t left = groups;  // groups not yet pushed, A holds the first of them
 #pragma unroll 1
-                for (uint32_t gi = 0; gi < groups; gi++, xp += 4) {  // four independent loads in flight
-                    const float4 q0 = __ldg(xp), q1 = __ldg(xp + 1), q2 = __ldg(xp + 2), q3 = __ldg(xp + 3);
+                for (;;) {
+                    if (left > 1) load4(xp + 4, b0, b1, b2, b3);
+                    hits = push_hit(hits, p, a0, limit);
+                    hits = push_hit(hits, p, a1, limit);
+                    hits = push_hit(hits, p, a2, limit);
+                    hits = push_hit(hits, p, a3, limit);
+                    if (left == 1) break;
+                    if (left > 2) load4(xp + 8, a0, a1, a2, a3);
+                    hits = push_hit(hits, p, b0, limit);
+                    hits = push_hit(hits, p, b1, limit);
+                    hits = push_hit(hits, p, b2, limit);
+                    hits = push_hit(hits, p, b3, limit);
+                    if (left == 2) break;
+                    left -= 2;
+                    xp += 8;
+                }
+#else
+#pragma unroll 1
+                for (uint32_t gi = 0; gi < groups; gi++, xp += 4) {  // four candidates in flight per lane
+                    float4 q0, q1, q2, q3;
+                    load4(xp, q0, q1, q2, q3);
                     hits = push_hit(hits, p, q0, limit);
                     hits = push_hit(hits, p, q1, limit);
                     hits = push_hit(hits, p, q2, limit);
                     hits = push_hit(hits, p, q3, limit);
                 }
-                // first candidate to the top bit; drop what was read past the end of the run
-                hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt));
+#endif
+                // first slot to the top bit; drop the slot before the run (odd start) and what was read past its end
+                hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt)) & (0xffffffffu >> (b < start ? 1 : 0));
                 *tail = make_uint2(b, hits);
                 tail += hits ? GATHER_THREADS : 0;
                 if (tail == words_end) flush();
@@ -143,13 +216,14 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
 // The lambda and delta-p passes of an iteration read the SAME positions (the reference runs
 // computeLambda and computetpos on the same dc_npos, Simulator.cu:222-245), so their in-range
 // neighbour sets and the per-pair kernel values coincide. The lambda pass therefore saves, per
-// particle and in visiting order, the slot offset of every in-range neighbour plus the two values
-// the delta-p pass needs from the pair geometry: the spiky scale s and the poly6 weight w. The
-// delta-p pass replays the list: no cull, no sqrt, no division — only w^n_corr, which it can
+// particle and in visiting order, the slot of every in-range neighbour (itself excluded, as in
+// computetpos) plus the one expensive value the delta-p pass needs from the pair geometry: the
+// spiky scale s (sqrt + IEEE division). The delta-p pass replays the list: no cull, no sqrt, no
+// division — the poly6 weight is four multiplies from the r2 it forms anyway, and w^n_corr it can
 // afford (it is HBM bound) — and produces the same bits, because it consumes the very values its
 // own evaluation would have produced.
 // Layout (block b of 128 threads, entry k, thread t): [(b*PAIR_CAP + k)*128 + t] — a warp's k-th
-// entries are contiguous (4 B slot + 8 B (s, w^n)). A particle with more than PAIR_CAP neighbours
+// entries are contiguous 8-byte (slot, s) records. A particle with more than PAIR_CAP neighbours
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
 constexpr uint32_t PAIR_OVERFLOW = 1u << 31;
 
@@ -157,7 +231,7 @@ template <bool EXACT_POW, bool SAVE_PAIRS>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-              uint32_t* __restrict__ pair_idx, float2* __restrict__ pair_sw, uint32_t* __restrict__ pair_cnt,
+              uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
               const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
               const __grid_constant__ SolverConsts c) {
     extern __shared__ uint2 s_words[];
@@ -172,35 +246,28 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
     const float w_self = poly6_in(0.f, c);
     const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
     int n_pairs = 0;
-    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int k) {
-        float s = 0.f, pw = 0.f;
+    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
         if (j == (uint32_t)i) {
             rho = __fadd_rn(rho, w_self);
         } else {
             const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
             const float r2 = sumsq(dx, dy, dz);
-            const float w = poly6(r2, c);
-            rho = __fadd_rn(rho, w);
-            s = spiky_scale(r2, c);
+            rho = __fadd_rn(rho, poly6(r2, c));
+            const float s = spiky_scale(r2, c);
             float gx = __fmul_rn(dx, s), gy = __fmul_rn(dy, s), gz = __fmul_rn(dz, s);
             div3_pho0(gx, gy, gz, c);
             gix = __fadd_rn(gix, gx);
             giy = __fadd_rn(giy, gy);
             giz = __fadd_rn(giz, gz);
             gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
-            // The delta-p pass needs w^n_corr of this pair. The lambda pass is FP32-issue bound and the
-            // delta-p replay is HBM bound with idle issue slots, so the ~45-instruction powf is left to
-            // the replay: the list carries w itself, and powf(w, n) there yields the reference's bits.
-            pw = w;
-        }
-        // (the self entry is saved with s = pw = 0: the delta-p pass then adds an exact zero)
-        if (SAVE_PAIRS) {
-            if (k < PAIR_CAP) {
-                const size_t e = pair0 + (size_t)k * GATHER_THREADS;
-                pair_idx[e] = j;
-                pair_sw[e] = make_float2(s, pw);
+            // The delta-p pass needs s, poly6(r2) and its n_corr-th power for this pair. The lambda pass
+            // is instruction-issue bound and the delta-p replay is HBM bound with idle issue slots, so
+            // only s travels: the replay re-forms r2 from the same positions (the same bits) and
+            // evaluates poly6 and the ~45-instruction powf there.
+            if (SAVE_PAIRS) {
+                if (n_pairs < PAIR_CAP) pair_js[pair0 + (size_t)n_pairs * GATHER_THREADS] = make_uint2(j, __float_as_uint(s));
+                n_pairs++;
             }
-            n_pairs = k + 1;
         }
     });
     if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
@@ -237,7 +304,7 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
 template <bool EXACT_POW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
 delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, int64_t first, int64_t n,
-                      const uint32_t* __restrict__ pair_idx, const float2* __restrict__ pair_sw,
+                      const uint2* __restrict__ pair_js,
                       const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
                       const __grid_constant__ SolverConsts c) {
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
@@ -251,20 +318,22 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
 #pragma unroll 4
     for (uint32_t k = 0; k < cnt; k++) {
         const size_t e = pair0 + (size_t)k * GATHER_THREADS;
-        const uint32_t j = __ldg(&pair_idx[e]);
-        const float2 sw = __ldg(&pair_sw[e]);
-        const float4 q = __ldg(&xl[j]);
-        float pw;  // sw.y = poly6(r2) of the pair, saved by the lambda pass
+        const uint2 js = __ldg(&pair_js[e]);
+        const float4 q = __ldg(&xl[js.x]);
+        const float sj = __uint_as_float(js.y);  // spiky scale of the pair, saved by the lambda pass
+        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+        const float w = poly6(sumsq(dx, dy, dz), c);
+        float pw;
         if (EXACT_POW) {
-            pw = powf(sw.y, c.n_corr);
+            pw = powf(w, c.n_corr);
         } else {  // n_corr == 4
-            const float w2 = __fmul_rn(sw.y, sw.y);
+            const float w2 = __fmul_rn(w, w);
             pw = __fmul_rn(w2, w2);
         }
         const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-        ax = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.x, q.x), sw.x), ax);
-        ay = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.y, q.y), sw.x), ay);
-        az = __fmaf_rn(sc, __fmul_rn(__fsub_rn(p.z, q.z), sw.x), az);
+        ax = __fmaf_rn(sc, __fmul_rn(dx, sj), ax);
+        ay = __fmaf_rn(sc, __fmul_rn(dy, sj), ay);
+        az = __fmaf_rn(sc, __fmul_rn(dz, sj), az);
     }
     const float4 out = delta_p_finish(p, ax, ay, az, c);
     x_out[i] = out;
@@ -390,12 +459,11 @@ cudaError_t preload_solver() {
 
 static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
-size_t pair_list_bytes(int64_t max_particles, size_t* idx_bytes, size_t* sw_bytes, size_t* cnt_bytes) {
+size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes) {
     const size_t blocks = (size_t)((max_particles + GATHER_THREADS - 1) / GATHER_THREADS);
-    *idx_bytes = blocks * PAIR_CAP * GATHER_THREADS * sizeof(uint32_t);
-    *sw_bytes = blocks * PAIR_CAP * GATHER_THREADS * sizeof(float2);
+    *js_bytes = blocks * PAIR_CAP * GATHER_THREADS * sizeof(uint2);
     *cnt_bytes = blocks * GATHER_THREADS * sizeof(uint32_t);
-    return *idx_bytes + *sw_bytes + *cnt_bytes;
+    return *js_bytes + *cnt_bytes;
 }
 
 cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t first,
@@ -404,12 +472,12 @@ cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* 
     if (n <= 0) return cudaSuccess;
     const bool exact = c.exact_pow || c.n_corr != 4.0f;
     const unsigned nb = nblocks(n, GATHER_THREADS);
-    if (!pl.idx)
-        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
+    if (!pl.js)
+        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
     else if (exact)
-        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
+        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
     else
-        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.idx, pl.sw, pl.cnt, hp, g, c);
+        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -420,12 +488,12 @@ cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_ra
     if (n <= 0) return cudaSuccess;
     const bool exact = c.exact_pow || c.n_corr != 4.0f;
     const unsigned nb = nblocks(n, GATHER_THREADS);
-    if (pl.idx) {
+    if (pl.js) {
         if (exact) {
-            delta_p_replay_kernel<true><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.idx, pl.sw, pl.cnt, hp, c);
+            delta_p_replay_kernel<true><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);
             delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.cnt, hp, g, c);
         } else {
-            delta_p_replay_kernel<false><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.idx, pl.sw, pl.cnt, hp, c);
+            delta_p_replay_kernel<false><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);
             delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.cnt, hp, g, c);
         }
         if (launches) (*launches)++;
