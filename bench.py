@@ -215,9 +215,10 @@ def run_product(args, rank, world, dist):
                 "algorithmic_bytes_per_particle": ALG_BYTES[dom],
                 "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved": round(step_gbs, 2),
                                "frac": round(step_gbs / peak, 5)},
-                "note": "the lambda / XSPH sweeps are FP32-issue bound, not HBM bound (SURVEY.md App. D, DESIGN.md 5): "
-                        "ncu shows 74% issue-slot utilisation at 19% DRAM throughput; the delta-p pass replays the "
-                        "lambda pass's neighbour list (and evaluates the exact powf): 53% issue, 27% DRAM (see delta_p below)",
+                "note": "the lambda / XSPH sweeps are bound by the L1 wavefront rate and instruction issue, not by HBM "
+                        "(SURVEY.md App. D, DESIGN.md 5): ncu at step 100 shows 60% issue-slot utilisation, 63-80% of the L1 "
+                        "data-pipe wavefront rate and 10% DRAM throughput; the delta-p pass replays the lambda pass's neighbour "
+                        "list and evaluates the exact powf: 76% issue, 27% DRAM (see delta_p below)",
                 "delta_p": {"kernel_ms": round(kacc["delta_p"], 4), "traffic": TRAFFIC["delta_p"],
                             "dram_GBps_from_traffic": round(TRAFFIC["delta_p"] / (kacc["delta_p"] * 1e-3) / 1e9, 1)}}
 
@@ -445,7 +446,7 @@ def run_product_slab(args, rank, world, dist):
                 "particles_on_this_rank": n_own,
                 "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved_per_gpu": round(step_gbs, 2),
                                "frac": round(step_gbs / peak, 5)},
-                "note": "rank 0's kernels; the lambda / XSPH sweeps are FP32-issue bound, not HBM bound (DESIGN.md 5)"}
+                "note": "rank 0's kernels; the lambda / XSPH sweeps are L1-wavefront / issue bound, not HBM bound (DESIGN.md 5)"}
     e2e = {"value": round(n_total * e2e_steps / float(t[0]), 1), "unit": "particle-steps/s", "steps": e2e_steps,
            "h2d_bytes_per_step": int(float(t[1]) / e2e_steps), "d2h_bytes_per_step": int(float(t[2]) / e2e_steps),
            "api": "every rank uploads its slab's pos/vel/iid from pinned host memory, SlabSimulator.step, downloads "
@@ -472,9 +473,10 @@ def run_product_slab(args, rank, world, dist):
             "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "clocks": clocks}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full`, dam_1m early state
-# (profiles/r01_gather_v5_ncu_summary.txt): the lambda pass writes the neighbour list the delta-p pass replays
-TRAFFIC = {"lambda": 594.66e6, "delta_p": 443.24e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full`, dam_1m at step ~100 — the state the
+# kernel timers above see (profiles/r01e_solver_ncu_summary.txt): the lambda pass writes the 8-byte neighbour
+# records (344 MB) the delta-p replay reads back (420 MB with its float4 gathers)
+TRAFFIC = {"lambda": 420.6e6, "delta_p": 437.9e6}
 
 
 def cpu_baseline(args, n, sc, steps=None):

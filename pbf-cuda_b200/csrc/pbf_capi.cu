@@ -73,6 +73,7 @@ struct pbf_sim {
     uint32_t* iid_sorted = nullptr;
     uint2* cell_range = nullptr;
     PairList pairs_list;            // lambda -> delta-p neighbour list (null when disabled / too large)
+    CullScratch cull;               // coordinate arrays of the sweeps' cull (solver.cu pack_kernel)
     uint32_t* count_scratch = nullptr;
     uint32_t* read_scratch = nullptr;
     double* stats_partial = nullptr;
@@ -256,6 +257,7 @@ void free_all(pbf_sim* s) {
     cudaFree(s->keys); cudaFree(s->sort_zero); cudaFree(s->pairs[0]); cudaFree(s->pairs[1]);
     cudaFree(s->x[0]); cudaFree(s->x[1]); cudaFree(s->xl); cudaFree(s->rho); cudaFree(s->iid_sorted);
     cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt);
+    cudaFree(s->cull.xs); cudaFree(s->cull.ys); cudaFree(s->cull.zs);
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
     if (s->stats_host) cudaFreeHost(s->stats_host);
@@ -355,6 +357,9 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     A((void**)&s->x[0], (n + 8) * sizeof(float4));
     A((void**)&s->x[1], (n + 8) * sizeof(float4));
     A((void**)&s->xl, (n + 8) * sizeof(float4));
+    A((void**)&s->cull.xs, (n + 8) * 4);
+    A((void**)&s->cull.ys, (n + 8) * 4);
+    A((void**)&s->cull.zs, (n + 8) * 4);
     A((void**)&s->rho, n * 4);
     A((void**)&s->iid_sorted, n * 4);
     A((void**)&s->cell_range, (size_t)cap * sizeof(uint2));
@@ -601,7 +606,7 @@ int pbf_stage_lambda(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_LAMBDA;
     return PBF_OK;
 }
@@ -611,7 +616,7 @@ int pbf_stage_delta_p(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->x[s->cur ^ 1], &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;
@@ -641,7 +646,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
 
 int pbf_stage_correct_velocity(pbf_sim* s) {
     if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
-    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
 }
@@ -991,7 +996,7 @@ int pbf_read(pbf_sim* s, int what, void* dst, int64_t count) {
             return extract(s->xl, 4, 0, 3);
         case PBF_READ_NEIGHBOR_COUNT: {
             if (!s->count_scratch) CUDA_TRY(cudaMalloc((void**)&s->count_scratch, (size_t)s->max_particles * 4));
-            CUDA_TRY(launch_neighbor_count(s->x[s->cur], s->cell_range, s->count_scratch, s->n_local, s->g, s->c, s->stream));
+            CUDA_TRY(launch_neighbor_count(s->x[s->cur], s->cull, s->cell_range, s->count_scratch, s->n_local, s->g, s->c, s->stream));
             return extract(s->count_scratch, 1, 0, 1);
         }
         default:

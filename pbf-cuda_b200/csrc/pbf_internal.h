@@ -142,15 +142,23 @@ struct PairList {
     uint32_t* cnt = nullptr;  // per particle: number of entries, or the overflow flag
 };
 size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes);
+// Coordinate arrays the cull of the neighbour sweeps reads (solver.cu CullSoA): max_particles + 8 floats
+// each, 16-byte aligned, rewritten from the float4 iterate before every sweep.
+struct CullScratch {
+    float* xs = nullptr;
+    float* ys = nullptr;
+    float* zs = nullptr;
+};
 // The passes compute slots [first, first + n) (slab mode: the owned slots; single GPU: 0, n) and
 // read neighbours from every slot. Internal arrays (x, xl, rho, v4, iid_sorted) are indexed by
 // slot; caller-facing arrays (pos/npos/vel/nvel/iid) and the pair list by slot - first.
-cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                          int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
-                          const SolverConsts& c, cudaStream_t st, int64_t* launches);
-cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t first, int64_t n,
-                           const PairList& pl, const HaloPush& hp, const GridConsts& g, const SolverConsts& c,
-                           cudaStream_t st, int64_t* launches);
+// `n_slots` = every slot the handle stores (ghosts included): the sweeps' cull reads them all.
+cudaError_t launch_lambda(const float4* x, const CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
+                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+cudaError_t launch_delta_p(const float4* xl, const CullScratch& cs, float4* x_out, const uint2* cell_range,
+                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
+                           const SolverConsts& c, cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
                                    const SolverConsts& c, cudaStream_t st, int64_t* launches);
@@ -165,9 +173,10 @@ cudaError_t launch_halo_publish(const int64_t* tail_src, int64_t* peer_right_tai
                                 uint32_t* peer_word_right, uint32_t seq, cudaStream_t st, int64_t* launches);
 cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
                              uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches);
-cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,
-                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n,
-                        const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+cudaError_t launch_xsph(const float4* x, const CullScratch& cs, int64_t n_slots, const float4* v4,
+                        const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
+                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                        int64_t* launches);
 // slab.cu: first slot of every local plane in the sorted pairs (nxl + 1 entries, the last one =
 // number of particles inside the local plane range; the rest carry the discard key)
 cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,
@@ -176,8 +185,8 @@ cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_s
 cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                                 float* npos, float* nvel, uint32_t* iid_out, int64_t n, cudaStream_t st,
                                 int64_t* launches);
-cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
-                                  const GridConsts& g, const SolverConsts& c, cudaStream_t st);
+cudaError_t launch_neighbor_count(const float4* x, const CullScratch& cs, const uint2* cell_range, uint32_t* count,
+                                  int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 
 // stats.cu: exhaustive check of the reciprocal division sequence for divisor d over all 2^32 bit
 // patterns of the dividend; returns the verified interval of |a| around 1 (lo > hi: none)

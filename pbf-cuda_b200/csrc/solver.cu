@@ -40,64 +40,87 @@ constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2); 
 //
 // Phase 1 (cull) walks the candidates in the reference's visiting order — dx, dy, dz nested,
 // ascending slot inside a cell; the three dz cells of a column are consecutive keys, hence ONE
-// contiguous slot run per (dx, dy), and the runs are visited in ascending slot order — with one
-// 16-byte load, 7 flops and one funnel shift per candidate and nothing else: the sign bit of
-// RN(r2 - limit) (set exactly when r2 < limit; IEEE subtraction with denormals never rounds a
-// non-zero difference to zero) is shifted into a hit word, 32 candidates per word, first
-// candidate in the top bit. Non-empty words go to a per-thread list in shared memory as
-// (first slot, hits) (entry k of thread t at [k][t]: conflict-free). Runs are read in groups of
-// four, up to three slots past their end (the arrays are padded); those bits are masked off.
+// contiguous slot run per (dx, dy), and the runs are visited in ascending slot order — with
+// three 16-byte loads, 14 two-lane flops and four funnel shifts per FOUR candidates and nothing
+// else: the sign bit of RN(r2 - limit) (set exactly when r2 < limit; IEEE subtraction with
+// denormals never rounds a non-zero difference to zero) is shifted into a hit word, 32 slots per
+// word, first slot in the top bit. Non-empty words go to a per-thread list in shared memory as
+// (first slot, hits) (entry k of thread t at [k][t]: conflict-free). Runs are read in aligned
+// groups of four slots, up to three before their start and after their end (the arrays are
+// padded); those bits are masked off.
 // Phase 2 (`heavy`) then runs the expensive exact arithmetic over the set bits only — count
 // leading zeros, clear, next word when empty — every lane busy, still in visiting order.
 // Without the split a warp executes the heavy path for nearly every candidate, because some
 // lane is almost always in range (~15 % of the candidates are), at ~15 % lane utilisation.
-// The list is drained after each dx slab (3 runs, ~11 neighbours) and whenever it is full, so
-// any neighbour count stays correct and ordered at 8 KB of shared memory per CTA, which leaves
-// the rest of the 256 KB for L1.
-__device__ __forceinline__ uint32_t push_hit(uint32_t hits, const float4 p, const float4 q, const float limit) {
-    const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
-    return __funnelshift_l(__float_as_uint(__fsub_rn(r2, limit)), hits, 1);
+// The list is drained once per particle — one heavy phase over ~33 neighbours keeps the lanes of a
+// warp busier than three phases over ~11 (measured: 3.78 -> 3.01 ms per step) — and whenever it
+// is full, so any neighbour count stays correct and ordered; 15 words per thread = 15 KB per CTA
+// keep 8 CTAs inside the 132 KB carve-out step and leave ~124 KB of L1.
+// Cull-side copy of the positions: three float arrays (structure of arrays), refreshed from the float4
+// iterate by pack_kernel before every sweep. Four consecutive candidates are then three 16-byte loads
+// (instead of four), and their coordinates sit in adjacent registers, which is what the packed FP32
+// instructions of sm_100 want.
+struct CullSoA {
+    const float* xs;
+    const float* ys;
+    const float* zs;
+};
+
+// Two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2, sm_100): each lane is the same IEEE
+// round-to-nearest operation as the scalar instruction, so r2 below has the bits of sumsq().
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// two candidates: RN(r2 - limit) of each, sign bits pushed into `hits` (first candidate first)
+__device__ __forceinline__ uint32_t push_hits2(uint32_t hits, f32x2 px, f32x2 py, f32x2 pz, f32x2 lim,
+                                               float x0, float x1, float y0, float y1, float z0, float z1) {
+    const f32x2 dx = sub2(px, pack2(x0, x1)), dy = sub2(py, pack2(y0, y1)), dz = sub2(pz, pack2(z0, z1));
+    const f32x2 t = sub2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lim);
+    uint32_t t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+    hits = __funnelshift_l(t0, hits, 1);
+    return __funnelshift_l(t1, hits, 1);
 }
 
-// Four consecutive candidates. sm_100 has 256-bit global loads (LDG.E.256): two of them instead of four
-// LDG.128 halve the L1 tag look-ups and data wavefronts of the cull, which is what bounds the later Jacobi
-// iterations (lanes whose home cell drifted apart read different lines: 8.5 tags per warp load, ncu).
-// `xp` is 32-byte aligned: words start at even slots.
-#ifndef PBF_CULL_LD256
-#define PBF_CULL_LD256 1
-#endif
-#ifndef PBF_CULL_PIPE
-#define PBF_CULL_PIPE 0
-#endif
-#ifndef PBF_HEAVY_PREFETCH
-#define PBF_HEAVY_PREFETCH 0
-#endif
-__device__ __forceinline__ void load4(const float4* __restrict__ xp, float4& q0, float4& q1, float4& q2, float4& q3) {
-#if PBF_CULL_LD256
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "l"(xp));
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w) : "l"(xp + 2));
-#else
-    q0 = __ldg(xp); q1 = __ldg(xp + 1); q2 = __ldg(xp + 2); q3 = __ldg(xp + 3);
-#endif
-}
-
+// (Measured and dropped: issuing the next group's loads before this group's arithmetic, and loading the
+//  next neighbour ahead of the heavy arithmetic — no change in either case. The sweeps are bound by the L1
+//  wavefront rate (70-80 % of peak, ncu): lanes of a warp sit in ~3 cells, and after the first Jacobi
+//  iteration their home cells drift apart, so one warp load touches 3-9 different lines.)
 template <bool SKIP_SELF, typename Heavy>
 __device__ __forceinline__ void gather(const float4 p, const uint32_t self, const float limit,
-                                       const float4* __restrict__ x, const uint2* __restrict__ cell_range,
-                                       const GridConsts& g, uint2* __restrict__ my_words, Heavy&& heavy) {
+                                       const float4* __restrict__ x, const CullSoA soa,
+                                       const uint2* __restrict__ cell_range, const GridConsts& g,
+                                       uint2* __restrict__ my_words, Heavy&& heavy) {
     const int3 cc = cell_of(p.x, p.y, p.z, g);
     const int zlo = max(cc.z - 1, 0), zhi = min(cc.z + 1, g.dim[2] - 1);
     uint2* const words_end = my_words + WORD_CAP * GATHER_THREADS;
     uint2* tail = my_words;  // next free entry of this thread's list
     int k_total = 0;         // in-range neighbours handed to `heavy` so far (its third argument)
+    const f32x2 px = pack2(p.x, p.x), py = pack2(p.y, p.y), pz = pack2(p.z, p.z), lim = pack2(limit, limit);
     auto flush = [&]() {
         const uint2* e = my_words;
         uint32_t first = 0, hits = 0;
-        auto next = [&](uint32_t& j) -> bool {  // next set bit of the list, in order
-            if (hits == 0) {
-                if (e == tail) return false;
+        for (;;) {
+            if (hits == 0) {  // next word of the list
+                if (e == tail) break;
                 const uint2 w = *e;
                 e += GATHER_THREADS;
                 first = w.x;
@@ -105,34 +128,11 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             }
             const int lead = __clz((int)hits);
             hits &= ~(0x80000000u >> lead);
-            j = first + (uint32_t)lead;
-            return true;
-        };
-#if PBF_HEAVY_PREFETCH
-        // the neighbour after the current one is loaded before the current one's arithmetic
-        uint32_t j = 0, jn = 0;
-        float4 q = p, qn = p;
-        bool have = next(j);
-        if (have) q = __ldg(&x[j]);
-        while (have) {
-            const bool have_n = next(jn);
-            if (have_n) qn = __ldg(&x[jn]);
-            if (!(SKIP_SELF && j == self)) {
-                heavy(j, q, k_total);
-                k_total++;
-            }
-            j = jn;
-            q = qn;
-            have = have_n;
-        }
-#else
-        uint32_t j;
-        while (next(j)) {
+            const uint32_t j = first + (uint32_t)lead;
             if (SKIP_SELF && j == self) continue;
             heavy(j, __ldg(&x[j]), k_total);
             k_total++;
         }
-#endif
         tail = my_words;
     };
 #pragma unroll 1
@@ -161,47 +161,21 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
                 }
             }
 #pragma unroll 1
-            for (uint32_t b = start & ~1u; b < end; b += 32) {   // words start at even slots (load4)
+            for (uint32_t b = start & ~3u; b < end; b += 32) {   // words start at multiples of four slots
                 const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
                 const uint32_t groups = (cnt + 3) >> 2;
-                const float4* xp = x + b;
+                const float4* xp = reinterpret_cast<const float4*>(soa.xs + b);
+                const float4* yp = reinterpret_cast<const float4*>(soa.ys + b);
+                const float4* zp = reinterpret_cast<const float4*>(soa.zs + b);
                 uint32_t hits = 0;
-#if PBF_CULL_PIPE
-                // software pipeline: the next group's loads are issued before this group's arithmetic
-                // (two register sets A / B in ping-pong, so no register is moved)
-                float4 a0, a1, a2, a3, b0, b1, b2, b3;
-                load4(xp, a0, a1, a2, a3);
-                uint32_t left = groups;  // groups not yet pushed, A holds the first of them
 #pragma unroll 1
-                for (;;) {
-                    if (left > 1) load4(xp + 4, b0, b1, b2, b3);
-                    hits = push_hit(hits, p, a0, limit);
-                    hits = push_hit(hits, p, a1, limit);
-                    hits = push_hit(hits, p, a2, limit);
-                    hits = push_hit(hits, p, a3, limit);
-                    if (left == 1) break;
-                    if (left > 2) load4(xp + 8, a0, a1, a2, a3);
-                    hits = push_hit(hits, p, b0, limit);
-                    hits = push_hit(hits, p, b1, limit);
-                    hits = push_hit(hits, p, b2, limit);
-                    hits = push_hit(hits, p, b3, limit);
-                    if (left == 2) break;
-                    left -= 2;
-                    xp += 8;
+                for (uint32_t gi = 0; gi < groups; gi++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
+                    const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
+                    hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
+                    hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
                 }
-#else
-#pragma unroll 1
-                for (uint32_t gi = 0; gi < groups; gi++, xp += 4) {  // four candidates in flight per lane
-                    float4 q0, q1, q2, q3;
-                    load4(xp, q0, q1, q2, q3);
-                    hits = push_hit(hits, p, q0, limit);
-                    hits = push_hit(hits, p, q1, limit);
-                    hits = push_hit(hits, p, q2, limit);
-                    hits = push_hit(hits, p, q3, limit);
-                }
-#endif
-                // first slot to the top bit; drop the slot before the run (odd start) and what was read past its end
-                hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt)) & (0xffffffffu >> (b < start ? 1 : 0));
+                // first slot to the top bit; drop the slots before the run and what was read past its end
+                hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt)) & (0xffffffffu >> (b < start ? start - b : 0));
                 *tail = make_uint2(b, hits);
                 tail += hits ? GATHER_THREADS : 0;
                 if (tail == words_end) flush();
@@ -210,6 +184,18 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
         if (PBF_FLUSH_PER_SLAB) flush();
     }
     if (!PBF_FLUSH_PER_SLAB) flush();
+}
+
+// float4 iterate -> the cull's three coordinate arrays, every stored slot (ghosts included); ~8 us per
+// million particles, HBM bound (16 B read, 12 B written per particle)
+__global__ void __launch_bounds__(256)
+pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restrict__ ys, float* __restrict__ zs, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 q = x[i];
+    xs[i] = q.x;
+    ys[i] = q.y;
+    zs[i] = q.z;
 }
 
 // ---- neighbour-list reuse between the two passes of one Jacobi iteration ------------------------
@@ -227,9 +213,9 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
 constexpr uint32_t PAIR_OVERFLOW = 1u << 31;
 
-template <bool EXACT_POW, bool SAVE_PAIRS>
+template <bool SAVE_PAIRS>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
-lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __restrict__ rho_out,
+lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
               uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
               const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
@@ -246,7 +232,7 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
     const float w_self = poly6_in(0.f, c);
     const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
     int n_pairs = 0;
-    gather<false>(p, (uint32_t)i, c.h2_cull, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
+    gather<false>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
         if (j == (uint32_t)i) {
             rho = __fadd_rn(rho, w_self);
         } else {
@@ -280,6 +266,19 @@ lambda_kernel(const float4* __restrict__ x, float4* __restrict__ xl, float* __re
     if (SAVE_PAIRS) pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
 }
 
+// w^n_corr of the delta-p pass's s_corr (Simulator_kernel.cuh:166 powf(..., n_corr)). POW = 1: powf with
+// the run-time exponent, exactly the call inside the reference; POW = 2: the same libdevice powf with the
+// exponent known to be 4.0f (the default n_corr) — the compiler folds the exponent-dependent parts of the
+// routine (~16 of ~84 instructions), the arithmetic and hence the bits are the same; POW = 0: (w*w)^2,
+// opt-in (pbf_set_option_exact_pow(0)), within 1e-5 but not bit-identical.
+template <int POW>
+__device__ __forceinline__ float pow_ncorr(float w, const SolverConsts& c) {
+    if (POW == 1) return powf(w, c.n_corr);
+    if (POW == 2) return powf(w, 4.0f);
+    const float w2 = __fmul_rn(w, w);
+    return __fmul_rn(w2, w2);
+}
+
 // shared tail of the delta-p pass: divide, clamp to MAX_DP, add, clamp to the box (f64 like the reference)
 __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float ay, float az, const SolverConsts& c) {
     const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
@@ -301,7 +300,7 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
 #ifndef PBF_REPLAY_MINBLOCKS
 #define PBF_REPLAY_MINBLOCKS 16
 #endif
-template <bool EXACT_POW>
+template <int POW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
 delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, int64_t first, int64_t n,
                       const uint2* __restrict__ pair_js,
@@ -322,14 +321,7 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
         const float4 q = __ldg(&xl[js.x]);
         const float sj = __uint_as_float(js.y);  // spiky scale of the pair, saved by the lambda pass
         const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-        const float w = poly6(sumsq(dx, dy, dz), c);
-        float pw;
-        if (EXACT_POW) {
-            pw = powf(w, c.n_corr);
-        } else {  // n_corr == 4
-            const float w2 = __fmul_rn(w, w);
-            pw = __fmul_rn(w2, w2);
-        }
+        const float pw = pow_ncorr<POW>(poly6(sumsq(dx, dy, dz), c), c);
         const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
         ax = __fmaf_rn(sc, __fmul_rn(dx, sj), ax);
         ay = __fmaf_rn(sc, __fmul_rn(dy, sj), ay);
@@ -340,9 +332,9 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
     halo_push(hp, t, out);
 }
 
-template <bool EXACT_POW, bool ONLY_OVERFLOW>
+template <int POW, bool ONLY_OVERFLOW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
-delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
+delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restrict__ x_out,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n,
                const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
@@ -353,17 +345,10 @@ delta_p_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
     const int64_t i = first + t;
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<true>(p, (uint32_t)i, c.h2_cull, xl, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
+    gather<true>(p, (uint32_t)i, c.h2_cull, xl, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
         const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
         const float r2 = sumsq(dx, dy, dz);
-        const float w = poly6(r2, c);
-        float pw;
-        if (EXACT_POW) {
-            pw = powf(w, c.n_corr);
-        } else {  // n_corr == 4
-            const float w2 = __fmul_rn(w, w);
-            pw = __fmul_rn(w2, w2);
-        }
+        const float pw = pow_ncorr<POW>(poly6(r2, c), c);
         const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
         const float s = spiky_scale(r2, c);
         ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
@@ -399,7 +384,7 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
 }
 
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
-xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
+xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
             const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
@@ -410,7 +395,10 @@ xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
     const float4 p = x[i];
     const float4 vi = v4[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<false>(p, (uint32_t)i, c.h2, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
+    // The particle itself (computeXSPH visits it) contributes 0 / (2 rho_i) = +0 per component, and an
+    // accumulator that starts at +0 never becomes -0 (x + y = -0 only for x = y = -0), so adding +0 changes
+    // no bit: it is skipped, which keeps three zero dividends off IEEE division's slow path in every warp.
+    gather<true>(p, (uint32_t)i, c.h2, x, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
         const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
         const float4 vj = __ldg(&v4[j]);
         const float w = poly6_in(r2, c);
@@ -425,14 +413,14 @@ xsph_kernel(const float4* __restrict__ x, const float4* __restrict__ v4,
 }
 
 __global__ void __launch_bounds__(GATHER_THREADS)
-neighbor_count_kernel(const float4* __restrict__ x, const uint2* __restrict__ cell_range,
+neighbor_count_kernel(const float4* __restrict__ x, const CullSoA soa, const uint2* __restrict__ cell_range,
                       uint32_t* __restrict__ count, int64_t n, const __grid_constant__ GridConsts g,
                       const __grid_constant__ SolverConsts c) {
     extern __shared__ uint2 s_words[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
     uint32_t cnt = 0;
-    gather<false>(x[i], (uint32_t)i, c.h2, x, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4, int) { cnt++; });
+    gather<false>(x[i], (uint32_t)i, c.h2, x, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4, int) { cnt++; });
     count[i] = cnt;
 }
 
@@ -442,22 +430,32 @@ neighbor_count_kernel(const float4* __restrict__ x, const uint2* __restrict__ ce
 cudaError_t preload_solver() {
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<true, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<false, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<true, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<0>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<1>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<2>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, update_velocity_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, neighbor_count_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_kernel);
     return e;
 }
 
 static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+static cudaError_t launch_pack(const float4* x, const CullScratch& cs, int64_t n_slots, cudaStream_t st, int64_t* launches) {
+    pack_kernel<<<nblocks(n_slots, 256), 256, 0, st>>>(x, cs.xs, cs.ys, cs.zs, n_slots);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+static inline CullSoA soa_of(const CullScratch& cs) { return CullSoA{cs.xs, cs.ys, cs.zs}; }
 
 size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes) {
     const size_t blocks = (size_t)((max_particles + GATHER_THREADS - 1) / GATHER_THREADS);
@@ -466,41 +464,45 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
     return *js_bytes + *cnt_bytes;
 }
 
-cudaError_t launch_lambda(const float4* x, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                          int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
-                          const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+cudaError_t launch_lambda(const float4* x, const CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
+                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    const bool exact = c.exact_pow || c.n_corr != 4.0f;
+    cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
+    if (pe != cudaSuccess) return pe;
+    const CullSoA soa = soa_of(cs);
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (!pl.js)
-        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
-    else if (exact)
-        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
+        lambda_kernel<false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
     else
-        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
+        lambda_kernel<true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
-cudaError_t launch_delta_p(const float4* xl, float4* x_out, const uint2* cell_range, int64_t first, int64_t n,
-                           const PairList& pl, const HaloPush& hp, const GridConsts& g, const SolverConsts& c,
-                           cudaStream_t st, int64_t* launches) {
+// (`cs` holds the positions the lambda pass of this iteration packed: the same ones xl carries)
+cudaError_t launch_delta_p(const float4* xl, const CullScratch& cs, float4* x_out, const uint2* cell_range,
+                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
+                           const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    const bool exact = c.exact_pow || c.n_corr != 4.0f;
+    const CullSoA soa = soa_of(cs);
+    // 2: exact powf with the exponent folded (n_corr == 4, the default); 1: exact powf, any exponent; 0: (w*w)^2
+    const int pow_mode = c.n_corr == 4.0f ? (c.exact_pow ? 2 : 0) : 1;
     const unsigned nb = nblocks(n, GATHER_THREADS);
-    if (pl.js) {
-        if (exact) {
-            delta_p_replay_kernel<true><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);
-            delta_p_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.cnt, hp, g, c);
-        } else {
-            delta_p_replay_kernel<false><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);
-            delta_p_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, pl.cnt, hp, g, c);
-        }
-        if (launches) (*launches)++;
-    } else {
-        if (exact) delta_p_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, hp, g, c);
-        else delta_p_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, x_out, cell_range, first, n, nullptr, hp, g, c);
-    }
+#define PBF_DP_LAUNCH(POW)                                                                                                   \
+    do {                                                                                                                     \
+        if (pl.js) {                                                                                                         \
+            delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);            \
+            delta_p_kernel<POW, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, cell_range, first, n, pl.cnt, hp, g, c); \
+            if (launches) (*launches)++;                                                                                     \
+        } else {                                                                                                             \
+            delta_p_kernel<POW, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, cell_range, first, n, nullptr, hp, g, c); \
+        }                                                                                                                    \
+    } while (0)
+    if (pow_mode == 2) PBF_DP_LAUNCH(2);
+    else if (pow_mode == 1) PBF_DP_LAUNCH(1);
+    else PBF_DP_LAUNCH(0);
+#undef PBF_DP_LAUNCH
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -514,19 +516,24 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
     return cudaGetLastError();
 }
 
-cudaError_t launch_xsph(const float4* x, const float4* v4, const uint2* cell_range, float* nvel_out,
-                        const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n,
-                        const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+cudaError_t launch_xsph(const float4* x, const CullScratch& cs, int64_t n_slots, const float4* v4,
+                        const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
+                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
+                        int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+    cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
+    if (pe != cudaSuccess) return pe;
+    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
-cudaError_t launch_neighbor_count(const float4* x, const uint2* cell_range, uint32_t* count, int64_t n,
-                                  const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
+cudaError_t launch_neighbor_count(const float4* x, const CullScratch& cs, const uint2* cell_range, uint32_t* count,
+                                  int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    neighbor_count_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, cell_range, count, n, g, c);
+    cudaError_t pe = launch_pack(x, cs, n, st, nullptr);
+    if (pe != cudaSuccess) return pe;
+    neighbor_count_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), cell_range, count, n, g, c);
     return cudaGetLastError();
 }
 
