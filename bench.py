@@ -600,6 +600,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     dist = None
+    # stdout carries exactly ONE line, the JSON result: anything a library prints on fd 1 meanwhile (NCCL's
+    # version banner, for one) goes to stderr
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         out = run_reference(args, rank, world)
     else:
@@ -614,8 +619,10 @@ def main():
             out = run_product(args, rank, world, dist)
         if dist:
             dist.destroy_process_group()
+    sys.stdout.flush()
     if rank == 0 and out is not None:
-        print(json.dumps(out))
+        os.write(result_fd, (json.dumps(out) + "\n").encode())
+    os.close(result_fd)
 
 
 if __name__ == "__main__":

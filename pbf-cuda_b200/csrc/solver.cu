@@ -31,7 +31,10 @@ namespace pbf {
 #ifndef PBF_PAIR_CAP
 #define PBF_PAIR_CAP 96
 #endif
-constexpr int GATHER_THREADS = 128;
+#ifndef PBF_GATHER_THREADS
+#define PBF_GATHER_THREADS 128
+#endif
+constexpr int GATHER_THREADS = PBF_GATHER_THREADS;
 constexpr int WORD_CAP = PBF_WORD_CAP;  // hit words (32 candidates each) buffered per thread before a flush
 constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pass can hand to the delta-p pass
 constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2);  // 8 KB per CTA
