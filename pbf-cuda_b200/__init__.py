@@ -41,6 +41,7 @@ EXPORTS = (
     "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
     "pbf_slab_halo_sync", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
     "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count", "pbf_get_const_div_interval",
+    "pbf_state_write", "pbf_state_read_info", "pbf_state_read", "pbf_checkpoint_save", "pbf_checkpoint_load",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
@@ -92,6 +93,12 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class StateInfo(C.Structure):
+    """pbf_state_info (include/pbf.h): header of a state file (checkpoint)."""
+    _fields_ = [("n", C.c_int64), ("frame", C.c_int64), ("params", GUIParams), ("ulim", C.c_float * 3),
+                ("llim", C.c_float * 3), ("exact_pow", C.c_int32), ("reserved", C.c_uint32), ("checksum", C.c_uint64)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -191,6 +198,42 @@ def _ptr(x):
 
 def version():
     return _lib.pbf_version().decode()
+
+
+_lib.pbf_state_write.argtypes = [C.c_char_p, C.POINTER(StateInfo), _vp, _vp, _vp]
+_lib.pbf_state_read_info.argtypes = [C.c_char_p, C.POINTER(StateInfo)]
+_lib.pbf_state_read.argtypes = [C.c_char_p, C.POINTER(StateInfo), _vp, _vp, _vp, _i64]
+_lib.pbf_checkpoint_save.argtypes = [_vp, C.c_char_p, _vp, _vp, _vp, _i64, _i64]
+_lib.pbf_checkpoint_load.argtypes = [_vp, C.c_char_p, _vp, _vp, _vp, _i64, C.POINTER(_i64), C.POINTER(_i64)]
+
+
+def state_write(path, pos, vel, iid, params, ulim, llim, frame=0, exact_pow=1):
+    """Host arrays -> state file (include/pbf.h pbf_state_write). No device involved."""
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    vel = np.ascontiguousarray(vel, np.float32).reshape(-1, 3)
+    iid = np.ascontiguousarray(iid, np.uint32).reshape(-1)
+    assert len(pos) == len(vel) == len(iid)
+    info = StateInfo()
+    info.n, info.frame, info.exact_pow = len(iid), int(frame), int(exact_pow)
+    C.memmove(C.byref(info.params), C.byref(params), C.sizeof(GUIParams))
+    info.ulim[:] = [float(v) for v in ulim]
+    info.llim[:] = [float(v) for v in llim]
+    _check(_lib.pbf_state_write(os.fsencode(path), C.byref(info), pos.ctypes.data, vel.ctypes.data, iid.ctypes.data))
+
+
+def state_info(path):
+    info = StateInfo()
+    _check(_lib.pbf_state_read_info(os.fsencode(path), C.byref(info)))
+    return info
+
+
+def state_read(path):
+    """State file -> (info, pos, vel, iid) as host arrays; verifies the checksum."""
+    info = state_info(path)
+    n = int(info.n)
+    pos, vel, iid = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.uint32)
+    _check(_lib.pbf_state_read(os.fsencode(path), C.byref(info), pos.ctypes.data, vel.ctypes.data, iid.ctypes.data, n))
+    return info, pos, vel, iid
 
 
 def default_params():
@@ -402,6 +445,17 @@ class Simulator:
         _check(_lib.pbf_get_stats(self._h, _ptr(npos), _ptr(nvel), int(n), C.byref(st)))
         return st.as_dict()
 
+    def checkpoint_save(self, path, pos, vel, iid, n, frame=0):
+        """Device state (what the next step would consume) + parameters + box -> state file."""
+        _check(_lib.pbf_checkpoint_save(self._h, os.fsencode(path), _ptr(pos), _ptr(vel), _ptr(iid), int(n), int(frame)))
+
+    def checkpoint_load(self, path, pos, vel, iid, capacity):
+        """State file -> device buffers; applies the file's parameters, box and pow option. Returns (n, frame)."""
+        n, frame = _i64(0), _i64(0)
+        _check(_lib.pbf_checkpoint_load(self._h, os.fsencode(path), _ptr(pos), _ptr(vel), _ptr(iid), int(capacity),
+                                        C.byref(n), C.byref(frame)))
+        return int(n.value), int(frame.value)
+
     def enable_stage_timing(self, on=True):
         _check(_lib.pbf_enable_stage_timing(self._h, int(on)))
 
@@ -460,6 +514,50 @@ class DoubleDamSource(ParticleSource):
         pos, vel, iid, _ = _scene_cubes(self.blocks, self.seed)
         self.count = len(iid)
         return pos, vel, iid
+
+
+class EmitterSource(ParticleSource):
+    """Mirror of host/ParticleSource.h EmitterSource: one ny x nz lattice layer at `origin` (spacing d,
+    velocity v0) every `period` calls, appended at the end of the caller's buffers, until `total` particles
+    exist. update(pos, vel, iid, capacity) writes into torch / numpy buffers in place and returns the count."""
+
+    def __init__(self, origin, ny, nz, d, v0, period, total):
+        self.origin, self.ny, self.nz, self.d = np.asarray(origin, np.float32), int(ny), int(nz), np.float32(d)
+        self.v0, self.period, self.total = np.asarray(v0, np.float32), max(int(period), 1), int(total)
+        self.count = self.calls = 0
+
+    def layer(self):
+        j, k = np.meshgrid(np.arange(self.ny, dtype=np.float32), np.arange(self.nz, dtype=np.float32), indexing="ij")
+        pos = np.empty((self.ny * self.nz, 3), np.float32)
+        pos[:, 0] = self.origin[0]
+        pos[:, 1] = (self.origin[1] + self.d * j).reshape(-1)   # float32 throughout, like the C++ loop
+        pos[:, 2] = (self.origin[2] + self.d * k).reshape(-1)
+        vel = np.broadcast_to(self.v0, pos.shape).copy()
+        iid = np.arange(self.count, self.count + len(pos), dtype=np.uint32)
+        return pos, vel, iid
+
+    def initialize(self, pos, vel, iid, capacity):
+        self.count = self.calls = 0
+        return self.update(pos, vel, iid, capacity)
+
+    def update(self, pos, vel, iid, capacity):
+        m = self.ny * self.nz
+        if self.calls % self.period == 0 and self.count + m <= min(self.total, int(capacity)):
+            p, v, i = self.layer()
+            a, b = self.count, self.count + m
+            if isinstance(pos, np.ndarray):
+                pos[a:b], vel[a:b], iid[a:b] = p, v, i
+            else:   # torch tensors on the device
+                import torch
+                pos[a:b] = torch.from_numpy(p).to(pos.device)
+                vel[a:b] = torch.from_numpy(v).to(vel.device)
+                iid[a:b] = torch.from_numpy(i.astype(np.int64)).to(iid.device).to(iid.dtype)
+            self.count = b
+        self.calls += 1
+        return self.count
+
+    def reset(self, pos, vel, iid, capacity):
+        return self.initialize(pos, vel, iid, capacity)
 
 
 def _scene_cubes(blocks, seed):

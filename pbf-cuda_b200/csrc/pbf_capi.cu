@@ -13,6 +13,8 @@
 #include <unistd.h>
 
 #include <new>
+#include <string>
+#include <vector>
 
 #include "pbf_internal.h"
 
@@ -275,6 +277,64 @@ void free_all(pbf_sim* s) {
 }
 
 }  // namespace
+
+// ---- state files (checkpoint / resume) -------------------------------------------------------------
+
+namespace {
+
+struct StateHeader {            // 128 bytes on disk, little endian
+    char magic[8];              // "PBFSTAT1"
+    uint32_t version;           // 1
+    uint32_t header_bytes;      // 128
+    int64_t n;
+    int64_t frame;
+    pbf_params params;          // 44 bytes
+    float ulim[3];
+    float llim[3];
+    int32_t exact_pow;
+    uint64_t checksum;          // FNV-1a-64 over the payload, 8 bytes at a time (+ byte-wise tail)
+    uint8_t pad[128 - 8 - 4 - 4 - 8 - 8 - 44 - 12 - 12 - 4 - 8];
+} __attribute__((packed));
+static_assert(sizeof(StateHeader) == 128, "state header is 128 bytes");
+
+uint64_t fnv1a64(uint64_t h, const void* data, size_t bytes) {
+    const uint8_t* p = (const uint8_t*)data;
+    const uint64_t prime = 1099511628211ull;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * prime;
+    }
+    for (; i < bytes; i++) h = (h ^ p[i]) * prime;
+    return h;
+}
+uint64_t payload_checksum(const float* pos, const float* vel, const uint32_t* iid, int64_t n) {
+    uint64_t h = 14695981039346656037ull;
+    h = fnv1a64(h, pos, (size_t)n * 12);
+    h = fnv1a64(h, vel, (size_t)n * 12);
+    return fnv1a64(h, iid, (size_t)n * 4);
+}
+int read_header(FILE* f, const char* path, StateHeader* hd) {
+    if (fread(hd, 1, sizeof(*hd), f) != sizeof(*hd)) return fail(PBF_ERR_INVALID, "%s: shorter than a state header", path);
+    if (memcmp(hd->magic, "PBFSTAT1", 8) != 0) return fail(PBF_ERR_INVALID, "%s: not a pbf state file (bad magic)", path);
+    if (hd->version != 1 || hd->header_bytes != sizeof(*hd)) return fail(PBF_ERR_INVALID, "%s: unsupported state version %u", path, hd->version);
+    if (hd->n < 0 || hd->n >= ((int64_t)1 << 30)) return fail(PBF_ERR_INVALID, "%s: implausible particle count %lld", path, (long long)hd->n);
+    return PBF_OK;
+}
+void info_of(const StateHeader& hd, pbf_state_info* out) {
+    memset(out, 0, sizeof(*out));
+    out->n = hd.n;
+    out->frame = hd.frame;
+    out->params = hd.params;
+    memcpy(out->ulim, hd.ulim, sizeof(out->ulim));
+    memcpy(out->llim, hd.llim, sizeof(out->llim));
+    out->exact_pow = hd.exact_pow;
+    out->checksum = hd.checksum;
+}
+
+}  // namespace
+
 
 extern "C" {
 
@@ -1117,6 +1177,135 @@ int pbf_scene_block_device(const float origin[3], const int32_t n[3], float spac
                            uint32_t first_iid, float* d_pos, float* d_vel, uint32_t* d_iid, void* stream) {
     if (!origin || !n || !d_pos || !d_vel || !d_iid) return fail(PBF_ERR_INVALID, "null argument");
     CUDA_TRY(launch_scene_block(origin, n, spacing, seed, first_iid, 0, n[0], d_pos, d_vel, d_iid, (cudaStream_t)stream));
+    return PBF_OK;
+}
+
+// ---- state files (checkpoint / resume), see include/pbf.h ----------------------------------------
+
+int pbf_state_write(const char* path, const pbf_state_info* info, const float* pos, const float* vel, const uint32_t* iid) {
+    if (!path || !info) return fail(PBF_ERR_INVALID, "null argument");
+    if (info->n < 0 || info->n >= ((int64_t)1 << 30)) return fail(PBF_ERR_INVALID, "bad particle count");
+    if (info->n > 0 && (!pos || !vel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
+    StateHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "PBFSTAT1", 8);
+    hd.version = 1;
+    hd.header_bytes = sizeof(hd);
+    hd.n = info->n;
+    hd.frame = info->frame;
+    hd.params = info->params;
+    memcpy(hd.ulim, info->ulim, sizeof(hd.ulim));
+    memcpy(hd.llim, info->llim, sizeof(hd.llim));
+    hd.exact_pow = info->exact_pow;
+    hd.checksum = payload_checksum(pos, vel, iid, info->n);
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(PBF_ERR_INVALID, "%s: cannot open for writing", tmp.c_str());
+    const size_t n = (size_t)info->n;
+    bool ok = fwrite(&hd, 1, sizeof(hd), f) == sizeof(hd);
+    ok = ok && fwrite(pos, 12, n, f) == n && fwrite(vel, 12, n, f) == n && fwrite(iid, 4, n, f) == n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { remove(tmp.c_str()); return fail(PBF_ERR_INVALID, "%s: write failed", tmp.c_str()); }
+    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(PBF_ERR_INVALID, "%s: rename failed", path); }
+    return PBF_OK;
+}
+
+int pbf_state_read_info(const char* path, pbf_state_info* out) {
+    if (!path || !out) return fail(PBF_ERR_INVALID, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(PBF_ERR_INVALID, "%s: cannot open", path);
+    StateHeader hd;
+    int rc = read_header(f, path, &hd);
+    fclose(f);
+    if (rc) return rc;
+    info_of(hd, out);
+    return PBF_OK;
+}
+
+int pbf_state_read(const char* path, pbf_state_info* out, float* pos, float* vel, uint32_t* iid, int64_t capacity) {
+    if (!path || !out) return fail(PBF_ERR_INVALID, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(PBF_ERR_INVALID, "%s: cannot open", path);
+    StateHeader hd;
+    int rc = read_header(f, path, &hd);
+    if (rc) { fclose(f); return rc; }
+    if (hd.n > capacity) { fclose(f); return fail(PBF_ERR_CAPACITY, "%s holds %lld particles, the buffers %lld", path, (long long)hd.n, (long long)capacity); }
+    if (hd.n > 0 && (!pos || !vel || !iid)) { fclose(f); return fail(PBF_ERR_INVALID, "null particle buffer"); }
+    const size_t n = (size_t)hd.n;
+    const bool ok = fread(pos, 12, n, f) == n && fread(vel, 12, n, f) == n && fread(iid, 4, n, f) == n;
+    char extra;
+    const bool trailing = ok && fread(&extra, 1, 1, f) == 1;
+    fclose(f);
+    if (!ok) return fail(PBF_ERR_INVALID, "%s: truncated (header says %lld particles)", path, (long long)hd.n);
+    if (trailing) return fail(PBF_ERR_INVALID, "%s: longer than its header says", path);
+    const uint64_t sum = payload_checksum(pos, vel, iid, hd.n);
+    if (sum != hd.checksum) return fail(PBF_ERR_INVALID, "%s: checksum mismatch (file %016llx, data %016llx)", path, (unsigned long long)hd.checksum, (unsigned long long)sum);
+    info_of(hd, out);
+    return PBF_OK;
+}
+
+int pbf_checkpoint_save(pbf_sim* s, const char* path, const float* pos, const float* vel, const uint32_t* iid, int64_t n, int64_t frame) {
+    if (!s || !path) return fail(PBF_ERR_INVALID, "null argument");
+    if (n < 0 || n > s->max_particles) return fail(PBF_ERR_INVALID, "bad n");
+    if (n > 0 && (!pos || !vel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    std::vector<float> h_pos((size_t)n * 3), h_vel((size_t)n * 3);
+    std::vector<uint32_t> h_iid((size_t)n);
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpy(h_pos.data(), pos, (size_t)n * 12, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_vel.data(), vel, (size_t)n * 12, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_iid.data(), iid, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    pbf_state_info info;
+    memset(&info, 0, sizeof(info));
+    info.n = n;
+    info.frame = frame;
+    info.params = s->p;
+    memcpy(info.ulim, s->ulim, sizeof(info.ulim));
+    memcpy(info.llim, s->llim, sizeof(info.llim));
+    info.exact_pow = s->exact_pow;
+    return pbf_state_write(path, &info, h_pos.data(), h_vel.data(), h_iid.data());
+}
+
+int pbf_checkpoint_load(pbf_sim* s, const char* path, float* pos, float* vel, uint32_t* iid, int64_t capacity, int64_t* n_out, int64_t* frame_out) {
+    if (!s || !path) return fail(PBF_ERR_INVALID, "null argument");
+    pbf_state_info info;
+    int rc = pbf_state_read_info(path, &info);
+    if (rc) return rc;
+    if (info.n > capacity || info.n > s->max_particles)
+        return fail(PBF_ERR_CAPACITY, "%s holds %lld particles, the handle %lld, the buffers %lld", path, (long long)info.n, (long long)s->max_particles, (long long)capacity);
+    if (info.n > 0 && (!pos || !vel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
+    std::vector<float> h_pos((size_t)info.n * 3), h_vel((size_t)info.n * 3);
+    std::vector<uint32_t> h_iid((size_t)info.n);
+    rc = pbf_state_read(path, &info, h_pos.data(), h_vel.data(), h_iid.data(), info.n);
+    if (rc) return rc;
+    // parameters and box first: a file that does not fit this handle must not leave it half-configured
+    const pbf_params old_p = s->p;
+    float old_u[3], old_l[3];
+    memcpy(old_u, s->ulim, sizeof(old_u));
+    memcpy(old_l, s->llim, sizeof(old_l));
+    const int old_exact = s->exact_pow;
+    s->exact_pow = info.exact_pow ? 1 : 0;
+    rc = pbf_set_params(s, &info.params);
+    if (rc == PBF_OK) rc = pbf_set_lim(s, info.ulim, info.llim);
+    if (rc != PBF_OK) {
+        char msg[sizeof(g_err)];
+        snprintf(msg, sizeof(msg), "%s", g_err);
+        s->exact_pow = old_exact;
+        pbf_set_params(s, &old_p);
+        pbf_set_lim(s, old_u, old_l);
+        return fail(rc, "%s does not fit this handle: %s", path, msg);
+    }
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (info.n > 0) {
+        CUDA_TRY(cudaMemcpy(pos, h_pos.data(), (size_t)info.n * 12, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(vel, h_vel.data(), (size_t)info.n * 12, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(iid, h_iid.data(), (size_t)info.n * 4, cudaMemcpyHostToDevice));
+    }
+    if (n_out) *n_out = info.n;
+    if (frame_out) *frame_out = info.frame;
     return PBF_OK;
 }
 

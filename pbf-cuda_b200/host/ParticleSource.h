@@ -66,3 +66,55 @@ private:
     std::vector<pbf_host::Block> m_blocks;
     int m_count;
 };
+
+// An emitter: the use the reference's interface was made for but never shipped — FluidSystem::stepSource()
+// (fluids/FluidSystem.cpp:92-97, defined but never called) hands update() the CURRENT ping-pong buffers and
+// takes the returned count, while both shipped sources return a constant (DoubleDamSource.cpp:43-45).
+// EmitterSource appends one lattice layer (ns.x = 1 layers of ny x nz particles, spacing `d`, at `origin`,
+// all with velocity `v0`) every `period` calls, at the end of the caller's buffers — the solver accepts any
+// order and permutes iid along — until `total` particles exist. iid continues the running count.
+// Deterministic (no jitter): a run is a function of (origin, ny, nz, d, v0, period, total) and the call count.
+class EmitterSource : public ParticleSource {
+public:
+    EmitterSource(float3 origin, int ny, int nz, float d, float3 v0, int period, int total)
+        : m_origin(origin), m_ny(ny), m_nz(nz), m_d(d), m_v0(v0), m_period(period < 1 ? 1 : period), m_total(total),
+          m_count(0), m_calls(0) {}
+    int initialize(uint pos, uint vel, uint iid, int max_nparticle) {
+        m_count = 0;
+        m_calls = 0;
+        return update(pos, vel, iid, max_nparticle);
+    }
+    int update(uint pos, uint vel, uint iid, int max_nparticle) {
+        const int layer = m_ny * m_nz;
+        const int limit = m_total < max_nparticle ? m_total : max_nparticle;
+        if (m_calls % m_period == 0 && m_count + layer <= limit) {
+            std::vector<float> h_pos((size_t)layer * 3), h_vel((size_t)layer * 3);
+            std::vector<uint32_t> h_iid((size_t)layer);
+            for (int j = 0; j < m_ny; j++)
+                for (int k = 0; k < m_nz; k++) {
+                    const int e = j * m_nz + k;
+                    h_pos[3 * e] = m_origin.x;
+                    h_pos[3 * e + 1] = m_origin.y + m_d * (float)j;
+                    h_pos[3 * e + 2] = m_origin.z + m_d * (float)k;
+                    h_vel[3 * e] = m_v0.x; h_vel[3 * e + 1] = m_v0.y; h_vel[3 * e + 2] = m_v0.z;
+                    h_iid[e] = (uint32_t)(m_count + e);
+                }
+            DeviceBuffers& b = DeviceBuffers::getInstance();
+            b.subData(pos, (size_t)m_count * 12, (size_t)layer * 12, h_pos.data());
+            b.subData(vel, (size_t)m_count * 12, (size_t)layer * 12, h_vel.data());
+            b.subData(iid, (size_t)m_count * 4, (size_t)layer * 4, h_iid.data());
+            m_count += layer;
+        }
+        m_calls++;
+        return m_count;
+    }
+    int reset(uint pos, uint vel, uint iid, int max_nparticle) { return initialize(pos, vel, iid, max_nparticle); }
+    // resume from a state file: `count` particles exist after `calls` update() calls
+    void restore(int count, int calls) { m_count = count; m_calls = calls; }
+private:
+    float3 m_origin;
+    int m_ny, m_nz;
+    float m_d;
+    float3 m_v0;
+    int m_period, m_total, m_count, m_calls;
+};

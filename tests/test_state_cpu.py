@@ -1,0 +1,83 @@
+"""State files (include/pbf.h pbf_state_*): host-side I/O of the checkpoint format — no device involved.
+SURVEY.md 8(f) rank 1; the reference has no dump / resume, so the contract is the header's own."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+
+def _state(n, seed=3):
+    rng = np.random.default_rng(seed)
+    pos = rng.random((n, 3), dtype=np.float32) * 4 - 2
+    vel = rng.standard_normal((n, 3)).astype(np.float32)
+    iid = rng.permutation(n).astype(np.uint32)
+    return pos, vel, iid
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 32000])
+def test_round_trip_is_bit_exact(pbf, tmp_path, n):
+    pos, vel, iid = _state(n)
+    p = pbf.default_params()
+    p.niter, p.n_corr, p.k_boundaryDensity = 3, 3.0, 0.25
+    f = str(tmp_path / "a.pbfstate")
+    pbf.state_write(f, pos, vel, iid, p, (4.0, 2.0, 4.0), (-2.0, -2.0, 0.0), frame=123, exact_pow=0)
+    assert os.path.getsize(f) == 128 + 28 * n and not os.path.exists(f + ".tmp")
+    info, a, b, c = pbf.state_read(f)
+    assert (info.n, info.frame, info.exact_pow) == (n, 123, 0)
+    assert (info.params.niter, info.params.n_corr, info.params.k_boundaryDensity) == (3, 3.0, 0.25)
+    assert list(info.ulim) == [4.0, 2.0, 4.0] and list(info.llim) == [-2.0, -2.0, 0.0]
+    assert a.tobytes() == pos.tobytes() and b.tobytes() == vel.tobytes() and c.tobytes() == iid.tobytes()
+    assert pbf.state_info(f).checksum == info.checksum
+
+
+def test_header_layout_is_the_documented_one(pbf, tmp_path):
+    pos, vel, iid = _state(5)
+    f = str(tmp_path / "h.pbfstate")
+    pbf.state_write(f, pos, vel, iid, pbf.default_params(), (2, 2, 4), (-2, -2, 0), frame=9)
+    raw = open(f, "rb").read()
+    assert raw[:8] == b"PBFSTAT1"
+    version, header_bytes, n, frame = struct.unpack_from("<IIqq", raw, 8)
+    assert (version, header_bytes, n, frame) == (1, 128, 5, 9)
+    niter, pho0, g, h, dt = struct.unpack_from("<iffff", raw, 32)
+    assert (niter, pho0, h) == (4, 8000.0, np.float32(0.1)) and np.float32(dt) == np.float32(0.0083)
+    assert np.frombuffer(raw, np.float32, 15, 128).tobytes() == pos.tobytes()
+    # the checksum covers the payload: same payload, different header -> same checksum
+    f2 = str(tmp_path / "h2.pbfstate")
+    pbf.state_write(f2, pos, vel, iid, pbf.default_params(), (2, 2, 4), (-2, -2, 0), frame=10)
+    assert pbf.state_info(f).checksum == pbf.state_info(f2).checksum
+    iid2 = iid.copy()
+    iid2[0] ^= 1
+    pbf.state_write(f2, pos, vel, iid2, pbf.default_params(), (2, 2, 4), (-2, -2, 0), frame=10)
+    assert pbf.state_info(f).checksum != pbf.state_info(f2).checksum
+
+
+def test_damaged_files_are_refused(pbf, tmp_path):
+    pos, vel, iid = _state(100)
+    f = str(tmp_path / "d.pbfstate")
+    pbf.state_write(f, pos, vel, iid, pbf.default_params(), (2, 2, 4), (-2, -2, 0))
+    good = open(f, "rb").read()
+
+    def expect(data, what, code=pbf.ERR_INVALID):
+        open(f, "wb").write(data)
+        with pytest.raises(pbf.PbfError) as e:
+            pbf.state_read(f)
+        assert e.value.code == code and what in str(e.value)
+
+    flipped = bytearray(good)
+    flipped[128 + 777] ^= 0x10
+    expect(bytes(flipped), "checksum mismatch")
+    expect(good[:-1], "truncated")
+    expect(good + b"\0", "longer than its header")
+    expect(good[:64], "shorter than a state header")
+    expect(b"NOTASTAT" + good[8:], "bad magic")
+    expect(good[:8] + struct.pack("<I", 2) + good[12:], "unsupported state version")
+    with pytest.raises(pbf.PbfError):
+        pbf.state_info(str(tmp_path / "missing.pbfstate"))
+    # capacity of the caller's buffers is checked before anything is written into them
+    open(f, "wb").write(good)
+    import ctypes as C
+    info = pbf.StateInfo()
+    small = np.zeros((10, 3), np.float32)
+    rc = pbf.lib().pbf_state_read(os.fsencode(f), C.byref(info), small.ctypes.data, small.ctypes.data, small.ctypes.data, 10)
+    assert rc == pbf.ERR_CAPACITY and not small.any()

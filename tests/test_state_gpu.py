@@ -1,0 +1,157 @@
+"""Checkpoint / resume on the device (pbf_checkpoint_save / _load, pbf_headless --save / --resume / --stats):
+a resumed run must reproduce the uninterrupted run BIT FOR BIT — the state file carries the particle order
+(the tie-break of the next stable sort), the parameters, the box and the frame counter of the wall schedule."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _run(pbf, torch, sim, d, d_iid, n, ulim, llim, first, steps, moving):
+    for s in range(first, first + steps):
+        if moving:
+            sim.setLim(*pbf.wall_lim(ulim, llim, (2, 0, 0), (0, 0, 0), 0.05, s))
+        sim.step(d[0], d[1], d[2], d[3], d_iid, n)
+        d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("moving", [0, 1])
+def test_resume_is_bit_identical(pbf, torch, tmp_path, moving):
+    pos, vel, iid, ulim, llim = pbf.scene_double_dam_reference()
+    n = len(iid)
+    params = pbf.default_params()
+    params.niter = 3   # not the default, so that the file's parameters matter
+
+    def fresh():
+        sim = pbf.Simulator(params, (4.0, 2.0, 4.0), llim, 40000)
+        sim.setLim(ulim, llim)
+        return sim
+
+    def upload():
+        d = [torch.from_numpy(a).cuda() for a in (pos, np.zeros_like(pos), vel, np.zeros_like(vel))]
+        return d, torch.from_numpy(iid.astype(np.int64)).cuda().to(torch.int32)
+
+    # uninterrupted: 12 steps
+    sim = fresh()
+    d, d_iid = upload()
+    _run(pbf, torch, sim, d, d_iid, n, ulim, llim, 0, 12, moving)
+    want = (d[0].cpu().numpy(), d[2].cpu().numpy(), d_iid.cpu().numpy())
+    sim.close()
+
+    # 5 steps, checkpoint, throw everything away, resume in a handle created with DEFAULT parameters
+    sim = fresh()
+    d, d_iid = upload()
+    _run(pbf, torch, sim, d, d_iid, n, ulim, llim, 0, 5, moving)
+    ck = str(tmp_path / "ck.pbfstate")
+    sim.checkpoint_save(ck, d[0], d[2], d_iid, n, frame=5)
+    sim.close()
+    info = pbf.state_info(ck)
+    assert (info.n, info.frame, info.params.niter) == (n, 5, 3)
+
+    sim2 = pbf.Simulator(pbf.default_params(), (4.0, 2.0, 4.0), llim, 40000)
+    e = [torch.zeros((40000, 3), dtype=torch.float32, device="cuda") for _ in range(4)]
+    e_iid = torch.zeros(40000, dtype=torch.int32, device="cuda")
+    n2, frame = sim2.checkpoint_load(ck, e[0], e[2], e_iid, 40000)
+    assert (n2, frame) == (n, 5) and sim2.saveParams().niter == 3
+    _run(pbf, torch, sim2, e, e_iid, n, ulim, llim, frame, 7, moving)
+    got = (e[0][:n].cpu().numpy(), e[2][:n].cpu().numpy(), e_iid[:n].cpu().numpy())
+    for a, b in zip(want, got):
+        assert a.tobytes() == b.tobytes()
+
+    # a file that does not fit the handle leaves the handle as it was
+    big = str(tmp_path / "big.pbfstate")
+    pbf.state_write(big, pos, vel, iid, params, (400.0, 200.0, 4.0), llim)
+    before = (sim2.saveParams().niter, sim2.getLim())
+    with pytest.raises(pbf.PbfError) as err:
+        sim2.checkpoint_load(big, e[0], e[2], e_iid, 40000)
+    assert err.value.code == pbf.ERR_CAPACITY
+    after = (sim2.saveParams().niter, sim2.getLim())
+    assert before[0] == after[0] and np.array_equal(np.asarray(before[1]), np.asarray(after[1]))
+    with pytest.raises(pbf.PbfError) as err:
+        sim2.checkpoint_load(ck, e[0], e[2], e_iid, 100)
+    assert err.value.code == pbf.ERR_CAPACITY
+    sim2.close()
+
+
+def _load_dump(path):
+    raw = np.fromfile(path, np.uint8)
+    n = int(raw[:4].view(np.int32)[0])
+    return raw[4:4 + 12 * n].tobytes(), raw[4 + 12 * n:4 + 24 * n].tobytes(), raw[4 + 24 * n:].tobytes()
+
+
+@pytest.mark.parametrize("moving", [0, 1])
+def test_headless_harness_save_resume_and_stats(pbf, torch, tmp_path, moving):
+    exe = os.path.join(ROOT, "pbf-cuda_b200", "pbf_headless")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe), "harness"], stdout=subprocess.DEVNULL)
+    full, part, ck, stats = (str(tmp_path / x) for x in ("full.bin", "part.bin", "ck.pbfstate", "stats.jsonl"))
+    a = subprocess.run([exe, "20", str(moving), full], capture_output=True, text=True, check=True)
+    subprocess.run([exe, "8", str(moving), "--save", ck, "--save-every", "3", "--stats", stats, "--stats-every", "4"],
+                   capture_output=True, text=True, check=True)
+    assert pbf.state_info(ck).frame == 8
+    b = subprocess.run([exe, "12", str(moving), part, "--resume", ck, "--stats", stats, "--stats-every", "4"],
+                       capture_output=True, text=True, check=True)
+    assert _load_dump(full) == _load_dump(part)
+    ja, jb = json.loads(a.stdout), json.loads(b.stdout)
+    assert ja["frame"] == jb["frame"] == 20 and ja["kinetic_energy"] == jb["kinetic_energy"]
+    lines = [json.loads(l) for l in open(stats)]
+    assert [l["step"] for l in lines] == [4, 8, 12, 16, 20]
+    assert all(l["ms_per_step"] > 0 and l["kinetic_energy"] > 0 and np.isfinite(l["density_err_max"]) for l in lines)
+    assert lines[-1]["kinetic_energy"] == ja["kinetic_energy"]
+    r = subprocess.run([exe, "1", "0", "--resume", str(tmp_path / "missing")], capture_output=True, text=True)
+    assert r.returncode != 0 and "cannot open" in r.stderr
+
+
+def test_emitter_source_grows_the_scene_and_matches_the_harness(pbf, torch, tmp_path):
+    """a ParticleSource whose update() changes the count every other step. The C++
+    harness (EmitterSource + stepSource(), host/ParticleSource.h) and the Python mirror must agree bit for
+    bit; the count follows the schedule; iid stays a permutation; everything stays inside the box."""
+    exe = os.path.join(ROOT, "pbf-cuda_b200", "pbf_headless")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe), "harness"], stdout=subprocess.DEVNULL)
+    steps, total = 41, 4000
+    dump = str(tmp_path / "jet.bin")
+    r = subprocess.run([exe, str(steps), "0", dump, "--emitter", str(total)], capture_output=True, text=True, check=True)
+    info = json.loads(r.stdout)
+    layer = 16 * 16
+    want_n = min((steps - 1) // 2 + 1, total // layer) * layer   # layers at calls 0, 2, 4, ... while they fit
+    assert info["particles"] == want_n == 15 * layer
+
+    cap = 130000
+    ulim, llim = (2.0, 2.0, 4.0), (-2.0, -2.0, 0.0)
+    sim = pbf.Simulator(pbf.default_params(), (4.0, 2.0, 4.0), llim, cap)
+    sim.setLim(ulim, llim)
+    d = [torch.zeros((cap, 3), dtype=torch.float32, device="cuda") for _ in range(4)]
+    d_iid = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    src = pbf.EmitterSource((-1.9, -0.4, 2.0), 16, 16, 0.05, (3.0, 0.0, 0.0), 2, total)
+    n = src.initialize(d[0], d[2], d_iid, cap)
+    counts = []
+    for s in range(steps):
+        if s > 0:
+            n = src.update(d[0], d[2], d_iid, cap)
+        counts.append(n)
+        sim.step(d[0], d[1], d[2], d[3], d_iid, n)
+        d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+    torch.cuda.synchronize()
+    assert counts[0] == layer and counts[1] == layer and counts[2] == 2 * layer and counts[-1] == want_n
+    g_pos, g_vel, g_iid = d[0][:n].cpu().numpy(), d[2][:n].cpu().numpy(), d_iid[:n].cpu().numpy().view(np.uint32)
+    c_pos, c_vel, c_iid = _load_dump(dump)
+    assert g_pos.tobytes() == c_pos and g_vel.tobytes() == c_vel and g_iid.tobytes() == c_iid
+    assert np.array_equal(np.sort(g_iid), np.arange(n, dtype=np.uint32))
+    assert (g_pos >= np.asarray(llim, np.float32) + 1e-3 - 1e-6).all() and (g_pos <= np.asarray(ulim, np.float32) - 1e-3 + 1e-6).all()
+    assert np.isfinite(g_vel).all() and g_pos[:, 0].max() > -1.0   # the jet travelled
+    sim.close()
