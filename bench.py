@@ -96,8 +96,8 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def scene_state(pbf, torch, name, dev):
-    sc = pbf.SCENES[name]
+def scene_state(pbf, torch, name, dev, sc=None):
+    sc = sc or pbf.SCENES[name]
     if "blocks" in sc:
         n = sum(int(np.prod(b[1])) for b in sc["blocks"])
         pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
@@ -530,7 +530,10 @@ def run_reference(args, rank, world):
     pbf = importlib.import_module("pbf-cuda_b200")
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    sc, n, pos, vel, iid = scene_state(pbf, torch, args.scene, dev)   # same generator, same bits
+    # N > 1: the product arm runs ONE scene over N GPUs (weak: the block repeated N times along x; strong: the
+    # named scene); the single-GPU reference gets that same scene, whole, on one GPU
+    sc_n = slab_scene(pbf, args.scene, world, args.scaling) if (world > 1 and not args.replicas) else None
+    sc, n, pos, vel, iid = scene_state(pbf, torch, args.scene, dev, sc_n)   # same generator, same bits
     npos, nvel = torch.zeros_like(pos), torch.zeros_like(vel)
     ref = _ref.RefSimulator(O.default_params(), sc.get("ulim_max", sc["ulim"]), sc["llim"], n)
     ref.set_lim(sc["ulim"], sc["llim"])
@@ -564,8 +567,9 @@ def run_reference(args, rank, world):
     value = n * args.steps / (total_ms * 1e-3)
     return {"impl": "reference", "metric": "particle-steps/s", "value": round(value, 1), "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.scene, sc, n),
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.scene + (" x%d along x (weak)" % world if (sc_n is not None and args.scaling == "weak") else ""), sc, n),
                        "note": "the reference's own Simulator.cu + Simulator_kernel.cuh compiled unchanged for sm_100 "
                                "(oracle/_ref/libpbf_ref.so), Thrust sort and its cudaDeviceSynchronize fences kept, GL interop "
                                "excluded; runs on one GPU (the reference is single-GPU, rank 0 only)",
