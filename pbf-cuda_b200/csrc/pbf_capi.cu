@@ -134,6 +134,11 @@ struct pbf_sim {
     // verified constant division (refresh_consts)
     bool div_verified = false;
     float div_d = 0.f, div_rcp = 0.f, div_lo = 1.f, div_hi = 0.f;
+    // branch-free spiky scale (pbf_math.cuh spiky_scale_fast): verified exhaustively for this h, or off
+    bool spiky_checked = false;
+    float spiky_h = 0.f;
+    int spiky_ok = 0;
+    unsigned long long spiky_mismatches = 0;
 
     int64_t launches = 0;
     bool timing = false;
@@ -252,6 +257,25 @@ int refresh_consts(pbf_sim* s) {
     c.pho0_rcp = s->div_rcp;
     c.div_lo = s->div_lo;
     c.div_hi = s->div_hi;
+    // the same idea for the spiky scale: every float r2 the sweeps can hand to it is checked on the device
+    // whenever h changes; PBF_NO_FAST_SPIKY=1 keeps the sqrt.rn / div.rn sequence
+    if (!(s->spiky_checked && s->spiky_h == p.h)) {
+        s->spiky_ok = 0;
+        s->spiky_mismatches = 0;
+        const char* off = getenv("PBF_NO_FAST_SPIKY");
+        if (!(off && off[0] == '1') && cudaSetDevice(s->device) == cudaSuccess) {
+            unsigned long long bad = ~0ull;
+            if (verify_spiky(c, c.h2_cull, &bad, nullptr) == cudaSuccess) {
+                s->spiky_mismatches = bad;
+                s->spiky_ok = bad == 0 ? 1 : 0;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        s->spiky_h = p.h;
+        s->spiky_checked = true;
+    }
+    c.fast_spiky = s->spiky_ok;
     return PBF_OK;
 }
 
@@ -510,6 +534,12 @@ int pbf_get_lim(const pbf_sim* s, float ulim[3], float llim[3]) {
 int pbf_get_const_div_interval(const pbf_sim* s, float* lo, float* hi) {
     if (!s || !lo || !hi) return fail(PBF_ERR_INVALID, "null argument");
     *lo = s->div_lo; *hi = s->div_hi;
+    return PBF_OK;
+}
+int pbf_get_fast_spiky(const pbf_sim* s, int32_t* on, uint64_t* mismatches) {
+    if (!s || !on || !mismatches) return fail(PBF_ERR_INVALID, "null argument");
+    *on = s->spiky_ok;
+    *mismatches = (uint64_t)s->spiky_mismatches;
     return PBF_OK;
 }
 int pbf_get_grid_dim(const pbf_sim* s, int32_t dim[3]) {

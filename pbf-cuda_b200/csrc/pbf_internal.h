@@ -74,6 +74,8 @@ struct SolverConsts {
     // |a| in [div_lo, div_hi], an interval VERIFIED exhaustively on the device against div.rn
     float pho0_rcp;    // RN(1 / pho0)
     float div_lo, div_hi;
+    // 1: spiky_scale_fast (pbf_math.cuh) matched spiky_scale for EVERY float r2 in [0, h2_cull] on this device
+    int32_t fast_spiky;
 };
 
 // (key, source index) pair the radix sort moves; one 8-byte transaction per element.
@@ -191,6 +193,8 @@ cudaError_t launch_neighbor_count(const float4* x, const CullScratch& cs, const 
 // stats.cu: exhaustive check of the reciprocal division sequence for divisor d over all 2^32 bit
 // patterns of the dividend; returns the verified interval of |a| around 1 (lo > hi: none)
 cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStream_t st);
+// stats.cu: exhaustive comparison of spiky_scale_fast with spiky_scale over every float r2 in [0, top]
+cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* mismatches, cudaStream_t st);
 
 // force-load every kernel of a translation unit (see the comment at preload_solver in solver.cu)
 cudaError_t preload_advect_key();

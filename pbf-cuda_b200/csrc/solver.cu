@@ -216,7 +216,7 @@ pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restr
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
 constexpr uint32_t PAIR_OVERFLOW = 1u << 31;
 
-template <bool SAVE_PAIRS>
+template <bool SAVE_PAIRS, bool FAST_SPIKY>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
@@ -242,7 +242,7 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
             const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
             const float r2 = sumsq(dx, dy, dz);
             rho = __fadd_rn(rho, poly6(r2, c));
-            const float s = spiky_scale(r2, c);
+            const float s = FAST_SPIKY ? spiky_scale_fast(r2, c) : spiky_scale(r2, c);
             float gx = __fmul_rn(dx, s), gy = __fmul_rn(dy, s), gz = __fmul_rn(dz, s);
             div3_pho0(gx, gy, gz, c);
             gix = __fadd_rn(gix, gx);
@@ -433,8 +433,10 @@ neighbor_count_kernel(const float4* __restrict__ x, const CullSoA soa, const uin
 cudaError_t preload_solver() {
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<0>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<2>);
@@ -475,10 +477,14 @@ cudaError_t launch_lambda(const float4* x, const CullScratch& cs, int64_t n_slot
     if (pe != cudaSuccess) return pe;
     const CullSoA soa = soa_of(cs);
     const unsigned nb = nblocks(n, GATHER_THREADS);
-    if (!pl.js)
-        lambda_kernel<false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+    if (!pl.js && !c.fast_spiky)
+        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+    else if (!pl.js)
+        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+    else if (!c.fast_spiky)
+        lambda_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
     else
-        lambda_kernel<true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
+        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -4,7 +4,7 @@
 // tree order, f64 accumulation; the host adds the per-block partials in index order.
 #include <string.h>
 
-#include "pbf_internal.h"
+#include "pbf_math.cuh"
 
 namespace pbf {
 
@@ -88,9 +88,40 @@ cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStrea
     return cudaSuccess;
 }
 
+// ---- exhaustive verification of the branch-free spiky scale (pbf_math.cuh spiky_scale_fast) -------------
+// Every float r2 from +0 up to `top` (bit patterns 0 .. bits(top), which order like the values): does the fast
+// sequence give the bits of the exact one? Counts the mismatches; the caller uses the fast sequence only if
+// there are none.
+__global__ void __launch_bounds__(256) spiky_check_kernel(uint32_t top_bits, SolverConsts c, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (uint64_t b = (uint64_t)blockIdx.x * 256 + threadIdx.x; b <= top_bits; b += (uint64_t)gridDim.x * 256) {
+        const float r2 = __uint_as_float((uint32_t)b);
+        if (__float_as_uint(spiky_scale_fast(r2, c)) != __float_as_uint(spiky_scale(r2, c))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* mismatches, cudaStream_t st) {
+    unsigned long long* dev = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dev, 8);
+    if (e != cudaSuccess) return e;
+    uint32_t top_bits;
+    memcpy(&top_bits, &top, 4);
+    e = cudaMemsetAsync(dev, 0, 8, st);
+    if (e == cudaSuccess) {
+        spiky_check_kernel<<<148 * 16, 256, 0, st>>>(top_bits, c, dev);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches, dev, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return e;
+}
+
 cudaError_t preload_stats() {
     cudaFuncAttributes a;
     cudaError_t e = cudaFuncGetAttributes(&a, const_div_check_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spiky_check_kernel);
     return e != cudaSuccess ? e : cudaFuncGetAttributes(&a, stats_kernel);
 }
 

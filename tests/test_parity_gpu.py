@@ -398,3 +398,37 @@ def test_const_division_sequence_is_verified_and_used(pbf, torch):
     lo3, hi3 = sim.const_div_interval()
     assert (lo3 > hi3) or (lo3 <= 1e-30 and hi3 >= 1e30)
     sim.close()
+
+
+def test_fast_spiky_scale_is_verified_for_every_r2(pbf, torch, monkeypatch):
+    """The branch-free spiky scale of the lambda pass is used only if it matched the sqrt.rn / div.rn sequence
+    for EVERY float r2 in [0, h^2] on this device (about 1e9 values per h). For the default h and two others it
+    must verify without a single mismatch; the golden-vector tests above prove the step's bits did not change,
+    and a step with PBF_NO_FAST_SPIKY=1 must give the same bits as a step with it."""
+    pos, vel, iid, ulim, llim = pbf.scene_double_dam_reference()
+    n = len(iid)
+
+    def one_step(sim):
+        d = [torch.from_numpy(a).cuda() for a in (pos, np.zeros_like(pos), vel, np.zeros_like(vel))]
+        d_iid = torch.from_numpy(iid.astype(np.int64)).cuda().to(torch.int32)
+        for _ in range(3):
+            sim.step(d[0], d[1], d[2], d[3], d_iid, n)
+            d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+        torch.cuda.synchronize()
+        return d[0].cpu().numpy().tobytes(), d[2].cpu().numpy().tobytes(), sim.read(pbf.READ_RHO).tobytes()
+
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    assert sim.fast_spiky() == (1, 0)
+    fast = one_step(sim)
+    for h in (0.125, 0.07):
+        p = pbf.default_params()
+        p.h = h
+        sim.loadParams(p)
+        assert sim.fast_spiky() == (1, 0), (h, sim.fast_spiky())
+    sim.close()
+    monkeypatch.setenv("PBF_NO_FAST_SPIKY", "1")
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    assert sim.fast_spiky() == (0, 0)
+    exact = one_step(sim)
+    sim.close()
+    assert fast == exact
