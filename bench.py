@@ -223,23 +223,37 @@ def run_product(args, rank, world, dist):
                             "dram_GBps_from_traffic": round(TRAFFIC["delta_p"] / (kacc["delta_p"] * 1e-3) / 1e9, 1)}}
 
     # ---- end to end through the host-buffer entry point --------------------------------------------
-    e2e_steps = max(3, min(args.steps, 20))
+    # the SAME window of the SAME scene as `value`: a fresh initial state, `warmup` untimed steps, `steps`
+    # timed steps, every one of them uploading its inputs from pinned host memory and downloading its result
+    sc2, n2, pos0, vel0, iid0 = scene_state(pbf, torch, args.scene, dev)
     h = [torch.empty((n, 3), dtype=torch.float32).pin_memory() for _ in range(4)]
     h_iid = torch.empty(n, dtype=torch.int32).pin_memory()
-    h[0].copy_(bufs[0]); h[2].copy_(bufs[2]); h_iid.copy_(iid)
+    h[0].copy_(pos0); h[2].copy_(vel0); h_iid.copy_(iid0)
+    del pos0, vel0, iid0
     hn = [t.numpy() for t in h]
     hi = h_iid.numpy().view(np.uint32)
-    sim.step_host(hn[0], hn[1], hn[2], hn[3], hi)   # warm-up: allocates the device staging
-    hn[0], hn[1], hn[2], hn[3] = hn[1], hn[0], hn[3], hn[2]
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    sim.setLim(sc["ulim"], sc["llim"])
+    e2e_frame = [0]
+
+    def host_step():
+        lim = lim_at(pbf, sc, e2e_frame[0])
+        if lim is not None:
+            sim.setLim(*lim)
         sim.step_host(hn[0], hn[1], hn[2], hn[3], hi)
         hn[0], hn[1], hn[2], hn[3] = hn[1], hn[0], hn[3], hn[2]
+        e2e_frame[0] += 1
+
+    for _ in range(args.warmup):
+        host_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
     e2e_s = time.perf_counter() - t0
-    e2e = {"value": round(n * e2e_steps / e2e_s, 1), "unit": "particle-steps/s", "steps": e2e_steps,
+    e2e = {"value": round(n * args.steps / e2e_s, 1), "unit": "particle-steps/s", "steps": args.steps,
            "h2d_bytes_per_step": 28 * n, "d2h_bytes_per_step": 28 * n,
-           "api": "pbf_step_host (pinned host buffers; upload pos/vel/iid, step, download npos/nvel/iid)"}
+           "api": "pbf_step_host (pinned host buffers; upload pos/vel/iid, step, download npos/nvel/iid), "
+                  "same scene and step window as `value`, wall clock around the synchronous calls"}
 
     out = {"metric": "particle-steps/s", "value": round(value, 1), "unit": "particle-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),

@@ -83,6 +83,10 @@ struct pbf_sim {
     // staging for pbf_step_host
     float* h_pos = nullptr; float* h_npos = nullptr; float* h_vel = nullptr; float* h_nvel = nullptr;
     uint32_t* h_iid = nullptr;
+    // pbf_step_host: its own two non-blocking streams, so that the download of the final positions and of
+    // iid runs on the copy engine while the XSPH sweep still computes the velocities
+    cudaStream_t host_main = nullptr, host_copy = nullptr;
+    cudaEvent_t host_ev = nullptr;
 
     // bound state of the step in flight
     Stage stage = ST_IDLE;
@@ -286,6 +290,9 @@ void free_all(pbf_sim* s) {
     cudaFree(s->cull.xs); cudaFree(s->cull.ys); cudaFree(s->cull.zs);
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
+    if (s->host_main) cudaStreamDestroy(s->host_main);
+    if (s->host_copy) cudaStreamDestroy(s->host_copy);
+    if (s->host_ev) cudaEventDestroy(s->host_ev);
     if (s->stats_host) cudaFreeHost(s->stats_host);
     cudaFree(s->plane_dev);
     if (s->plane_host) cudaFreeHost(s->plane_host);
@@ -778,15 +785,48 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
         CUDA_TRY(cudaMalloc((void**)&s->h_nvel, m * 12));
         CUDA_TRY(cudaMalloc((void**)&s->h_iid, m * 4));
     }
-    cudaStream_t st = nullptr;
+    if (!s->host_main) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->host_main, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->host_copy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->host_ev, cudaEventDisableTiming));
+    }
+    cudaStream_t st = s->host_main;
     CUDA_TRY(cudaMemcpyAsync(s->h_pos, pos, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->h_vel, vel, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->h_iid, iid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    int rc = pbf_step(s, s->h_pos, s->h_npos, s->h_vel, s->h_nvel, s->h_iid, n, st);
+    // the stage sequence of pbf_step, with the downloads of what is final after update_velocity — the
+    // positions and the sorted iid — issued on the copy stream before the XSPH sweep starts
+    int rc = pbf_stage_begin(s, s->h_pos, s->h_npos, s->h_vel, s->h_nvel, s->h_iid, n, st);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(npos, s->h_npos, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(nvel, s->h_nvel, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(iid, s->h_iid, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = pbf_stage_advect(s))) return rc;
+    if ((rc = pbf_stage_build_grid(s))) return rc;
+    for (int i = 0; i < s->p.niter; i++)
+        if ((rc = pbf_stage_correct_density(s))) return rc;
+    if ((rc = pbf_stage_update_velocity(s))) return rc;
+    if (n > 0) {
+        CUDA_TRY(cudaEventRecord(s->host_ev, st));
+        CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
+        CUDA_TRY(cudaMemcpyAsync(npos, s->h_npos, (size_t)n * 12, cudaMemcpyDeviceToHost, s->host_copy));
+        CUDA_TRY(cudaMemcpyAsync(iid, s->iid_sorted, (size_t)n * 4, cudaMemcpyDeviceToHost, s->host_copy));
+    }
+    // the XSPH sweep in up to four slices of the sorted order: the velocities of a finished slice go home
+    // while the next slice is computed (a slice is at least 128 K particles, so small scenes take one launch)
+    const int64_t slices = n >= 4 * 131072 ? 4 : n >= 2 * 131072 ? 2 : 1;
+    if (s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "step_host: velocity update missing");
+    if ((rc = kernel_event(s, PBF_KERNEL_XSPH, 0))) return rc;
+    for (int64_t k = 0; k < slices && n > 0; k++) {
+        const int64_t a = n * k / slices, b = n * (k + 1) / slices;
+        CUDA_TRY(launch_xsph(s->x[s->cur], s->cull, k == 0 ? s->n_local : 0, s->xl, s->cell_range, s->nvel + 3 * a,
+                             s->iid_sorted, s->iid + a, a, b - a, s->g, s->c, st, &s->launches));
+        CUDA_TRY(cudaEventRecord(s->host_ev, st));
+        CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
+        CUDA_TRY(cudaMemcpyAsync(nvel + 3 * a, s->h_nvel + 3 * a, (size_t)(b - a) * 12, cudaMemcpyDeviceToHost, s->host_copy));
+    }
+    if ((rc = kernel_event(s, PBF_KERNEL_XSPH, 1))) return rc;
+    s->stage = ST_XSPH;
+    if ((rc = stage_event(s, 5))) return rc;
+    if ((rc = pbf_stage_end(s))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->host_copy));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PBF_OK;
 }

@@ -525,13 +525,16 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
     return cudaGetLastError();
 }
 
+// n_slots > 0: refresh the cull's coordinate arrays first; 0: they are current (a further chunk of the same sweep)
 cudaError_t launch_xsph(const float4* x, const CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
                         int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
                         int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
-    if (pe != cudaSuccess) return pe;
+    if (n_slots > 0) {
+        cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
+        if (pe != cudaSuccess) return pe;
+    }
     xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
