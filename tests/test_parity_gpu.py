@@ -183,6 +183,40 @@ def test_all_particles_in_one_cell(pbf, torch):
     assert np.abs(a["s0.npos"] - b["s0.npos"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("n,odd", [(1200, 0), (1999, 1)])
+def test_dense_cluster_flushes_and_overflows(pbf, torch, n, odd):
+    """Collision edge case for the hit-word list and the neighbour-list hand-over: n particles crammed into a
+    2x2x2 block of cells. Every particle sees 4 non-empty runs of ~n/4 slots (tens of hit words: the 15-word
+    list drains several times per particle), hundreds of neighbours (the 96-entry pair list overflows, the
+    delta-p pass takes its full-gather kernel), run starts at every alignment (n odd: the aligned 4-slot
+    groups read before the start and past the end of runs and of the arrays). Two steps, every stage,
+    bit for bit against the reference's own library on this GPU (the oracle where that is not present)."""
+    rng = np.random.RandomState(11 + odd)
+    pos = (np.float32([0.5, 0.5, 0.5]) + rng.rand(n, 3).astype(np.float32) * np.float32(0.2)).astype(np.float32)
+    pos[:7] = pos[7:14]                                    # coincident particles: r2 == 0 pairs that are not self
+    vel = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(0.2)
+    scene = dict(name="cluster", params=O.default_params(), ulim=np.float32([1.2, 1.2, 1.2]), llim=np.float32([0, 0, 0]),
+                 pos=pos, vel=vel, iid=rng.permutation(n).astype(np.uint32), steps=2, wall=None)
+    a = T.trace_product(scene, pbf)
+    assert a["s0.ncount"].max() > 96 and a["s0.ncount"].min() > 15
+    if _ref.available():
+        b = T.trace_reference(scene)
+        for k in b:
+            assert np.ascontiguousarray(a[k]).tobytes() == np.ascontiguousarray(b[k]).tobytes(), k
+    else:
+        b = T.trace_oracle(scene, threads=4)
+        assert np.array_equal(a["s0.key"], b["s0.key"]) and np.array_equal(a["s0.iid"], b["s0.iid"])
+        assert np.array_equal(a["s0.pho0"], b["s0.pho0"]) and np.array_equal(a["s0.lam0"], b["s0.lam0"])
+    # the neighbour-list path and the full-gather path of the delta-p pass agree (PBF_NO_PAIR_REUSE is read at create)
+    os.environ["PBF_NO_PAIR_REUSE"] = "1"
+    try:
+        c = T.trace_product(scene, pbf)
+    finally:
+        del os.environ["PBF_NO_PAIR_REUSE"]
+    for k in a:
+        assert np.ascontiguousarray(a[k]).tobytes() == np.ascontiguousarray(c[k]).tobytes(), k
+
+
 # ---- full-size properties (BASELINE config 2: 1 048 576 particles) ---------------------------------
 
 @pytest.fixture(scope="module")
