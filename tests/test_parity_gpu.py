@@ -297,6 +297,34 @@ def test_full_size_matches_oracle_sample_and_is_deterministic(pbf, torch, big):
     o.close()
 
 
+def test_full_size_trajectory_is_bit_identical_to_the_reference_library(pbf, torch, big):
+    """BASELINE config 2 itself: 1 048 576 particles over the benchmark's whole window, 110 steps into the collapse
+    (the compressed regime in which home cells drift and neighbour lists are long) — positions, velocities and
+    order after every tenth step equal the reference's own Simulator.cu run live on this GPU, bit for bit. The stable sort makes the orders equal, so
+    nothing has to be matched up by iid."""
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libpbf_ref.so not present on this box")
+    n, sc = big["n"], big["sc"]
+    sim = big["sim"]
+    sim.setLim(sc["ulim"], sc["llim"])
+    ref = _ref.RefSimulator(O.default_params(), sc["ulim"], sc["llim"], n)
+    ref.set_lim(sc["ulim"], sc["llim"])
+    a = [big["pos"].clone(), torch.zeros_like(big["pos"]), big["vel"].clone(), torch.zeros_like(big["vel"])]
+    b = [t.clone() for t in a]
+    a_iid, b_iid = big["iid"].clone(), big["iid"].clone()
+    for step in range(1, 111):
+        sim.step(a[0], a[1], a[2], a[3], a_iid, n)
+        ref.step(b[0], b[1], b[2], b[3], b_iid, n)
+        a[0], a[1], a[2], a[3] = a[1], a[0], a[3], a[2]
+        b[0], b[1], b[2], b[3] = b[1], b[0], b[3], b[2]
+        if step % 10 == 0:
+            torch.cuda.synchronize()
+            assert torch.equal(a_iid, b_iid), step
+            assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32)), step   # bit patterns, NaN-safe
+            assert torch.equal(a[2].view(torch.int32), b[2].view(torch.int32)), step
+    ref.close()
+
+
 def test_trajectory_statistics_vs_oracle(pbf, torch):
     """50 steps of the reference scene: density error and kinetic energy track the CPU oracle.
     Trajectories are chaotic, so this compares statistics, not particles (north_star); the
