@@ -488,9 +488,9 @@ def run_product_slab(args, rank, world, dist):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full`, dam_1m at step ~100 — the state the
-# kernel timers above see (profiles/r01e_solver_ncu_summary.txt): the lambda pass writes the 8-byte neighbour
+# kernel timers above see (profiles/r01f_solver_ncu_summary.txt): the lambda pass writes the 8-byte neighbour
 # records (344 MB) the delta-p replay reads back (420 MB with its float4 gathers)
-TRAFFIC = {"lambda": 420.6e6, "delta_p": 437.9e6}
+TRAFFIC = {"lambda": 418.9e6, "delta_p": 436.1e6}
 
 
 def cpu_baseline(args, n, sc, steps=None):
