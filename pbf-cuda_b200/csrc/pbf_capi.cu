@@ -451,6 +451,11 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     A((void**)&s->cull.xs, (n + 8) * 4);
     A((void**)&s->cull.ys, (n + 8) * 4);
     A((void**)&s->cull.zs, (n + 8) * 4);
+    // (the cull reads whole groups of four slots, the hits of the slots outside a run are masked off: the
+    //  slots past the last particle are never written, so give them a defined value once)
+    if (e == cudaSuccess) e = cudaMemset(s->cull.xs, 0, (n + 8) * 4);
+    if (e == cudaSuccess) e = cudaMemset(s->cull.ys, 0, (n + 8) * 4);
+    if (e == cudaSuccess) e = cudaMemset(s->cull.zs, 0, (n + 8) * 4);
     A((void**)&s->rho, n * 4);
     A((void**)&s->iid_sorted, n * 4);
     A((void**)&s->cell_range, (size_t)cap * sizeof(uint2));
