@@ -10,11 +10,12 @@
 // order (dx, dy, dz nested, ascending slot inside a cell) with the reference's exact fp32
 // operation sequence (pbf_math.cuh), so rho / lambda / positions reproduce the reference's CUDA
 // build bit for bit (with exact_pow) instead of merely within tolerance. What changes is the
-// data path: one 16-byte load per candidate from the sorted float4 array instead of three
-// scalar loads from AoS float3 (+1 for lambda), the three z-cells of a column visited as one
-// contiguous slot run (9 runs instead of 27 cells), and the expensive part (sqrt, 4 IEEE
-// divisions, pow) only for pairs that pass an r2 cull — candidates outside h contribute exact
-// zeros in the reference, so skipping them does not change a single bit.
+// data path: the three z-cells of a column visited as one contiguous slot run (9 runs instead
+// of 27 cells); a cull that tests four candidates with three 16-byte loads from coordinate
+// arrays and 14 two-lane FP32 instructions and records the hits as bits; and the expensive part
+// (sqrt, 4 IEEE divisions, pow) only for the pairs that passed — candidates outside h contribute
+// exact zeros in the reference, so skipping them does not change a single bit — with the
+// neighbour list of the lambda pass handed to the delta-p pass of the same iteration.
 #include "pbf_math.cuh"
 
 namespace pbf {
