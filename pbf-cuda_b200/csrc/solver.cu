@@ -16,29 +16,9 @@
 // (sqrt, 4 IEEE divisions, pow) only for the pairs that passed — candidates outside h contribute
 // exact zeros in the reference, so skipping them does not change a single bit — with the
 // neighbour list of the lambda pass handed to the delta-p pass of the same iteration.
-#include "pbf_math.cuh"
+#include "solver_common.cuh"
 
 namespace pbf {
-
-#ifndef PBF_GATHER_MINBLOCKS
-#define PBF_GATHER_MINBLOCKS 8
-#endif
-#ifndef PBF_WORD_CAP
-#define PBF_WORD_CAP 15
-#endif
-#ifndef PBF_FLUSH_PER_SLAB
-#define PBF_FLUSH_PER_SLAB 0
-#endif
-#ifndef PBF_PAIR_CAP
-#define PBF_PAIR_CAP 96
-#endif
-#ifndef PBF_GATHER_THREADS
-#define PBF_GATHER_THREADS 128
-#endif
-constexpr int GATHER_THREADS = PBF_GATHER_THREADS;
-constexpr int WORD_CAP = PBF_WORD_CAP;  // hit words (32 candidates each) buffered per thread before a flush
-constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pass can hand to the delta-p pass
-constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2);  // 8 KB per CTA
 
 // Two-phase gather of one particle (one thread), the core of all three neighbour sweeps.
 //
@@ -60,50 +40,6 @@ constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2); 
 // warp busier than three phases over ~11 (measured: 3.78 -> 3.01 ms per step) — and whenever it
 // is full, so any neighbour count stays correct and ordered; 15 words per thread = 15 KB per CTA
 // keep 8 CTAs inside the 132 KB carve-out step and leave ~124 KB of L1.
-// Cull-side copy of the positions: three float arrays (structure of arrays), refreshed from the float4
-// iterate by pack_kernel before every sweep. Four consecutive candidates are then three 16-byte loads
-// (instead of four), and their coordinates sit in adjacent registers, which is what the packed FP32
-// instructions of sm_100 want.
-struct CullSoA {
-    const float* xs;
-    const float* ys;
-    const float* zs;
-};
-
-// Two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2, sm_100): each lane is the same IEEE
-// round-to-nearest operation as the scalar instruction, so r2 below has the bits of sumsq().
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-// two candidates: RN(r2 - limit) of each, sign bits pushed into `hits` (first candidate first)
-__device__ __forceinline__ uint32_t push_hits2(uint32_t hits, f32x2 px, f32x2 py, f32x2 pz, f32x2 lim,
-                                               float x0, float x1, float y0, float y1, float z0, float z1) {
-    const f32x2 dx = sub2(px, pack2(x0, x1)), dy = sub2(py, pack2(y0, y1)), dz = sub2(pz, pack2(z0, z1));
-    const f32x2 t = sub2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lim);
-    uint32_t t0, t1;
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
-    hits = __funnelshift_l(t0, hits, 1);
-    return __funnelshift_l(t1, hits, 1);
-}
-
 // (Measured and dropped: issuing the next group's loads before this group's arithmetic, and loading the
 //  next neighbour ahead of the heavy arithmetic — no change in either case. The sweeps are bound by the L1
 //  wavefront rate (70-80 % of peak, ncu): lanes of a warp sit in ~3 cells, and after the first Jacobi
@@ -185,9 +121,8 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
                 if (tail == words_end) flush();
             }
         }
-        if (PBF_FLUSH_PER_SLAB) flush();
     }
-    if (!PBF_FLUSH_PER_SLAB) flush();
+    flush();
 }
 
 // float4 iterate -> the cull's three coordinate arrays, every stored slot (ghosts included); ~8 us per
@@ -215,7 +150,6 @@ pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restr
 // Layout (block b of 128 threads, entry k, thread t): [(b*PAIR_CAP + k)*128 + t] — a warp's k-th
 // entries are contiguous 8-byte (slot, s) records. A particle with more than PAIR_CAP neighbours
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
-constexpr uint32_t PAIR_OVERFLOW = 1u << 31;
 
 template <bool SAVE_PAIRS, bool FAST_SPIKY>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
@@ -268,32 +202,6 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     halo_push(hp, t, out);
     rho_out[i] = rho;
     if (SAVE_PAIRS) pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
-}
-
-// w^n_corr of the delta-p pass's s_corr (Simulator_kernel.cuh:166 powf(..., n_corr)). POW = 1: powf with
-// the run-time exponent, exactly the call inside the reference; POW = 2: the same libdevice powf with the
-// exponent known to be 4.0f (the default n_corr) — the compiler folds the exponent-dependent parts of the
-// routine (~16 of ~84 instructions), the arithmetic and hence the bits are the same; POW = 0: (w*w)^2,
-// opt-in (pbf_set_option_exact_pow(0)), within 1e-5 but not bit-identical.
-template <int POW>
-__device__ __forceinline__ float pow_ncorr(float w, const SolverConsts& c) {
-    if (POW == 1) return powf(w, c.n_corr);
-    if (POW == 2) return powf(w, 4.0f);
-    const float w2 = __fmul_rn(w, w);
-    return __fmul_rn(w2, w2);
-}
-
-// shared tail of the delta-p pass: divide, clamp to MAX_DP, add, clamp to the box (f64 like the reference)
-__device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float ay, float az, const SolverConsts& c) {
-    const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
-    div3_pho0(ax, ay, az, c);
-    const float vx = fmaxf(fminf(ax, max_dp), -max_dp);
-    const float vy = fmaxf(fminf(ay, max_dp), -max_dp);
-    const float vz = fmaxf(fminf(az, max_dp), -max_dp);
-    const float qx = (float)fmax(fmin((double)__fadd_rn(p.x, vx), c.lim_hi[0]), c.lim_lo[0]);
-    const float qy = (float)fmax(fmin((double)__fadd_rn(p.y, vy), c.lim_hi[1]), c.lim_lo[1]);
-    const float qz = (float)fmax(fmin((double)__fadd_rn(p.z, vz), c.lim_hi[2]), c.lim_lo[2]);
-    return make_float4(qx, qy, qz, 0.f);
 }
 
 // The delta-p pass comes as two kernels. The REPLAY kernel walks the neighbour list the lambda pass saved:
@@ -451,10 +359,18 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, neighbor_count_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_kernel);
+    if (e == cudaSuccess) e = preload_solver_team();
     return e;
 }
 
 static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// Small scenes take the four-lanes-per-particle kernels of solver_team.cu (latency bound, not throughput bound).
+// PBF_TEAM=0 / 1 forces the choice (tests run the golden scenes through both, tuning experiments).
+static bool use_team(int64_t n) {
+    if (const char* e = getenv("PBF_TEAM")) return e[0] == '1';   // (read per launch: tests flip it inside one process)
+    return n < TEAM_MAX_PARTICLES;
+}
 
 static cudaError_t launch_pack(const float4* x, const CullScratch& cs, int64_t n_slots, cudaStream_t st, int64_t* launches) {
     pack_kernel<<<nblocks(n_slots, 256), 256, 0, st>>>(x, cs.xs, cs.ys, cs.zs, n_slots);
@@ -477,6 +393,11 @@ cudaError_t launch_lambda(const float4* x, const CullScratch& cs, int64_t n_slot
     cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
     if (pe != cudaSuccess) return pe;
     const CullSoA soa = soa_of(cs);
+    if (use_team(n)) {
+        launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c, st);
+        if (launches) (*launches)++;
+        return cudaGetLastError();
+    }
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (!pl.js && !c.fast_spiky)
         lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
@@ -502,7 +423,8 @@ cudaError_t launch_delta_p(const float4* xl, const CullScratch& cs, float4* x_ou
 #define PBF_DP_LAUNCH(POW)                                                                                                   \
     do {                                                                                                                     \
         if (pl.js) {                                                                                                         \
-            delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);            \
+            if (use_team(n)) launch_delta_p_replay_team(xl, x_out, first, n, pl.js, pl.cnt, hp, c, POW, st);                 \
+            else delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);       \
             delta_p_kernel<POW, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, cell_range, first, n, pl.cnt, hp, g, c); \
             if (launches) (*launches)++;                                                                                     \
         } else {                                                                                                             \
@@ -535,6 +457,11 @@ cudaError_t launch_xsph(const float4* x, const CullScratch& cs, int64_t n_slots,
     if (n_slots > 0) {
         cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
         if (pe != cudaSuccess) return pe;
+    }
+    if (use_team(n)) {
+        launch_xsph_team(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c, st);
+        if (launches) (*launches)++;
+        return cudaGetLastError();
     }
     xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
     if (launches) (*launches)++;

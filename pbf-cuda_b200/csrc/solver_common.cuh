@@ -1,0 +1,111 @@
+// solver_common.cuh — what the neighbour-sweep kernels of solver.cu (one thread per particle) and
+// solver_team.cu (four lanes per particle, small scenes) share: sizes, the cull's coordinate arrays and its
+// two-lane FP32 test, the neighbour-list layout, the tails of the delta-p pass.
+#pragma once
+#include "pbf_math.cuh"
+
+namespace pbf {
+
+#ifndef PBF_GATHER_MINBLOCKS
+#define PBF_GATHER_MINBLOCKS 8
+#endif
+#ifndef PBF_WORD_CAP
+#define PBF_WORD_CAP 15
+#endif
+#ifndef PBF_PAIR_CAP
+#define PBF_PAIR_CAP 96
+#endif
+#ifndef PBF_GATHER_THREADS
+#define PBF_GATHER_THREADS 128
+#endif
+constexpr int GATHER_THREADS = PBF_GATHER_THREADS;
+constexpr int WORD_CAP = PBF_WORD_CAP;  // hit words (32 candidates each) buffered per thread before a flush
+constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pass can hand to the delta-p pass
+constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2);  // 8 KB per CTA
+
+constexpr uint32_t PAIR_OVERFLOW = 1u << 31;   // pair_cnt: more than PAIR_CAP neighbours, the delta-p pass gathers
+
+// Cull-side copy of the positions: three float arrays (structure of arrays), refreshed from the float4
+// iterate by pack_kernel before every sweep. Four consecutive candidates are then three 16-byte loads
+// (instead of four), and their coordinates sit in adjacent registers, which is what the packed FP32
+// instructions of sm_100 want.
+struct CullSoA {
+    const float* xs;
+    const float* ys;
+    const float* zs;
+};
+
+// Two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2, sm_100): each lane is the same IEEE
+// round-to-nearest operation as the scalar instruction, so r2 below has the bits of sumsq().
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// two candidates: RN(r2 - limit) of each, sign bits pushed into `hits` (first candidate first)
+__device__ __forceinline__ uint32_t push_hits2(uint32_t hits, f32x2 px, f32x2 py, f32x2 pz, f32x2 lim,
+                                               float x0, float x1, float y0, float y1, float z0, float z1) {
+    const f32x2 dx = sub2(px, pack2(x0, x1)), dy = sub2(py, pack2(y0, y1)), dz = sub2(pz, pack2(z0, z1));
+    const f32x2 t = sub2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lim);
+    uint32_t t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+    hits = __funnelshift_l(t0, hits, 1);
+    return __funnelshift_l(t1, hits, 1);
+}
+
+// w^n_corr of the delta-p pass's s_corr (Simulator_kernel.cuh:166 powf(..., n_corr)). POW = 1: powf with
+// the run-time exponent, exactly the call inside the reference; POW = 2: the same libdevice powf with the
+// exponent known to be 4.0f (the default n_corr) — the compiler folds the exponent-dependent parts of the
+// routine (~16 of ~84 instructions), the arithmetic and hence the bits are the same; POW = 0: (w*w)^2,
+// opt-in (pbf_set_option_exact_pow(0)), within 1e-5 but not bit-identical.
+template <int POW>
+__device__ __forceinline__ float pow_ncorr(float w, const SolverConsts& c) {
+    if (POW == 1) return powf(w, c.n_corr);
+    if (POW == 2) return powf(w, 4.0f);
+    const float w2 = __fmul_rn(w, w);
+    return __fmul_rn(w2, w2);
+}
+
+// shared tail of the delta-p pass: divide, clamp to MAX_DP, add, clamp to the box (f64 like the reference)
+__device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float ay, float az, const SolverConsts& c) {
+    const float max_dp = (float)0.1;  // MAX_DP through clamp3f's float parameters (helper.h:9,26)
+    div3_pho0(ax, ay, az, c);
+    const float vx = fmaxf(fminf(ax, max_dp), -max_dp);
+    const float vy = fmaxf(fminf(ay, max_dp), -max_dp);
+    const float vz = fmaxf(fminf(az, max_dp), -max_dp);
+    const float qx = (float)fmax(fmin((double)__fadd_rn(p.x, vx), c.lim_hi[0]), c.lim_lo[0]);
+    const float qy = (float)fmax(fmin((double)__fadd_rn(p.y, vy), c.lim_hi[1]), c.lim_lo[1]);
+    const float qz = (float)fmax(fmin((double)__fadd_rn(p.z, vz), c.lim_hi[2]), c.lim_lo[2]);
+    return make_float4(qx, qy, qz, 0.f);
+}
+
+// solver_team.cu: the same sweeps with four lanes per particle, for scenes too small to fill the machine
+constexpr int64_t TEAM_MAX_PARTICLES = 2 * 148 * PBF_GATHER_MINBLOCKS * GATHER_THREADS / 4;   // < half a wave of threads
+cudaError_t preload_solver_team();
+void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
+                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp, const GridConsts& g,
+                        const SolverConsts& c, cudaStream_t st);
+void launch_delta_p_replay_team(const float4* xl, float4* x_out, int64_t first, int64_t n, const uint2* pair_js,
+                                const uint32_t* pair_cnt, const HaloPush& hp, const SolverConsts& c, int pow_mode,
+                                cudaStream_t st);
+void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
+                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, const GridConsts& g,
+                      const SolverConsts& c, cudaStream_t st);
+
+}  // namespace pbf

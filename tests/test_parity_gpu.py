@@ -54,6 +54,16 @@ def test_bit_exact_vs_reference_golden(pbf, torch, name):
     assert checked >= 30
 
 
+@pytest.mark.parametrize("team", ["0", "1"])
+@pytest.mark.parametrize("name", SCENES)
+def test_both_kernel_families_are_bit_exact(pbf, torch, monkeypatch, name, team):
+    """The sweeps exist twice: one thread per particle (solver.cu, what large scenes run) and four lanes per
+    particle (solver_team.cu, what scenes below ~75 K particles run). The golden scenes are small, so left alone
+    they would only ever exercise the second family: PBF_TEAM forces each in turn through the golden comparison."""
+    monkeypatch.setenv("PBF_TEAM", team)
+    test_bit_exact_vs_reference_golden(pbf, torch, name)
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_bit_exact_vs_reference_library(pbf, torch, name):
     """Same comparison against the reference's library run live on this GPU (all fields, no subsampling)."""
@@ -183,14 +193,18 @@ def test_all_particles_in_one_cell(pbf, torch):
     assert np.abs(a["s0.npos"] - b["s0.npos"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("team", ["0", "1"])
 @pytest.mark.parametrize("n,odd", [(1200, 0), (1999, 1)])
-def test_dense_cluster_flushes_and_overflows(pbf, torch, n, odd):
+def test_dense_cluster_flushes_and_overflows(pbf, torch, monkeypatch, n, odd, team):
     """Collision edge case for the hit-word list and the neighbour-list hand-over: n particles crammed into a
     2x2x2 block of cells. Every particle sees 4 non-empty runs of ~n/4 slots (tens of hit words: the 15-word
     list drains several times per particle), hundreds of neighbours (the 96-entry pair list overflows, the
     delta-p pass takes its full-gather kernel), run starts at every alignment (n odd: the aligned 4-slot
     groups read before the start and past the end of runs and of the arrays). Two steps, every stage,
-    bit for bit against the reference's own library on this GPU (the oracle where that is not present)."""
+    bit for bit against the reference's own library on this GPU (the oracle where that is not present) — through
+    the thread-per-particle kernels (team = 0: the 15-word list drains) and the four-lane kernels (team = 1: the
+    128-slot neighbour list drains)."""
+    monkeypatch.setenv("PBF_TEAM", team)
     rng = np.random.RandomState(11 + odd)
     pos = (np.float32([0.5, 0.5, 0.5]) + rng.rand(n, 3).astype(np.float32) * np.float32(0.2)).astype(np.float32)
     pos[:7] = pos[7:14]                                    # coincident particles: r2 == 0 pairs that are not self
