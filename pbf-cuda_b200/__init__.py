@@ -652,6 +652,9 @@ def wall_lim(ulim0, llim0, a_ulim, a_llim, w, frame, start_frame=0):
 # The named benchmark scenes (BASELINE.md section 3 / SURVEY.md 8d).
 SCENES = {
     "double_dam_32k": dict(ulim=(2.0, 2.0, 4.0), llim=(-2.0, -2.0, 0.0), n=32000),
+    # intermediate sizes (tuning of the small-scene kernels; same shape as dam_1m, scaled)
+    "dam_128k": dict(ulim=(8.0, 2.0, 4.8), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (64, 32, 64))]),
+    "dam_256k": dict(ulim=(8.0, 3.6, 4.8), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (64, 64, 64))]),
     "dam_1m": dict(ulim=(16.0, 3.6, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (128, 64, 128))]),
     "sweep_4m": dict(ulim=(19.2, 6.8, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (256, 128, 128))],
                      wall=dict(a_ulim=(4.8, 0.0, 0.0), a_llim=(0.0, 0.0, 0.0), w=0.05), ulim_max=(24.0, 6.8, 9.6)),

@@ -96,7 +96,10 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
 }
 
 // solver_team.cu: the same sweeps with four lanes per particle, for scenes too small to fill the machine
-constexpr int64_t TEAM_MAX_PARTICLES = 2 * 148 * PBF_GATHER_MINBLOCKS * GATHER_THREADS / 4;   // < half a wave of threads
+// Measured (B200, ms per step, thread-per-particle vs team): 32 K 0.380 vs 0.282; 131 K 0.599 vs 0.871; 262 K 0.893 vs
+// 1.490 — the team kernels stop being latency bound near 45 K particles and cost ~1.6x the instruction slots from
+// there on, the thread kernels stay near their latency floor up to ~130 K: the crossover is near 60 K.
+constexpr int64_t TEAM_MAX_PARTICLES = 48 * 1024;
 cudaError_t preload_solver_team();
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
                         int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp, const GridConsts& g,
