@@ -339,6 +339,40 @@ def test_full_size_trajectory_is_bit_identical_to_the_reference_library(pbf, tor
     ref.close()
 
 
+def test_sweeping_tank_4m_is_bit_identical_to_the_reference_library(pbf, torch):
+    """BASELINE config 3: 4 194 304 particles, the wall moving every step (grid dimensions change with it), XSPH on —
+    20 steps, state compared with the reference's library bit for bit after steps 10 and 20."""
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libpbf_ref.so not present on this box")
+    sc = pbf.SCENES["sweep_4m"]
+    (origin, n3), = sc["blocks"]
+    n = int(np.prod(n3))
+    pos = torch.empty((n, 3), device="cuda"); vel = torch.empty_like(pos)
+    iid = torch.empty(n, dtype=torch.int32, device="cuda")
+    pbf.scene_block_device(origin, n3, pos, vel, iid)
+    sim = pbf.Simulator(pbf.default_params(), sc["ulim_max"], sc["llim"], n)
+    ref = _ref.RefSimulator(O.default_params(), sc["ulim_max"], sc["llim"], n)
+    a = [pos, torch.zeros_like(pos), vel, torch.zeros_like(vel)]
+    b = [t.clone() for t in a]
+    a_iid, b_iid = iid, iid.clone()
+    w = sc["wall"]
+    for step in range(1, 21):
+        lim = pbf.wall_lim(sc["ulim"], sc["llim"], w["a_ulim"], w["a_llim"], w["w"], step - 1)
+        sim.setLim(*lim)
+        ref.set_lim(*lim)
+        sim.step(a[0], a[1], a[2], a[3], a_iid, n)
+        ref.step(b[0], b[1], b[2], b[3], b_iid, n)
+        a[0], a[1], a[2], a[3] = a[1], a[0], a[3], a[2]
+        b[0], b[1], b[2], b[3] = b[1], b[0], b[3], b[2]
+        if step % 10 == 0:
+            torch.cuda.synchronize()
+            assert torch.equal(a_iid, b_iid), step
+            assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32)), step
+            assert torch.equal(a[2].view(torch.int32), b[2].view(torch.int32)), step
+    ref.close()
+    sim.close()
+
+
 def test_trajectory_statistics_vs_oracle(pbf, torch):
     """50 steps of the reference scene: density error and kinetic energy track the CPU oracle.
     Trajectories are chaotic, so this compares statistics, not particles (north_star); the
