@@ -373,6 +373,38 @@ def test_sweeping_tank_4m_is_bit_identical_to_the_reference_library(pbf, torch):
     sim.close()
 
 
+def test_double_dam_16m_is_bit_identical_to_the_reference_library(pbf, torch):
+    """BASELINE config 4 on one GPU: 16 777 216 particles in two blocks, 14.2 M cells (24-bit keys: three sort
+    passes, 64-bit offsets everywhere) — 4 steps, bit for bit against the reference's library."""
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libpbf_ref.so not present on this box")
+    sc = pbf.SCENES["double_dam_16m"]
+    n = sum(int(np.prod(b[1])) for b in sc["blocks"])
+    pos = torch.empty((n, 3), device="cuda"); vel = torch.empty_like(pos)
+    iid = torch.empty(n, dtype=torch.int32, device="cuda")
+    off = 0
+    for origin, n3 in sc["blocks"]:
+        pbf.scene_block_device(origin, n3, pos[off:], vel[off:], iid[off:], first_iid=off)
+        off += int(np.prod(n3))
+    sim = pbf.Simulator(pbf.default_params(), sc["ulim"], sc["llim"], n)
+    ref = _ref.RefSimulator(O.default_params(), sc["ulim"], sc["llim"], n)
+    ref.set_lim(sc["ulim"], sc["llim"])
+    a = [pos, torch.zeros_like(pos), vel, torch.zeros_like(vel)]
+    b = [t.clone() for t in a]
+    a_iid, b_iid = iid, iid.clone()
+    for step in range(4):
+        sim.step(a[0], a[1], a[2], a[3], a_iid, n)
+        ref.step(b[0], b[1], b[2], b[3], b_iid, n)
+        a[0], a[1], a[2], a[3] = a[1], a[0], a[3], a[2]
+        b[0], b[1], b[2], b[3] = b[1], b[0], b[3], b[2]
+    torch.cuda.synchronize()
+    assert torch.equal(a_iid, b_iid)
+    assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32))
+    assert torch.equal(a[2].view(torch.int32), b[2].view(torch.int32))
+    ref.close()
+    sim.close()
+
+
 def test_trajectory_statistics_vs_oracle(pbf, torch):
     """50 steps of the reference scene: density error and kinetic energy track the CPU oracle.
     Trajectories are chaotic, so this compares statistics, not particles (north_star); the
