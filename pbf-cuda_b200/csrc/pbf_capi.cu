@@ -75,6 +75,7 @@ struct pbf_sim {
     uint32_t* iid_sorted = nullptr;
     uint2* cell_range = nullptr;
     PairList pairs_list;            // lambda -> delta-p neighbour list (null when disabled / too large)
+    int pair_parity = 0;            // parity of the Jacobi iteration count since create (PairList::ovf_flag)
     CullScratch cull;               // coordinate arrays of the sweeps' cull (solver.cu pack_kernel)
     uint32_t* count_scratch = nullptr;
     uint32_t* read_scratch = nullptr;
@@ -286,8 +287,8 @@ int refresh_consts(pbf_sim* s) {
 void free_all(pbf_sim* s) {
     cudaFree(s->keys); cudaFree(s->sort_zero); cudaFree(s->pairs[0]); cudaFree(s->pairs[1]);
     cudaFree(s->x[0]); cudaFree(s->x[1]); cudaFree(s->xl); cudaFree(s->rho); cudaFree(s->iid_sorted);
-    cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt);
-    cudaFree(s->cull.xs); cudaFree(s->cull.ys); cudaFree(s->cull.zs);
+    cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt); cudaFree(s->pairs_list.ovf_flag);
+    for (int k = 0; k < 2; k++) { cudaFree(s->cull.xs[k]); cudaFree(s->cull.ys[k]); cudaFree(s->cull.zs[k]); }
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
     if (s->host_main) cudaStreamDestroy(s->host_main);
@@ -448,14 +449,16 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     A((void**)&s->x[0], (n + 8) * sizeof(float4));
     A((void**)&s->x[1], (n + 8) * sizeof(float4));
     A((void**)&s->xl, (n + 8) * sizeof(float4));
-    A((void**)&s->cull.xs, (n + 8) * 4);
-    A((void**)&s->cull.ys, (n + 8) * 4);
-    A((void**)&s->cull.zs, (n + 8) * 4);
     // (the cull reads whole groups of four slots, the hits of the slots outside a run are masked off: the
     //  slots past the last particle are never written, so give them a defined value once)
-    if (e == cudaSuccess) e = cudaMemset(s->cull.xs, 0, (n + 8) * 4);
-    if (e == cudaSuccess) e = cudaMemset(s->cull.ys, 0, (n + 8) * 4);
-    if (e == cudaSuccess) e = cudaMemset(s->cull.zs, 0, (n + 8) * 4);
+    for (int k = 0; k < 2; k++) {
+        A((void**)&s->cull.xs[k], (n + 8) * 4);
+        A((void**)&s->cull.ys[k], (n + 8) * 4);
+        A((void**)&s->cull.zs[k], (n + 8) * 4);
+        if (e == cudaSuccess) e = cudaMemset(s->cull.xs[k], 0, (n + 8) * 4);
+        if (e == cudaSuccess) e = cudaMemset(s->cull.ys[k], 0, (n + 8) * 4);
+        if (e == cudaSuccess) e = cudaMemset(s->cull.zs[k], 0, (n + 8) * 4);
+    }
     A((void**)&s->rho, n * 4);
     A((void**)&s->iid_sorted, n * 4);
     A((void**)&s->cell_range, (size_t)cap * sizeof(uint2));
@@ -488,8 +491,10 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
         if (!(np && np[0] == '1') && need <= free_b / 10 * 4) {
             cudaError_t pe = cudaMalloc((void**)&s->pairs_list.js, jb);
             if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.cnt, cb);
+            if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.ovf_flag, 2 * sizeof(uint32_t));
+            if (pe == cudaSuccess) pe = cudaMemset(s->pairs_list.ovf_flag, 0, 2 * sizeof(uint32_t));
             if (pe != cudaSuccess) {
-                cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt);
+                cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt); cudaFree(s->pairs_list.ovf_flag);
                 s->pairs_list = PairList();
                 cudaGetLastError();
             }
@@ -694,7 +699,7 @@ int pbf_stage_build_grid(pbf_sim* s) {
         int rc = slab_learn_layout(s);
         if (rc) return rc;
     }
-    KTIMED(PBF_KERNEL_REORDER, launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->npos, s->iid_sorted,
+    KTIMED(PBF_KERNEL_REORDER, launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->cull, s->npos, s->iid_sorted,
                                               s->cell_range, s->n_local, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
     s->cur = 0;
     s->pos0_in_npos = true;
@@ -708,7 +713,7 @@ int pbf_stage_lambda(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_LAMBDA;
     return PBF_OK;
 }
@@ -718,7 +723,8 @@ int pbf_stage_delta_p(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->x[s->cur ^ 1], &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->stream, &s->launches));
+    s->pair_parity ^= 1;
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;

@@ -129,11 +129,27 @@ cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npa
                         int* result_buf, cudaStream_t st, int64_t* launches);
 size_t sort_scratch_zero_bytes(int64_t n, int npass);
 
+// Coordinate arrays the cull of the neighbour sweeps reads (solver.cu CullSoA): max_particles + 8 floats
+// each, 16-byte aligned.
+struct CullScratch {
+    // two sets (the delta-p kernels write the next iterate's coordinates while their overflow kernel still
+    // culls on this iterate's); `cur` = the set the sweeps read
+    float* xs[2] = {nullptr, nullptr};
+    float* ys[2] = {nullptr, nullptr};
+    float* zs[2] = {nullptr, nullptr};
+    int cur = 0;
+    // the float4 array whose positions (ALL stored slots) the arrays of set `cur` mirror right now, or null.
+    // The kernels that produce an iterate write the coordinates along (reorder: every slot; the delta-p
+    // kernels: the owned slots, which is every slot on a single GPU), so the sweeps launch pack_kernel only
+    // when they find something else here — in slab mode, where ghost slots are refreshed by the neighbours.
+    const float4* holds = nullptr;
+};
+
 // gather the payload into sorted SoA + cell ranges (reorder.cu)
 // `n` slots are gathered (slab mode: ghosts included); pos0_out is written for the owned slots
 // [own_first, own_first + own_count) only, at slot - own_first.
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
-                           float4* x0, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
+                           float4* x0, CullScratch& cs, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
                            int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches);
 
@@ -142,24 +158,21 @@ cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* 
 struct PairList {
     uint2* js = nullptr;      // (slot of the k-th in-range neighbour, spiky scale of that pair as bits)
     uint32_t* cnt = nullptr;  // per particle: number of entries, or the overflow flag
+    // two words: "some list of this iteration overflowed", one per iteration parity. The lambda pass of
+    // iteration k raises flag[k & 1]; the delta-p pass's overflow kernel of iteration k leaves at once if it is
+    // down, and clears flag[(k + 1) & 1] — the one nobody reads until the lambda pass of iteration k + 1 sets it.
+    uint32_t* ovf_flag = nullptr;
 };
 size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes);
-// Coordinate arrays the cull of the neighbour sweeps reads (solver.cu CullSoA): max_particles + 8 floats
-// each, 16-byte aligned, rewritten from the float4 iterate before every sweep.
-struct CullScratch {
-    float* xs = nullptr;
-    float* ys = nullptr;
-    float* zs = nullptr;
-};
 // The passes compute slots [first, first + n) (slab mode: the owned slots; single GPU: 0, n) and
 // read neighbours from every slot. Internal arrays (x, xl, rho, v4, iid_sorted) are indexed by
 // slot; caller-facing arrays (pos/npos/vel/nvel/iid) and the pair list by slot - first.
 // `n_slots` = every slot the handle stores (ghosts included): the sweeps' cull reads them all.
-cudaError_t launch_lambda(const float4* x, const CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
-                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
+cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp,
                           const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
-cudaError_t launch_delta_p(const float4* xl, const CullScratch& cs, float4* x_out, const uint2* cell_range,
-                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
+cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
+                           int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
@@ -175,7 +188,7 @@ cudaError_t launch_halo_publish(const int64_t* tail_src, int64_t* peer_right_tai
                                 uint32_t* peer_word_right, uint32_t seq, cudaStream_t st, int64_t* launches);
 cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
                              uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches);
-cudaError_t launch_xsph(const float4* x, const CullScratch& cs, int64_t n_slots, const float4* v4,
+cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
                         int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
                         int64_t* launches);
@@ -187,7 +200,7 @@ cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_s
 cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                                 float* npos, float* nvel, uint32_t* iid_out, int64_t n, cudaStream_t st,
                                 int64_t* launches);
-cudaError_t launch_neighbor_count(const float4* x, const CullScratch& cs, const uint2* cell_range, uint32_t* count,
+cudaError_t launch_neighbor_count(const float4* x, CullScratch& cs, const uint2* cell_range, uint32_t* count,
                                   int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 
 // stats.cu: exhaustive check of the reciprocal division sequence for divisor d over all 2^32 bit

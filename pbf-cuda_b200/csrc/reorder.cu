@@ -4,6 +4,7 @@
 // (b) the two cudaMemset + computeGridRange (Simulator.cu:200-204, Simulator_kernel.cuh:21-50).
 // For sorted slot s with source index j:
 //   x0[s]      = (advect(pos[j], vel[j]), 0)      float4, the iterate the solver works on
+//   xs/ys/zs[s] = the same coordinates as three arrays, what the sweeps' cull reads
 //   pos0[s]    = pos[j]                           tight float3, parked in the caller's npos buffer
 //   iid_s[s]   = iid[j]
 //   cell_range[key] = {first slot, one past last slot}; empty cells stay {0,0} (reference
@@ -16,7 +17,7 @@
 // pos0 is parked for the owned slots only.
 //
 // HBM traffic: R 8 (pair) + 28 (gathered pos, vel, iid; near-sequential because the input is
-// last step's sorted order) ; W 16 + 12 + 4 per particle, + 8 B per occupied cell.
+// last step's sorted order) ; W 16 + 12 + 12 + 4 per particle, + 8 B per occupied cell.
 #include "pbf_math.cuh"
 
 namespace pbf {
@@ -26,7 +27,8 @@ constexpr int RO_THREADS = 256;
 __global__ void __launch_bounds__(RO_THREADS)
 reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
                const float* __restrict__ vel, const uint32_t* __restrict__ iid,
-               float4* __restrict__ x0, float* __restrict__ pos0_out, uint32_t* __restrict__ iid_sorted,
+               float4* __restrict__ x0, float* __restrict__ xs, float* __restrict__ ys, float* __restrict__ zs,
+               float* __restrict__ pos0_out, uint32_t* __restrict__ iid_sorted,
                uint2* __restrict__ cell_range, int64_t n, int64_t own_first, int64_t own_count,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     const int64_t s = (int64_t)blockIdx.x * RO_THREADS + threadIdx.x;
@@ -36,6 +38,7 @@ reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
     const float3 p = load_f3(pos, e.idx), v = load_f3(vel, e.idx);
     const float3 q = advect_pos(p, v, c);
     x0[s] = make_float4(q.x, q.y, q.z, 0.f);
+    xs[s] = q.x; ys[s] = q.y; zs[s] = q.z;   // the cull's copy of the coordinates (solver.cu CullSoA)
     if (s >= own_first && s - own_first < own_count) store_f3(pos0_out, s - own_first, p.x, p.y, p.z);
     iid_sorted[s] = iid[e.idx];
     // Green-style range detection (reference computeGridRange)
@@ -57,16 +60,19 @@ cudaError_t preload_reorder() {
 }
 
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
-                           float4* x0, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
+                           float4* x0, CullScratch& cs, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
                            int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+    cs.holds = nullptr;
     cudaError_t e = cudaMemsetAsync(cell_range, 0, sizeof(uint2) * (size_t)g.ncell, st);
     if (e != cudaSuccess) return e;
     if (launches) (*launches)++;
     if (n <= 0) return cudaSuccess;
     unsigned blocks = (unsigned)((n + RO_THREADS - 1) / RO_THREADS);
-    reorder_kernel<<<blocks, RO_THREADS, 0, st>>>(sorted, pos, vel, iid, x0, pos0_out, iid_sorted, cell_range, n, own_first, own_count, g, c);
+    reorder_kernel<<<blocks, RO_THREADS, 0, st>>>(sorted, pos, vel, iid, x0, cs.xs[0], cs.ys[0], cs.zs[0], pos0_out, iid_sorted, cell_range, n, own_first, own_count, g, c);
     if (launches) (*launches)++;
+    cs.cur = 0;
+    cs.holds = x0;   // every stored slot
     return cudaGetLastError();
 }
 

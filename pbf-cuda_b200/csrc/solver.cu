@@ -155,7 +155,7 @@ template <bool SAVE_PAIRS, bool FAST_SPIKY>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-              uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
+              uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt, uint32_t* __restrict__ ovf_flag,
               const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
               const __grid_constant__ SolverConsts c) {
     extern __shared__ uint2 s_words[];
@@ -201,7 +201,10 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     xl[i] = out;
     halo_push(hp, t, out);
     rho_out[i] = rho;
-    if (SAVE_PAIRS) pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
+    if (SAVE_PAIRS) {
+        pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
+        if (n_pairs > PAIR_CAP) *ovf_flag = 1u;   // (every writer stores the same value)
+    }
 }
 
 // The delta-p pass comes as two kernels. The REPLAY kernel walks the neighbour list the lambda pass saved:
@@ -214,7 +217,7 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
 #endif
 template <int POW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
-delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, int64_t first, int64_t n,
+delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                       const uint2* __restrict__ pair_js,
                       const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
                       const __grid_constant__ SolverConsts c) {
@@ -241,35 +244,45 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
     }
     const float4 out = delta_p_finish(p, ax, ay, az, c);
     x_out[i] = out;
+    co.store(i, out);
     halo_push(hp, t, out);
 }
 
 template <int POW, bool ONLY_OVERFLOW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
-delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restrict__ x_out,
+delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restrict__ x_out, const CullOut co,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-               const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
+               const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__ flag_read,
+               uint32_t* __restrict__ flag_clear, const __grid_constant__ HaloPush hp,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint2 s_words[];
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
-    if (t >= n) return;
-    if (ONLY_OVERFLOW && !(pair_cnt[t] & PAIR_OVERFLOW)) return;
-    const int64_t i = first + t;
-    const float4 p = xl[i];
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<true>(p, (uint32_t)i, c.h2_cull, xl, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
-        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-        const float r2 = sumsq(dx, dy, dz);
-        const float pw = pow_ncorr<POW>(poly6(r2, c), c);
-        const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-        const float s = spiky_scale(r2, c);
-        ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
-        ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
-        az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
-    });
-    const float4 out = delta_p_finish(p, ax, ay, az, c);
-    x_out[i] = out;
-    halo_push(hp, t, out);
+    // ONLY_OVERFLOW: a small grid that strides over the particles — and leaves at once when no list of this
+    // iteration overflowed, which is the normal case (see PairList::ovf_flag)
+    if (ONLY_OVERFLOW) {
+        const bool any = *flag_read != 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *flag_clear = 0u;
+        if (!any) return;
+    }
+    for (int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x; t < n; t += (int64_t)gridDim.x * GATHER_THREADS) {
+        if (ONLY_OVERFLOW && !(pair_cnt[t] & PAIR_OVERFLOW)) continue;
+        const int64_t i = first + t;
+        const float4 p = xl[i];
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        gather<true>(p, (uint32_t)i, c.h2_cull, xl, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            const float r2 = sumsq(dx, dy, dz);
+            const float pw = pow_ncorr<POW>(poly6(r2, c), c);
+            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+            const float s = spiky_scale(r2, c);
+            ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
+            ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
+            az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
+        });
+        const float4 out = delta_p_finish(p, ax, ay, az, c);
+        x_out[i] = out;
+        co.store(i, out);   // (reads of this iteration's coordinates go to `soa` = the OTHER set of arrays)
+        halo_push(hp, t, out);
+    }
 }
 
 // vel = (npos - pos) * inv_dt, plus everything the caller-facing buffers need from this point:
@@ -372,12 +385,16 @@ static bool use_team(int64_t n) {
     return n < TEAM_MAX_PARTICLES;
 }
 
-static cudaError_t launch_pack(const float4* x, const CullScratch& cs, int64_t n_slots, cudaStream_t st, int64_t* launches) {
-    pack_kernel<<<nblocks(n_slots, 256), 256, 0, st>>>(x, cs.xs, cs.ys, cs.zs, n_slots);
+// the cull's coordinate arrays must mirror `x`: nothing to do if the producer of `x` wrote them along
+static cudaError_t launch_pack(const float4* x, CullScratch& cs, int64_t n_slots, cudaStream_t st, int64_t* launches) {
+    if (cs.holds == x) return cudaSuccess;
+    pack_kernel<<<nblocks(n_slots, 256), 256, 0, st>>>(x, cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur], n_slots);
     if (launches) (*launches)++;
+    cs.holds = x;
     return cudaGetLastError();
 }
-static inline CullSoA soa_of(const CullScratch& cs) { return CullSoA{cs.xs, cs.ys, cs.zs}; }
+static inline CullSoA soa_of(const CullScratch& cs) { return CullSoA{cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur]}; }
+static inline CullOut out_of(const CullScratch& cs) { return CullOut{cs.xs[cs.cur ^ 1], cs.ys[cs.cur ^ 1], cs.zs[cs.cur ^ 1]}; }
 
 size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes) {
     const size_t blocks = (size_t)((max_particles + GATHER_THREADS - 1) / GATHER_THREADS);
@@ -386,56 +403,70 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
     return *js_bytes + *cnt_bytes;
 }
 
-cudaError_t launch_lambda(const float4* x, const CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
-                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
+cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp,
                           const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
     if (pe != cudaSuccess) return pe;
     const CullSoA soa = soa_of(cs);
     if (use_team(n)) {
-        launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c, st);
+        launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, pl.js ? pl.ovf_flag + (parity & 1) : nullptr, hp, g, c, st);
         if (launches) (*launches)++;
         return cudaGetLastError();
     }
     const unsigned nb = nblocks(n, GATHER_THREADS);
     if (!pl.js && !c.fast_spiky)
-        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
     else if (!pl.js)
-        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
     else if (!c.fast_spiky)
-        lambda_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
+        lambda_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, pl.ovf_flag + (parity & 1), hp, g, c);
     else
-        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c);
+        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, pl.ovf_flag + (parity & 1), hp, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
 // (`cs` holds the positions the lambda pass of this iteration packed: the same ones xl carries)
-cudaError_t launch_delta_p(const float4* xl, const CullScratch& cs, float4* x_out, const uint2* cell_range,
-                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const GridConsts& g,
+cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
+                           int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    const CullSoA soa = soa_of(cs);
+    const CullSoA soa = soa_of(cs);   // this iteration's coordinates: what the overflow kernel culls on
+    const CullOut co = out_of(cs);    // the other set receives the coordinates of x_out
     // 2: exact powf with the exponent folded (n_corr == 4, the default); 1: exact powf, any exponent; 0: (w*w)^2
     const int pow_mode = c.n_corr == 4.0f ? (c.exact_pow ? 2 : 0) : 1;
     const unsigned nb = nblocks(n, GATHER_THREADS);
-#define PBF_DP_LAUNCH(POW)                                                                                                   \
-    do {                                                                                                                     \
-        if (pl.js) {                                                                                                         \
-            if (use_team(n)) launch_delta_p_replay_team(xl, x_out, first, n, pl.js, pl.cnt, hp, c, POW, st);                 \
-            else delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, first, n, pl.js, pl.cnt, hp, c);       \
-            delta_p_kernel<POW, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, cell_range, first, n, pl.cnt, hp, g, c); \
-            if (launches) (*launches)++;                                                                                     \
-        } else {                                                                                                             \
-            delta_p_kernel<POW, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, cell_range, first, n, nullptr, hp, g, c); \
-        }                                                                                                                    \
+    const unsigned nb_ovf = nb < 148u * PBF_GATHER_MINBLOCKS ? nb : 148u * PBF_GATHER_MINBLOCKS;
+    uint32_t* const f_read = pl.js ? pl.ovf_flag + (parity & 1) : nullptr;
+    uint32_t* const f_clear = pl.js ? pl.ovf_flag + ((parity & 1) ^ 1) : nullptr;
+#define PBF_DP_LAUNCH(POW)                                                                                                    \
+    do {                                                                                                                      \
+        if (pl.js) {                                                                                                          \
+            if (use_team(n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c, POW, st);              \
+            else delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c);    \
+            delta_p_kernel<POW, true><<<nb_ovf, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n,    \
+                                                                                  pl.cnt, f_read, f_clear, hp, g, c);          \
+            if (launches) (*launches)++;                                                                                      \
+        } else {                                                                                                              \
+            delta_p_kernel<POW, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n,       \
+                                                                               nullptr, nullptr, nullptr, hp, g, c);          \
+        }                                                                                                                     \
     } while (0)
     if (pow_mode == 2) PBF_DP_LAUNCH(2);
     else if (pow_mode == 1) PBF_DP_LAUNCH(1);
     else PBF_DP_LAUNCH(0);
 #undef PBF_DP_LAUNCH
     if (launches) (*launches)++;
+    // the other set now mirrors x_out — if the pass covered every stored slot (single GPU); in slab mode the ghost
+    // slots of x_out are the neighbours' to fill, and the next sweep packs
+    if (first == 0 && n == n_slots) {
+        cs.cur ^= 1;
+        cs.holds = x_out;
+    } else {
+        cs.holds = nullptr;
+    }
     return cudaGetLastError();
 }
 
@@ -449,7 +480,7 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
 }
 
 // n_slots > 0: refresh the cull's coordinate arrays first; 0: they are current (a further chunk of the same sweep)
-cudaError_t launch_xsph(const float4* x, const CullScratch& cs, int64_t n_slots, const float4* v4,
+cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
                         int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
                         int64_t* launches) {
@@ -468,7 +499,7 @@ cudaError_t launch_xsph(const float4* x, const CullScratch& cs, int64_t n_slots,
     return cudaGetLastError();
 }
 
-cudaError_t launch_neighbor_count(const float4* x, const CullScratch& cs, const uint2* cell_range, uint32_t* count,
+cudaError_t launch_neighbor_count(const float4* x, CullScratch& cs, const uint2* cell_range, uint32_t* count,
                                   int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     cudaError_t pe = launch_pack(x, cs, n, st, nullptr);

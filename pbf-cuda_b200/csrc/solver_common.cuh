@@ -34,6 +34,14 @@ struct CullSoA {
     const float* ys;
     const float* zs;
 };
+// the same arrays for the kernels that PRODUCE an iterate (reorder, the delta-p kernels): they write the
+// coordinates along, so that the next sweep needs no pack_kernel (pbf_internal.h CullScratch::holds)
+struct CullOut {
+    float* xs;
+    float* ys;
+    float* zs;
+    __device__ __forceinline__ void store(int64_t i, const float4 q) const { xs[i] = q.x; ys[i] = q.y; zs[i] = q.z; }
+};
 
 // Two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2, sm_100): each lane is the same IEEE
 // round-to-nearest operation as the scalar instruction, so r2 below has the bits of sumsq().
@@ -102,9 +110,9 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
 constexpr int64_t TEAM_MAX_PARTICLES = 48 * 1024;
 cudaError_t preload_solver_team();
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp, const GridConsts& g,
-                        const SolverConsts& c, cudaStream_t st);
-void launch_delta_p_replay_team(const float4* xl, float4* x_out, int64_t first, int64_t n, const uint2* pair_js,
+                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, uint32_t* ovf_flag, const HaloPush& hp,
+                        const GridConsts& g, const SolverConsts& c, cudaStream_t st);
+void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut co, int64_t first, int64_t n, const uint2* pair_js,
                                 const uint32_t* pair_cnt, const HaloPush& hp, const SolverConsts& c, int pow_mode,
                                 cudaStream_t st);
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,

@@ -134,7 +134,7 @@ template <bool SAVE_PAIRS, bool FAST_SPIKY>
 __global__ void __launch_bounds__(TEAM_THREADS, 8)
 lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
                    const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-                   uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
+                   uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt, uint32_t* __restrict__ ovf_flag,
                    const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
                    const __grid_constant__ SolverConsts c) {
     extern __shared__ uint32_t s_list[];
@@ -187,14 +187,17 @@ lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __re
     xl[i] = out;
     halo_push(hp, t, out);
     rho_out[i] = rho;
-    if (SAVE_PAIRS) pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
+    if (SAVE_PAIRS) {
+        pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
+        if (n_pairs > PAIR_CAP) *ovf_flag = 1u;   // see PairList::ovf_flag
+    }
 }
 
 // ---- delta-p replay ----------------------------------------------------------------------------------------
 
 template <int POW>
 __global__ void __launch_bounds__(TEAM_THREADS, 16)
-delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, int64_t first, int64_t n,
+delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                            const uint2* __restrict__ pair_js, const uint32_t* __restrict__ pair_cnt,
                            const __grid_constant__ HaloPush hp, const __grid_constant__ SolverConsts c) {
     const Team tm = team_of();
@@ -231,6 +234,7 @@ delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x
     if (tm.lane != 0) return;
     const float4 out = delta_p_finish(p, ax, ay, az, c);
     x_out[i] = out;
+    co.store(i, out);
     halo_push(hp, t, out);
 }
 
@@ -293,26 +297,26 @@ cudaError_t preload_solver_team() {
 }
 
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp, const GridConsts& g,
-                        const SolverConsts& c, cudaStream_t st) {
+                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, uint32_t* ovf_flag, const HaloPush& hp,
+                        const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
     const unsigned nb = team_blocks(n);
     if (!pair_js && !c.fast_spiky)
-        lambda_team_kernel<false, false><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+        lambda_team_kernel<false, false><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
     else if (!pair_js)
-        lambda_team_kernel<false, true><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+        lambda_team_kernel<false, true><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
     else if (!c.fast_spiky)
-        lambda_team_kernel<true, false><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, g, c);
+        lambda_team_kernel<true, false><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, ovf_flag, hp, g, c);
     else
-        lambda_team_kernel<true, true><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, g, c);
+        lambda_team_kernel<true, true><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, ovf_flag, hp, g, c);
 }
 
-void launch_delta_p_replay_team(const float4* xl, float4* x_out, int64_t first, int64_t n, const uint2* pair_js,
+void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut co, int64_t first, int64_t n, const uint2* pair_js,
                                 const uint32_t* pair_cnt, const HaloPush& hp, const SolverConsts& c, int pow_mode,
                                 cudaStream_t st) {
     const unsigned nb = team_blocks(n);
-    if (pow_mode == 2) delta_p_replay_team_kernel<2><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, first, n, pair_js, pair_cnt, hp, c);
-    else if (pow_mode == 1) delta_p_replay_team_kernel<1><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, first, n, pair_js, pair_cnt, hp, c);
-    else delta_p_replay_team_kernel<0><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, first, n, pair_js, pair_cnt, hp, c);
+    if (pow_mode == 2) delta_p_replay_team_kernel<2><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
+    else if (pow_mode == 1) delta_p_replay_team_kernel<1><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
+    else delta_p_replay_team_kernel<0><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
 }
 
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
