@@ -50,7 +50,7 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
                                        const uint2* __restrict__ cell_range, const GridConsts& g,
                                        uint2* __restrict__ my_words, Heavy&& heavy) {
     const int3 cc = cell_of(p.x, p.y, p.z, g);
-    const int zlo = max(cc.z - 1, 0), zhi = min(cc.z + 1, g.dim[2] - 1);
+    const bool has_below = cc.z > 0, has_above = cc.z + 1 < g.dim[2];
     uint2* const words_end = my_words + WORD_CAP * GATHER_THREADS;
     uint2* tail = my_words;  // next free entry of this thread's list
     int k_total = 0;         // in-range neighbours handed to `heavy` so far (its third argument)
@@ -91,15 +91,16 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             const int cy = cc.y + dy;
             if (cy < 0 || cy >= g.dim[1]) continue;
             const int cbase = lx * g.dyz + cy * g.dim[2];
-            uint32_t start = 0, end = 0;
-            bool any = false;
-            for (int z = zlo; z <= zhi; z++) {
-                const uint2 r = __ldg(&cell_range[cbase + z]);
-                if (r.y > r.x) {
-                    if (!any) { start = r.x; any = true; }
-                    end = r.y;
-                }
-            }
+            // the run = from the first slot of the first non-empty cell of the column's (up to) three to the
+            // end of the last non-empty one; empty and out-of-range cells read {0, 0}, so an empty column gives
+            // start == end == 0. Straight-line on purpose: as a loop over z (1-3 trips) this was ~80 instructions.
+            const uint2 zero = make_uint2(0u, 0u);
+            const uint2 r0 = has_below ? __ldg(&cell_range[cbase + cc.z - 1]) : zero;
+            const uint2 r1 = __ldg(&cell_range[cbase + cc.z]);
+            const uint2 r2 = has_above ? __ldg(&cell_range[cbase + cc.z + 1]) : zero;
+            const bool e0 = r0.y > r0.x, e1 = r1.y > r1.x, e2 = r2.y > r2.x;
+            const uint32_t start = e0 ? r0.x : e1 ? r1.x : r2.x;
+            const uint32_t end = e2 ? r2.y : e1 ? r1.y : r0.y;
 #pragma unroll 1
             for (uint32_t b = start & ~3u; b < end; b += 32) {   // words start at multiples of four slots
                 const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run

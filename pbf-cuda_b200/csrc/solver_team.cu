@@ -48,7 +48,7 @@ __device__ __forceinline__ void team_gather(const Team& tm, const float4 p, cons
                                             const CullSoA soa, const uint2* __restrict__ cell_range, const GridConsts& g,
                                             uint32_t* __restrict__ list, Eval&& eval, Add&& add) {
     const int3 cc = cell_of(p.x, p.y, p.z, g);
-    const int zlo = max(cc.z - 1, 0), zhi = min(cc.z + 1, g.dim[2] - 1);
+    const bool has_below = cc.z > 0, has_above = cc.z + 1 < g.dim[2];
     const f32x2 px = pack2(p.x, p.x), py = pack2(p.y, p.y), pz = pack2(p.z, p.z), lim = pack2(limit, limit);
     uint32_t n_list = 0;   // neighbours buffered (the same value on the four lanes)
     auto drain = [&]() {
@@ -78,15 +78,16 @@ __device__ __forceinline__ void team_gather(const Team& tm, const float4 p, cons
             const int cy = cc.y + dy;
             if (cy < 0 || cy >= g.dim[1]) continue;
             const int cbase = lx * g.dyz + cy * g.dim[2];
-            uint32_t start = 0, end = 0;
-            bool any = false;
-            for (int z = zlo; z <= zhi; z++) {
-                const uint2 r = __ldg(&cell_range[cbase + z]);
-                if (r.y > r.x) {
-                    if (!any) { start = r.x; any = true; }
-                    end = r.y;
-                }
-            }
+            // the run = from the first slot of the first non-empty cell of the column's (up to) three to the
+            // end of the last non-empty one; empty and out-of-range cells read {0, 0}, so an empty column gives
+            // start == end == 0. Straight-line on purpose: as a loop over z (1-3 trips) this was ~80 instructions.
+            const uint2 zero = make_uint2(0u, 0u);
+            const uint2 r0 = has_below ? __ldg(&cell_range[cbase + cc.z - 1]) : zero;
+            const uint2 r1 = __ldg(&cell_range[cbase + cc.z]);
+            const uint2 r2 = has_above ? __ldg(&cell_range[cbase + cc.z + 1]) : zero;
+            const bool e0 = r0.y > r0.x, e1 = r1.y > r1.x, e2 = r2.y > r2.x;
+            const uint32_t start = e0 ? r0.x : e1 ? r1.x : r2.x;
+            const uint32_t end = e2 ? r2.y : e1 ? r1.y : r0.y;
 #pragma unroll 1
             for (uint32_t b = start & ~3u; b < end; b += 32) {   // one 32-slot word per step of the team
                 // lane l tests the groups of four slots at b + 4l and b + 16 + 4l (loads only below `end`: the
