@@ -1,5 +1,5 @@
 """Scratch GPU probe: times the product and the reference's own CUDA build on a named scene."""
-import importlib, os, sys, time, ctypes as C
+import importlib, os, sys, ctypes as C
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
