@@ -20,7 +20,6 @@ CPU implementation of this path, its path IS CUDA — if that library is absent 
 timed instead.
 """
 import argparse
-import ctypes as C
 import importlib
 import json
 import os
