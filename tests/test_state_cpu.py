@@ -81,3 +81,23 @@ def test_damaged_files_are_refused(pbf, tmp_path):
     small = np.zeros((10, 3), np.float32)
     rc = pbf.lib().pbf_state_read(os.fsencode(f), C.byref(info), small.ctypes.data, small.ctypes.data, small.ctypes.data, 10)
     assert rc == pbf.ERR_CAPACITY and not small.any()
+
+
+def test_emitter_source_schedule_on_host_buffers(pbf):
+    """EmitterSource (the Python mirror of host/ParticleSource.h): one ny x nz layer every `period` calls, appended
+    behind the current particles, until `total` or the buffers are full; iid continues the running count."""
+    cap = 1000
+    pos, vel, iid = np.zeros((cap, 3), np.float32), np.zeros((cap, 3), np.float32), np.zeros(cap, np.uint32)
+    src = pbf.EmitterSource((-1.9, -0.4, 2.0), 4, 5, 0.05, (3.0, 0.0, 0.0), 3, 70)
+    counts = [src.initialize(pos, vel, iid, cap)] + [src.update(pos, vel, iid, cap) for _ in range(11)]
+    assert counts == [20, 20, 20, 40, 40, 40, 60, 60, 60, 60, 60, 60]          # 70 < 80: the fourth layer never fits
+    assert np.array_equal(iid[:60], np.arange(60, dtype=np.uint32)) and not iid[60:].any()
+    assert np.all(pos[:60, 0] == np.float32(-1.9)) and np.all(vel[:60] == np.float32([3.0, 0.0, 0.0]))
+    layer = pos[:20].reshape(4, 5, 3)
+    assert np.array_equal(layer[:, 0, 1], np.float32(-0.4) + np.float32(0.05) * np.arange(4, dtype=np.float32))
+    assert np.array_equal(layer[0, :, 2], np.float32(2.0) + np.float32(0.05) * np.arange(5, dtype=np.float32))
+    assert np.array_equal(pos[20:40], pos[:20]) and not pos[60:].any()
+    # the buffers, not `total`, can be the limit
+    small = pbf.EmitterSource((0, 0, 0), 4, 5, 0.05, (1, 0, 0), 1, 10 ** 6)
+    assert [small.initialize(pos, vel, iid, 45)] + [small.update(pos, vel, iid, 45) for _ in range(3)] == [20, 40, 40, 40]
+    assert src.reset(pos, vel, iid, cap) == 20
