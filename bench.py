@@ -215,8 +215,8 @@ def run_product(args, rank, world, dist):
                 "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved": round(step_gbs, 2),
                                "frac": round(step_gbs / peak, 5)},
                 "note": "the lambda / XSPH sweeps are bound by the L1 wavefront rate and instruction issue, not by HBM "
-                        "(SURVEY.md App. D, DESIGN.md 5): ncu at step 100 shows 60% issue-slot utilisation, 63-80% of the L1 "
-                        "data-pipe wavefront rate and 10% DRAM throughput; the delta-p pass replays the lambda pass's neighbour "
+                        "(SURVEY.md App. D, DESIGN.md 5): ncu at step 100 shows 67% issue-slot utilisation, 74-89% of the L1 "
+                        "data-pipe wavefront rate and 12% DRAM throughput; the delta-p pass replays the lambda pass's neighbour "
                         "list and evaluates the exact powf: 76% issue, 27% DRAM (see delta_p below)",
                 "delta_p": {"kernel_ms": round(kacc["delta_p"], 4), "traffic": TRAFFIC["delta_p"],
                             "dram_GBps_from_traffic": round(TRAFFIC["delta_p"] / (kacc["delta_p"] * 1e-3) / 1e9, 1)}}
@@ -487,9 +487,9 @@ def run_product_slab(args, rank, world, dist):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full`, dam_1m at step ~100 — the state the
-# kernel timers above see (profiles/r01f_solver_ncu_summary.txt): the lambda pass writes the 8-byte neighbour
+# kernel timers above see (profiles/r01h_solver_ncu_summary.txt): the lambda pass writes the 8-byte neighbour
 # records (344 MB) the delta-p replay reads back (420 MB with its float4 gathers)
-TRAFFIC = {"lambda": 418.9e6, "delta_p": 436.1e6}
+TRAFFIC = {"lambda": 432.8e6, "delta_p": 453.8e6}
 
 
 def cpu_baseline(args, n, sc, steps=None):
