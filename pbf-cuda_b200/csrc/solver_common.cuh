@@ -21,12 +21,13 @@ namespace pbf {
 constexpr int GATHER_THREADS = PBF_GATHER_THREADS;
 constexpr int WORD_CAP = PBF_WORD_CAP;  // hit words (32 candidates each) buffered per thread before a flush
 constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pass can hand to the delta-p pass
-constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2);  // 8 KB per CTA
+constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2);  // 15 KB per CTA
 
 constexpr uint32_t PAIR_OVERFLOW = 1u << 31;   // pair_cnt: more than PAIR_CAP neighbours, the delta-p pass gathers
 
-// Cull-side copy of the positions: three float arrays (structure of arrays), refreshed from the float4
-// iterate by pack_kernel before every sweep. Four consecutive candidates are then three 16-byte loads
+// Cull-side copy of the positions: three float arrays (structure of arrays), written along with the float4
+// iterate by the kernels that produce it (CullOut below; by pack_kernel in slab mode, where the neighbours
+// fill the ghost slots). Four consecutive candidates are then three 16-byte loads
 // (instead of four), and their coordinates sit in adjacent registers, which is what the packed FP32
 // instructions of sm_100 want.
 struct CullSoA {
