@@ -13,8 +13,6 @@
 #include <unistd.h>
 
 #include <new>
-#include <string>
-#include <vector>
 
 #include "pbf_internal.h"
 
@@ -87,7 +85,8 @@ struct pbf_sim {
     // pbf_step_host: its own two non-blocking streams, so that the download of the final positions and of
     // iid runs on the copy engine while the XSPH sweep still computes the velocities
     cudaStream_t host_main = nullptr, host_copy = nullptr;
-    cudaEvent_t host_ev = nullptr;
+    cudaEvent_t host_ev = nullptr, host_iid_ev = nullptr;
+    cudaEvent_t reorder_wait = nullptr;   // step_host: the iid upload, still in flight while the keys are sorted
 
     // bound state of the step in flight
     Stage stage = ST_IDLE;
@@ -294,6 +293,7 @@ void free_all(pbf_sim* s) {
     if (s->host_main) cudaStreamDestroy(s->host_main);
     if (s->host_copy) cudaStreamDestroy(s->host_copy);
     if (s->host_ev) cudaEventDestroy(s->host_ev);
+    if (s->host_iid_ev) cudaEventDestroy(s->host_iid_ev);
     if (s->stats_host) cudaFreeHost(s->stats_host);
     cudaFree(s->plane_dev);
     if (s->plane_host) cudaFreeHost(s->plane_host);
@@ -657,6 +657,7 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
     CUDA_TRY(cudaSetDevice(s->device));
     s->pos = pos; s->npos = npos; s->vel = vel; s->nvel = nvel; s->iid = iid; s->n = n;
     s->stream = (cudaStream_t)stream;
+    s->reorder_wait = nullptr;
     if (s->slab_on) {  // a plain step on a handle that ran slab steps before: back to the whole grid
         s->slab_on = false;
         int rc = refresh_consts(s);
@@ -698,6 +699,10 @@ int pbf_stage_build_grid(pbf_sim* s) {
     if (s->slab_on) {
         int rc = slab_learn_layout(s);
         if (rc) return rc;
+    }
+    if (s->reorder_wait) {   // reorder is the first kernel that reads iid
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->reorder_wait, 0));
+        s->reorder_wait = nullptr;
     }
     KTIMED(PBF_KERNEL_REORDER, launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->cull, s->npos, s->iid_sorted,
                                               s->cell_range, s->n_local, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
@@ -800,15 +805,24 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
         CUDA_TRY(cudaStreamCreateWithFlags(&s->host_main, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&s->host_copy, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&s->host_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->host_iid_ev, cudaEventDisableTiming));
     }
     cudaStream_t st = s->host_main;
     CUDA_TRY(cudaMemcpyAsync(s->h_pos, pos, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->h_vel, vel, (size_t)n * 12, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(s->h_iid, iid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    // iid is not needed before the reorder: it goes up on the copy stream, behind pos and vel on the wire,
+    // while the keys are computed and sorted
+    if (n > 0) {
+        CUDA_TRY(cudaEventRecord(s->host_ev, st));
+        CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
+        CUDA_TRY(cudaMemcpyAsync(s->h_iid, iid, (size_t)n * 4, cudaMemcpyHostToDevice, s->host_copy));
+        CUDA_TRY(cudaEventRecord(s->host_iid_ev, s->host_copy));
+    }
     // the stage sequence of pbf_step, with the downloads of what is final after update_velocity — the
     // positions and the sorted iid — issued on the copy stream before the XSPH sweep starts
     int rc = pbf_stage_begin(s, s->h_pos, s->h_npos, s->h_vel, s->h_nvel, s->h_iid, n, st);
     if (rc) return rc;
+    if (n > 0) s->reorder_wait = s->host_iid_ev;
     if ((rc = pbf_stage_advect(s))) return rc;
     if ((rc = pbf_stage_build_grid(s))) return rc;
     for (int i = 0; i < s->p.niter; i++)
@@ -1263,6 +1277,15 @@ int pbf_scene_block_device(const float origin[3], const int32_t n[3], float spac
 
 // ---- state files (checkpoint / resume), see include/pbf.h ----------------------------------------
 
+// host staging that cannot throw through the C boundary
+struct HostBuf {
+    void* p;
+    explicit HostBuf(size_t bytes) : p(malloc(bytes ? bytes : 1)) {}
+    ~HostBuf() { free(p); }
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+};
+
 int pbf_state_write(const char* path, const pbf_state_info* info, const float* pos, const float* vel, const uint32_t* iid) {
     if (!path || !info) return fail(PBF_ERR_INVALID, "null argument");
     if (info->n < 0 || info->n >= ((int64_t)1 << 30)) return fail(PBF_ERR_INVALID, "bad particle count");
@@ -1279,15 +1302,18 @@ int pbf_state_write(const char* path, const pbf_state_info* info, const float* p
     memcpy(hd.llim, info->llim, sizeof(hd.llim));
     hd.exact_pow = info->exact_pow;
     hd.checksum = payload_checksum(pos, vel, iid, info->n);
-    std::string tmp = std::string(path) + ".tmp";
-    FILE* f = fopen(tmp.c_str(), "wb");
-    if (!f) return fail(PBF_ERR_INVALID, "%s: cannot open for writing", tmp.c_str());
+    HostBuf tmp_buf(strlen(path) + 5);
+    if (!tmp_buf.p) return fail(PBF_ERR_INVALID, "out of host memory");
+    char* const tmp = (char*)tmp_buf.p;
+    snprintf(tmp, strlen(path) + 5, "%s.tmp", path);
+    FILE* f = fopen(tmp, "wb");
+    if (!f) return fail(PBF_ERR_INVALID, "%s: cannot open for writing", tmp);
     const size_t n = (size_t)info->n;
     bool ok = fwrite(&hd, 1, sizeof(hd), f) == sizeof(hd);
     ok = ok && fwrite(pos, 12, n, f) == n && fwrite(vel, 12, n, f) == n && fwrite(iid, 4, n, f) == n;
     ok = (fclose(f) == 0) && ok;
-    if (!ok) { remove(tmp.c_str()); return fail(PBF_ERR_INVALID, "%s: write failed", tmp.c_str()); }
-    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(PBF_ERR_INVALID, "%s: rename failed", path); }
+    if (!ok) { remove(tmp); return fail(PBF_ERR_INVALID, "%s: write failed", tmp); }
+    if (rename(tmp, path) != 0) { remove(tmp); return fail(PBF_ERR_INVALID, "%s: rename failed", path); }
     return PBF_OK;
 }
 
@@ -1331,12 +1357,12 @@ int pbf_checkpoint_save(pbf_sim* s, const char* path, const float* pos, const fl
     if (n > 0 && (!pos || !vel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    std::vector<float> h_pos((size_t)n * 3), h_vel((size_t)n * 3);
-    std::vector<uint32_t> h_iid((size_t)n);
+    HostBuf h_pos((size_t)n * 12), h_vel((size_t)n * 12), h_iid((size_t)n * 4);
+    if (!h_pos.p || !h_vel.p || !h_iid.p) return fail(PBF_ERR_INVALID, "out of host memory (%lld particles)", (long long)n);
     if (n > 0) {
-        CUDA_TRY(cudaMemcpy(h_pos.data(), pos, (size_t)n * 12, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(h_vel.data(), vel, (size_t)n * 12, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(h_iid.data(), iid, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_pos.p, pos, (size_t)n * 12, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_vel.p, vel, (size_t)n * 12, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_iid.p, iid, (size_t)n * 4, cudaMemcpyDeviceToHost));
     }
     pbf_state_info info;
     memset(&info, 0, sizeof(info));
@@ -1346,7 +1372,7 @@ int pbf_checkpoint_save(pbf_sim* s, const char* path, const float* pos, const fl
     memcpy(info.ulim, s->ulim, sizeof(info.ulim));
     memcpy(info.llim, s->llim, sizeof(info.llim));
     info.exact_pow = s->exact_pow;
-    return pbf_state_write(path, &info, h_pos.data(), h_vel.data(), h_iid.data());
+    return pbf_state_write(path, &info, (const float*)h_pos.p, (const float*)h_vel.p, (const uint32_t*)h_iid.p);
 }
 
 int pbf_checkpoint_load(pbf_sim* s, const char* path, float* pos, float* vel, uint32_t* iid, int64_t capacity, int64_t* n_out, int64_t* frame_out) {
@@ -1357,9 +1383,9 @@ int pbf_checkpoint_load(pbf_sim* s, const char* path, float* pos, float* vel, ui
     if (info.n > capacity || info.n > s->max_particles)
         return fail(PBF_ERR_CAPACITY, "%s holds %lld particles, the handle %lld, the buffers %lld", path, (long long)info.n, (long long)s->max_particles, (long long)capacity);
     if (info.n > 0 && (!pos || !vel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
-    std::vector<float> h_pos((size_t)info.n * 3), h_vel((size_t)info.n * 3);
-    std::vector<uint32_t> h_iid((size_t)info.n);
-    rc = pbf_state_read(path, &info, h_pos.data(), h_vel.data(), h_iid.data(), info.n);
+    HostBuf h_pos((size_t)info.n * 12), h_vel((size_t)info.n * 12), h_iid((size_t)info.n * 4);
+    if (!h_pos.p || !h_vel.p || !h_iid.p) return fail(PBF_ERR_INVALID, "out of host memory (%lld particles)", (long long)info.n);
+    rc = pbf_state_read(path, &info, (float*)h_pos.p, (float*)h_vel.p, (uint32_t*)h_iid.p, info.n);
     if (rc) return rc;
     // parameters and box first: a file that does not fit this handle must not leave it half-configured
     const pbf_params old_p = s->p;
@@ -1381,9 +1407,9 @@ int pbf_checkpoint_load(pbf_sim* s, const char* path, float* pos, float* vel, ui
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (info.n > 0) {
-        CUDA_TRY(cudaMemcpy(pos, h_pos.data(), (size_t)info.n * 12, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(vel, h_vel.data(), (size_t)info.n * 12, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(iid, h_iid.data(), (size_t)info.n * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(pos, h_pos.p, (size_t)info.n * 12, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(vel, h_vel.p, (size_t)info.n * 12, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(iid, h_iid.p, (size_t)info.n * 4, cudaMemcpyHostToDevice));
     }
     if (n_out) *n_out = info.n;
     if (frame_out) *frame_out = info.frame;
