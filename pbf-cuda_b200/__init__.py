@@ -41,7 +41,7 @@ EXPORTS = (
     "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
     "pbf_slab_halo_sync", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
     "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count", "pbf_get_const_div_interval",
-    "pbf_get_fast_spiky", "pbf_state_write", "pbf_state_read_info", "pbf_state_read", "pbf_checkpoint_save", "pbf_checkpoint_load",
+    "pbf_get_fast_spiky", "pbf_get_trim_pow", "pbf_state_write", "pbf_state_read_info", "pbf_state_read", "pbf_checkpoint_save", "pbf_checkpoint_load",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
@@ -117,6 +117,7 @@ _lib.pbf_get_lim.argtypes = [_vp, _f3, _f3]
 _lib.pbf_set_option_exact_pow.argtypes = [_vp, C.c_int]
 _lib.pbf_get_grid_dim.argtypes = [_vp, C.POINTER(C.c_int32)]
 _lib.pbf_get_fast_spiky.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+_lib.pbf_get_trim_pow.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
 _lib.pbf_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.pbf_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64]
 _lib.pbf_stage_begin.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
@@ -340,6 +341,12 @@ class Simulator:
         """(in use, mismatches) of the exhaustively verified branch-free spiky scale (pbf_get_fast_spiky)."""
         on, bad = C.c_int32(0), C.c_uint64(0)
         _check(_lib.pbf_get_fast_spiky(self._h, C.byref(on), C.byref(bad)))
+        return int(on.value), int(bad.value)
+
+    def trim_pow(self):
+        """(in use, mismatches) of the exhaustively verified trimmed powf(w, 4.0f) (pbf_get_trim_pow)."""
+        on, bad = C.c_int32(0), C.c_uint64(0)
+        _check(_lib.pbf_get_trim_pow(self._h, C.byref(on), C.byref(bad)))
         return int(on.value), int(bad.value)
 
     def grid_dim(self):

@@ -143,6 +143,11 @@ struct pbf_sim {
     float spiky_h = 0.f;
     int spiky_ok = 0;
     unsigned long long spiky_mismatches = 0;
+    // trimmed powf(w, 4.0f) (pbf_math.cuh pow4_trim): verified exhaustively up to this poly6(0), or off
+    bool pow4_checked = false;
+    float pow4_top = 0.f;
+    int pow4_ok = 0;
+    unsigned long long pow4_mismatches = 0;
 
     int64_t launches = 0;
     bool timing = false;
@@ -280,6 +285,27 @@ int refresh_consts(pbf_sim* s) {
         s->spiky_checked = true;
     }
     c.fast_spiky = s->spiky_ok;
+    // and for the delta-p pass's powf(w, 4.0f): every float w in [0, poly6(0)]; PBF_NO_TRIM_POW=1 keeps powf
+    {
+        const float w_top = ((c.poly6_coef * c.h2) * c.h2) * c.h2;   // poly6_in(0), the largest w (pbf_math.cuh)
+        if (!(s->pow4_checked && s->pow4_top == w_top)) {
+            s->pow4_ok = 0;
+            s->pow4_mismatches = 0;
+            const char* off = getenv("PBF_NO_TRIM_POW");
+            if (!(off && off[0] == '1') && w_top >= 0.f && w_top < 3.0e38f && cudaSetDevice(s->device) == cudaSuccess) {
+                unsigned long long bad = ~0ull;
+                if (verify_pow4(w_top, &bad, nullptr) == cudaSuccess) {
+                    s->pow4_mismatches = bad;
+                    s->pow4_ok = bad == 0 ? 1 : 0;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+            s->pow4_top = w_top;
+            s->pow4_checked = true;
+        }
+        c.trim_pow = s->pow4_ok;
+    }
     return PBF_OK;
 }
 
@@ -551,6 +577,12 @@ int pbf_get_lim(const pbf_sim* s, float ulim[3], float llim[3]) {
 int pbf_get_const_div_interval(const pbf_sim* s, float* lo, float* hi) {
     if (!s || !lo || !hi) return fail(PBF_ERR_INVALID, "null argument");
     *lo = s->div_lo; *hi = s->div_hi;
+    return PBF_OK;
+}
+int pbf_get_trim_pow(const pbf_sim* s, int32_t* on, uint64_t* mismatches) {
+    if (!s || !on || !mismatches) return fail(PBF_ERR_INVALID, "null argument");
+    *on = s->pow4_ok;
+    *mismatches = (uint64_t)s->pow4_mismatches;
     return PBF_OK;
 }
 int pbf_get_fast_spiky(const pbf_sim* s, int32_t* on, uint64_t* mismatches) {

@@ -76,6 +76,8 @@ struct SolverConsts {
     float div_lo, div_hi;
     // 1: spiky_scale_fast (pbf_math.cuh) matched spiky_scale for EVERY float r2 in [0, h2_cull] on this device
     int32_t fast_spiky;
+    // 1: pow4_trim (pbf_math.cuh) matched powf(w, 4.0f) for EVERY float w in [0, poly6(0)] on this device
+    int32_t trim_pow;
 };
 
 // (key, source index) pair the radix sort moves; one 8-byte transaction per element.
@@ -208,6 +210,7 @@ cudaError_t launch_neighbor_count(const float4* x, CullScratch& cs, const uint2*
 cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStream_t st);
 // stats.cu: exhaustive comparison of spiky_scale_fast with spiky_scale over every float r2 in [0, top]
 cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* mismatches, cudaStream_t st);
+cudaError_t verify_pow4(float top, unsigned long long* mismatches, cudaStream_t st);
 
 // force-load every kernel of a translation unit (see the comment at preload_solver in solver.cu)
 cudaError_t preload_advect_key();

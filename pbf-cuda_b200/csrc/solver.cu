@@ -216,6 +216,12 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
 #ifndef PBF_REPLAY_MINBLOCKS
 #define PBF_REPLAY_MINBLOCKS 16
 #endif
+// (the branch-free POW = 3 body lets the compiler overlap more pairs than 32 registers hold: unrolled by 4 it
+//  spills two values per trip of four pairs — and is still the faster one: 2.456 vs 2.494 ms per step unrolled by 2)
+#ifndef PBF_REPLAY_UNROLL3
+#define PBF_REPLAY_UNROLL3 4
+#endif
+constexpr int REPLAY_UNROLL3 = PBF_REPLAY_UNROLL3;
 template <int POW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
 delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
@@ -230,7 +236,7 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
-#pragma unroll 4
+#pragma unroll (POW == 3 ? REPLAY_UNROLL3 : 4)
     for (uint32_t k = 0; k < cnt; k++) {
         const size_t e = pair0 + (size_t)k * GATHER_THREADS;
         const uint2 js = __ldg(&pair_js[e]);
@@ -363,12 +369,15 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<0>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<2>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<3>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, update_velocity_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, neighbor_count_kernel);
@@ -436,8 +445,9 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
     if (n <= 0) return cudaSuccess;
     const CullSoA soa = soa_of(cs);   // this iteration's coordinates: what the overflow kernel culls on
     const CullOut co = out_of(cs);    // the other set receives the coordinates of x_out
-    // 2: exact powf with the exponent folded (n_corr == 4, the default); 1: exact powf, any exponent; 0: (w*w)^2
-    const int pow_mode = c.n_corr == 4.0f ? (c.exact_pow ? 2 : 0) : 1;
+    // 3: the verified special-case-free powf(w, 4) (n_corr == 4, the default); 2: the library's powf with the
+    // exponent folded (same bits; when 3 did not verify or is switched off); 1: powf, any exponent; 0: (w*w)^2
+    const int pow_mode = c.n_corr == 4.0f ? (c.exact_pow ? (c.trim_pow ? 3 : 2) : 0) : 1;
     const unsigned nb = nblocks(n, GATHER_THREADS);
     const unsigned nb_ovf = nb < 148u * PBF_GATHER_MINBLOCKS ? nb : 148u * PBF_GATHER_MINBLOCKS;
     uint32_t* const f_read = pl.js ? pl.ovf_flag + (parity & 1) : nullptr;
@@ -455,7 +465,8 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
                                                                                nullptr, nullptr, nullptr, hp, g, c);          \
         }                                                                                                                     \
     } while (0)
-    if (pow_mode == 2) PBF_DP_LAUNCH(2);
+    if (pow_mode == 3) PBF_DP_LAUNCH(3);
+    else if (pow_mode == 2) PBF_DP_LAUNCH(2);
     else if (pow_mode == 1) PBF_DP_LAUNCH(1);
     else PBF_DP_LAUNCH(0);
 #undef PBF_DP_LAUNCH

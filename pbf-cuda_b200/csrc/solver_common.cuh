@@ -81,12 +81,15 @@ __device__ __forceinline__ uint32_t push_hits2(uint32_t hits, f32x2 px, f32x2 py
 // w^n_corr of the delta-p pass's s_corr (Simulator_kernel.cuh:166 powf(..., n_corr)). POW = 1: powf with
 // the run-time exponent, exactly the call inside the reference; POW = 2: the same libdevice powf with the
 // exponent known to be 4.0f (the default n_corr) — the compiler folds the exponent-dependent parts of the
-// routine (~16 of ~84 instructions), the arithmetic and hence the bits are the same; POW = 0: (w*w)^2,
+// routine (~16 of ~84 instructions), the arithmetic and hence the bits are the same; POW = 3: that routine's
+// arithmetic without its special-case tests (pbf_math.cuh pow4_trim), used only after it matched powf(w, 4.0f)
+// for every w the pass can produce on this device (SolverConsts::trim_pow); POW = 0: (w*w)^2,
 // opt-in (pbf_set_option_exact_pow(0)), within 1e-5 but not bit-identical.
 template <int POW>
 __device__ __forceinline__ float pow_ncorr(float w, const SolverConsts& c) {
     if (POW == 1) return powf(w, c.n_corr);
     if (POW == 2) return powf(w, 4.0f);
+    if (POW == 3) return pow4_trim(w);
     const float w2 = __fmul_rn(w, w);
     return __fmul_rn(w2, w2);
 }

@@ -293,6 +293,7 @@ cudaError_t preload_solver_team() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_team_kernel<0>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_team_kernel<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_team_kernel<2>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_team_kernel<3>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_team_kernel);
     return e;
 }
@@ -315,7 +316,8 @@ void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut c
                                 const uint32_t* pair_cnt, const HaloPush& hp, const SolverConsts& c, int pow_mode,
                                 cudaStream_t st) {
     const unsigned nb = team_blocks(n);
-    if (pow_mode == 2) delta_p_replay_team_kernel<2><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
+    if (pow_mode == 3) delta_p_replay_team_kernel<3><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
+    else if (pow_mode == 2) delta_p_replay_team_kernel<2><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
     else if (pow_mode == 1) delta_p_replay_team_kernel<1><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
     else delta_p_replay_team_kernel<0><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
 }

@@ -118,10 +118,38 @@ cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* m
     return e;
 }
 
+// ---- the same for the trimmed powf(w, 4.0f) of the delta-p pass (pbf_math.cuh pow4_trim) ------------------
+__global__ void __launch_bounds__(256) pow4_check_kernel(uint32_t top_bits, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (uint64_t b = (uint64_t)blockIdx.x * 256 + threadIdx.x; b <= top_bits; b += (uint64_t)gridDim.x * 256) {
+        const float w = __uint_as_float((uint32_t)b);
+        if (__float_as_uint(pow4_trim(w)) != __float_as_uint(powf(w, 4.0f))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t verify_pow4(float top, unsigned long long* mismatches, cudaStream_t st) {
+    unsigned long long* dev = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dev, 8);
+    if (e != cudaSuccess) return e;
+    uint32_t top_bits;
+    memcpy(&top_bits, &top, 4);
+    e = cudaMemsetAsync(dev, 0, 8, st);
+    if (e == cudaSuccess) {
+        pow4_check_kernel<<<148 * 16, 256, 0, st>>>(top_bits, dev);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches, dev, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return e;
+}
+
 cudaError_t preload_stats() {
     cudaFuncAttributes a;
     cudaError_t e = cudaFuncGetAttributes(&a, const_div_check_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spiky_check_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pow4_check_kernel);
     return e != cudaSuccess ? e : cudaFuncGetAttributes(&a, stats_kernel);
 }
 

@@ -574,3 +574,47 @@ def test_fast_spiky_scale_is_verified_for_every_r2(pbf, torch, monkeypatch):
     exact = one_step(sim)
     sim.close()
     assert fast == exact
+
+
+def test_trimmed_pow_is_verified_for_every_w(pbf, torch, monkeypatch):
+    """The special-case-free powf(w, 4) of the delta-p pass is used only if it matched the library's
+    powf(w, 4.0f) for EVERY float w in [0, W(0)] on this device (about 1.15e9 values at the default h). It must
+    verify without a single mismatch for the default h and two others, and steps with PBF_NO_TRIM_POW=1 (the
+    library call) must give the same bits as steps with it."""
+    pos, vel, iid, ulim, llim = pbf.scene_double_dam_reference()
+    n = len(iid)
+
+    def steps(sim):
+        d = [torch.from_numpy(a).cuda() for a in (pos, np.zeros_like(pos), vel, np.zeros_like(vel))]
+        d_iid = torch.from_numpy(iid.astype(np.int64)).cuda().to(torch.int32)
+        for _ in range(12):
+            sim.step(d[0], d[1], d[2], d[3], d_iid, n)
+            d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+        torch.cuda.synchronize()
+        return d[0].cpu().numpy().tobytes(), d[2].cpu().numpy().tobytes(), sim.read(pbf.READ_RHO).tobytes()
+
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    assert sim.trim_pow() == (1, 0)
+    trimmed = steps(sim)
+    for h in (0.125, 0.07):
+        p = pbf.default_params()
+        p.h = h
+        sim.loadParams(p)
+        assert sim.trim_pow() == (1, 0), (h, sim.trim_pow())
+    sim.close()
+    monkeypatch.setenv("PBF_NO_TRIM_POW", "1")
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    assert sim.trim_pow() == (0, 0)
+    library = steps(sim)
+    sim.close()
+    assert trimmed == library
+    # the same with the thread-per-particle kernels (the 32 K scene takes the four-lane kernels by default)
+    monkeypatch.setenv("PBF_TEAM", "0")
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    assert steps(sim) == trimmed
+    sim.close()
+    monkeypatch.delenv("PBF_NO_TRIM_POW")
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    assert sim.trim_pow() == (1, 0)
+    assert steps(sim) == trimmed
+    sim.close()
