@@ -5,8 +5,20 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pbf_step (advect, grid, 4 Jacobi iterations of lambda / delta-p, velocity update,
-XSPH) over the whole scene. Default workload at N=1: BASELINE config 2, the 1 048 576-particle single
-dam break (pbf-cuda_b200 SCENES["dam_1m"]), synthetic, reference default parameters.
+XSPH) over the whole scene. The JSON line's headline (`value`, `ms_per_step`, `e2e`, `roofline`) is
+BASELINE config 2 at N=1 — the 1 048 576-particle single dam break (scenes.py SCENES["dam_1m"]),
+synthetic, reference default parameters — and that block repeated N times along x at N>1 (weak).
+
+Every OTHER named size of BASELINE.json rides along in the same line:
+  N=1   `sizes`: double_dam_32k (config 1, 200 steps), sweep_4m (config 3, moving wall, 20 steps),
+        double_dam_16m (config 4 on one GPU, 10 steps) — ms/step, particle-steps/s, whole-step HBM fraction,
+        the state digest after the window, and the ratio / digest comparison with the reference arm's run of
+        the same window on this box when that ran first (it leaves gpurun_out/bench_reference_last.json).
+  N>1   `legs`: double_dam_16m STRONG over the N ranks (config 4), and at N=8 dam_64m strong (config 5; the
+        same scene as its weak form, the 8.4 M-particle block per GPU repeated 8 times along x).
+  `parity`: after every multi-GPU window the order-independent digest (pbf_state_digest) of all ranks' owned
+        particles is compared with the digest of ONE GPU running the same scene for the same number of steps
+        (rank 0, after the timed region): "bit_exact" or "MISMATCH".
 
 Timed region (`value`): K steps, state resident in HBM, each step bracketed by CUDA events on the
 launching stream; L2 is flushed (a 256 MB memset, not timed) between steps. `e2e`: the same metric
@@ -15,12 +27,13 @@ inside the timed region). `roofline`: the dominant kernel (the lambda or delta-p
 with CUDA events inside the library, against the measured HBM peak of MEASURED_PEAKS.json.
 `cpu_baseline`: the scalar oracle (oracle/pbf_oracle.c, OpenMP over particles) on the host cores on a
 bounded sample of the same workload. `--impl reference` times the reference's own Simulator.cu
-(oracle/_ref/libpbf_ref.so, built headless for sm_100) on the same workload; the reference has no
+(oracle/_ref/libpbf_ref.so, built headless for sm_100) on the same workloads; the reference has no
 CPU implementation of this path, its path IS CUDA — if that library is absent the CPU oracle port is
-timed instead.
+timed instead. The reference arm never maps libpbf_b200.so: scenes come from the oracle's host generator.
 """
 import argparse
 import importlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -38,6 +51,20 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 ALG_BYTES_STEP = 488          # 296 + 48*K at K = 4, per particle-step
 ALG_BYTES = {"lambda": 20, "delta_p": 28}   # per particle per pass: R 12, W 4+4 / R 12+4, W 12
 FALLBACK_HBM_GBS = 6650.0     # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
+REF_FILE = os.path.join(ROOT, "gpurun_out", "bench_reference_last.json")
+
+# (scene, timed steps, warm-up steps) of the `sizes` entries at N=1 — the same windows in both arms
+SIZES = (("double_dam_32k", 200, 5), ("sweep_4m", 20, 5), ("double_dam_16m", 10, 3))
+# multi-GPU legs behind the weak headline: (scene, scaling, timed steps, warm-up, smallest world)
+LEGS = (("double_dam_16m", "strong", 10, 3, 2), ("dam_64m", "strong", 10, 3, 8))
+
+
+def load_scenes():
+    """scenes.py alone, by path: the reference arm must not import the package (that maps libpbf_b200.so)."""
+    spec = importlib.util.spec_from_file_location("_pbf_scenes", os.path.join(ROOT, "pbf-cuda_b200", "scenes.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
 
 
 def hbm_peak():
@@ -46,6 +73,31 @@ def hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def digest_numpy(pos, vel, iid):
+    """include/pbf.h pbf_state_digest_* restated in numpy (tests/test_state_cpu.py checks it against the library):
+    what the reference arm uses, which must not load the product's library."""
+    M = np.uint64
+    def mix(z):
+        z = z + M(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> M(30))) * M(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> M(27))) * M(0x94D049BB133111EB)
+        return z ^ (z >> M(31))
+    p = np.ascontiguousarray(pos, np.float32).view(np.uint32).reshape(-1, 3).astype(np.uint64)
+    v = np.ascontiguousarray(vel, np.float32).view(np.uint32).reshape(-1, 3).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = mix(np.ascontiguousarray(iid).view(np.uint32).astype(np.uint64))
+        h = mix(h ^ (p[:, 0] | (p[:, 1] << M(32))))
+        h = mix(h ^ (p[:, 2] | (v[:, 0] << M(32))))
+        h = mix(h ^ (v[:, 1] | (v[:, 2] << M(32))))
+        s = int(np.add.reduce(h, dtype=np.uint64)) if len(h) else 0
+        x = int(np.bitwise_xor.reduce(mix(h))) if len(h) else 0
+    return s, x
+
+
+def hexd(d):
+    return "%016x%016x" % (d[0], d[1])
 
 
 class ClockSampler:
@@ -95,37 +147,121 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def scene_state(pbf, torch, name, dev, sc=None):
-    sc = sc or pbf.SCENES[name]
-    if "blocks" in sc:
-        n = sum(int(np.prod(b[1])) for b in sc["blocks"])
-        pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        vel = torch.empty_like(pos)
-        iid = torch.empty(n, dtype=torch.int32, device=dev)
-        off = 0
-        for origin, n3 in sc["blocks"]:
-            m = int(np.prod(n3))
-            pbf.scene_block_device(origin, n3, pos[off:], vel[off:], iid[off:], first_iid=off)
-            off += m
-    else:
-        p, v, i, _, _ = pbf.scene_double_dam_reference()
-        n = len(i)
-        pos, vel = torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)
-        iid = torch.from_numpy(i.astype(np.int64)).to(dev).to(torch.int32)
-    torch.cuda.synchronize()
-    return sc, n, pos, vel, iid
-
-
-def workload_name(name, sc, n):
-    d = [int(np.ceil(np.float32(np.float32(u) - np.float32(l)) / np.float32(0.1))) for u, l in zip(sc["ulim"], sc["llim"])]
+def workload_name(S, name, sc, n):
+    d = S.scene_dims(sc)
     return "%s: %d particles, niter 4, box %dx%dx%d cells, reference default parameters" % (name, n, d[0], d[1], d[2])
 
 
-def lim_at(pbf, sc, frame):
+def lim_at(S, sc, frame):
     if "wall" not in sc:
         return None
     w = sc["wall"]
-    return pbf.wall_lim(sc["ulim"], sc["llim"], w["a_ulim"], w["a_llim"], w["w"], frame)
+    return S.wall_lim(sc["ulim"], sc["llim"], w["a_ulim"], w["a_llim"], w["w"], frame)
+
+
+def host_scene(sc):
+    """The scene's initial state from the ORACLE's host generator (bit-identical to the product's generators,
+    tests/test_capi_cpu.py, tests/test_parity_gpu.py) — used by the cpu_baseline leg and the reference arm."""
+    import _oracle as O
+    if "blocks" in sc:
+        parts, off = [], 0
+        for origin, n3 in sc["blocks"]:
+            parts.append(O.scene_block(origin, n3, 0.05, 27, off))
+            off += int(np.prod(n3))
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+    pos, vel, iid, _, _ = O.scene_double_dam_reference()
+    return pos, vel, iid
+
+
+def timed_window(torch, step, steps, warmup, flush, before=None):
+    """`warmup` untimed steps, then `steps` steps each bracketed by CUDA events on the current stream, L2 flushed
+    (outside the event pairs) between them. Returns (total ms, per-step ms)."""
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if before:
+        before()
+    torch.cuda.synchronize()
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    series = [a.elapsed_time(b) for a, b in ev]
+    return sum(series), series
+
+
+class ProductRun:
+    """One scene on one GPU through pbf_step on device buffers (the product's C-ABI via the ctypes mirror)."""
+
+    def __init__(self, pbf, torch, local, name, sc=None):
+        self.pbf, self.torch, self.name = pbf, torch, name
+        self.dev = torch.device("cuda", local)
+        sc = self.sc = sc or pbf.SCENES[name]
+        if "blocks" in sc:
+            n = pbf.scene_particles(sc)
+            pos = torch.empty((n, 3), dtype=torch.float32, device=self.dev)
+            vel = torch.empty_like(pos)
+            iid = torch.empty(n, dtype=torch.int32, device=self.dev)
+            off = 0
+            for origin, n3 in sc["blocks"]:
+                pbf.scene_block_device(origin, n3, pos[off:], vel[off:], iid[off:], first_iid=off)
+                off += int(np.prod(n3))
+        else:
+            p, v, i, _, _ = pbf.scene_double_dam_reference()
+            n = len(i)
+            pos, vel = torch.from_numpy(p).to(self.dev), torch.from_numpy(v).to(self.dev)
+            iid = torch.from_numpy(i.astype(np.int64)).to(self.dev).to(torch.int32)
+        torch.cuda.synchronize()
+        self.n, self.iid = n, iid
+        self.bufs = [pos, torch.zeros_like(pos), vel, torch.zeros_like(vel)]
+        self.sim = pbf.Simulator(pbf.default_params(), sc.get("ulim_max", sc["ulim"]), sc["llim"], n, device=local)
+        self.sim.setLim(sc["ulim"], sc["llim"])
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.frame = 0
+        self.local = local
+
+    def step(self):
+        lim = lim_at(self.pbf, self.sc, self.frame)
+        if lim is not None:
+            self.sim.setLim(*lim)
+        b = self.bufs
+        self.sim.step(b[0], b[1], b[2], b[3], self.iid, self.n, self.stream)
+        b[0], b[1] = b[1], b[0]
+        b[2], b[3] = b[3], b[2]
+        self.frame += 1
+
+    def digest(self):
+        return self.pbf.state_digest(self.bufs[0], self.bufs[2], self.iid, self.n, device=self.local, stream=self.stream)
+
+    def close(self):
+        self.sim.close()
+        self.bufs = self.iid = None
+
+
+def read_reference_file():
+    try:
+        with open(REF_FILE) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def size_entry(S, name, sc, n, steps, warmup, total_ms, digest, peak, ref):
+    value = n * steps / (total_ms * 1e-3)
+    e = {"scene": name, "workload": workload_name(S, name, sc, n), "particles": n, "steps": steps, "warmup": warmup,
+         "ms_per_step": round(total_ms / steps, 5), "value": round(value, 1), "unit": "particle-steps/s",
+         "whole_step_frac": round(ALG_BYTES_STEP * value / 1e9 / peak, 5), "digest": hexd(digest)}
+    r = (ref or {}).get("%s/%d/%d" % (name, steps, warmup))
+    if r:
+        e["reference_value"] = r["value"]
+        e["reference_ratio"] = round(value / r["value"], 2)
+        e["reference_source"] = "bench.py --impl reference, same window, this box (gpurun_out/bench_reference_last.json)"
+        if r.get("digest"):
+            e["parity_vs_reference"] = "bit_exact" if r["digest"] == e["digest"] else "MISMATCH"
+    return e
 
 
 def run_product(args, rank, world, dist):
@@ -134,47 +270,25 @@ def run_product(args, rank, world, dist):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    sc, n, pos, vel, iid = scene_state(pbf, torch, args.scene, dev)
-    npos, nvel = torch.zeros_like(pos), torch.zeros_like(vel)
-    params = pbf.default_params()
-    sim = pbf.Simulator(params, sc.get("ulim_max", sc["ulim"]), sc["llim"], n, device=local)
-    sim.setLim(sc["ulim"], sc["llim"])
-    stream = torch.cuda.current_stream().cuda_stream
-    bufs = [pos, npos, vel, nvel]
-    frame = [0]
-
-    def one_step():
-        lim = lim_at(pbf, sc, frame[0])
-        if lim is not None:
-            sim.setLim(*lim)
-        sim.step(bufs[0], bufs[1], bufs[2], bufs[3], iid, n, stream)
-        bufs[0], bufs[1] = bufs[1], bufs[0]
-        bufs[2], bufs[3] = bufs[3], bufs[2]
-        frame[0] += 1
-
+    run = ProductRun(pbf, torch, local, args.scene)
+    sc, n, sim = run.sc, run.n, run.sim
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    for _ in range(args.warmup):
-        one_step()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = sim.launch_count()
+    launches0 = [0]
+
+    def before():
+        if rank == 0:
+            sampler.start()
+        launches0[0] = sim.launch_count()
+        if dist:
+            dist.barrier()
+
+    total_ms, series = timed_window(torch, run.step, args.steps, args.warmup, flush, before)
     if dist:
         dist.barrier()
-    torch.cuda.synchronize()
-    for k in range(args.steps):
-        flush.zero_()
-        ev[k][0].record()
-        one_step()
-        ev[k][1].record()
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    launches = sim.launch_count() - launches0
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = sim.launch_count() - launches0[0]
     clocks = sampler.stop() if rank == 0 else None
+    digest = run.digest()
     if dist:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -186,7 +300,7 @@ def run_product(args, rank, world, dist):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        one_step()
+        run.step()
     e1.record()
     torch.cuda.synchronize()
     b2b_ms = e0.elapsed_time(e1) / args.steps
@@ -194,13 +308,13 @@ def run_product(args, rank, world, dist):
     kacc, sacc, reps = {}, {}, 5
     for _ in range(reps):
         flush.zero_()
-        one_step()
+        run.step()
         for k, v in sim.kernel_ms().items():
             kacc[k] = kacc.get(k, 0.0) + v / reps
         for k, v in sim.stage_ms().items():
             sacc[k] = sacc.get(k, 0.0) + v / reps
     sim.enable_stage_timing(False)
-    stats = sim.stats(bufs[0], bufs[2], n)
+    stats = sim.stats(run.bufs[0], run.bufs[2], n)
 
     if rank != 0:
         return None
@@ -209,26 +323,30 @@ def run_product(args, rank, world, dist):
     achieved = ALG_BYTES[dom] * n / (kacc[dom] * 1e-3) / 1e9
     step_gbs = ALG_BYTES_STEP * (value / world) / 1e9
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": TRAFFIC.get(dom),
+                "frac": round(achieved / peak, 5), "traffic": NCU[dom]["traffic"],
+                "traffic_source": NCU["source"] + " — a separate ncu run, NOT measured in this run",
+                "issue_slot_frac": NCU[dom]["issue"], "l1_frac": NCU[dom]["l1"], "dram_frac": NCU[dom]["dram"],
                 "peak_source": peak_src, "kernel_ms": round(kacc[dom], 4),
                 "algorithmic_bytes_per_particle": ALG_BYTES[dom],
                 "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved": round(step_gbs, 2),
                                "frac": round(step_gbs / peak, 5)},
                 "note": "the lambda / XSPH sweeps are bound by the L1 wavefront rate and instruction issue, not by HBM "
-                        "(SURVEY.md App. D, DESIGN.md 5): ncu at step 100 shows 67% issue-slot utilisation, 74-89% of the L1 "
-                        "data-pipe wavefront rate and 12% DRAM throughput; the delta-p pass replays the lambda pass's neighbour "
-                        "list and evaluates the exact powf: 76% issue, 27% DRAM (see delta_p below)",
-                "delta_p": {"kernel_ms": round(kacc["delta_p"], 4), "traffic": TRAFFIC["delta_p"],
-                            "dram_GBps_from_traffic": round(TRAFFIC["delta_p"] / (kacc["delta_p"] * 1e-3) / 1e9, 1)}}
+                        "(SURVEY.md App. D, DESIGN.md 5): issue_slot_frac / l1_frac / dram_frac are the ncu figures of "
+                        "the same kernel in the state the kernel timers see; the delta-p pass replays the lambda pass's "
+                        "neighbour list and evaluates the exact powf (see delta_p below)",
+                "delta_p": {"kernel_ms": round(kacc["delta_p"], 4), "traffic": NCU["delta_p"]["traffic"],
+                            "issue_slot_frac": NCU["delta_p"]["issue"], "dram_frac": NCU["delta_p"]["dram"],
+                            "dram_GBps_from_traffic": round(NCU["delta_p"]["traffic"] / (kacc["delta_p"] * 1e-3) / 1e9, 1)}}
 
     # ---- end to end through the host-buffer entry point --------------------------------------------
     # the SAME window of the SAME scene as `value`: a fresh initial state, `warmup` untimed steps, `steps`
     # timed steps, every one of them uploading its inputs from pinned host memory and downloading its result
-    sc2, n2, pos0, vel0, iid0 = scene_state(pbf, torch, args.scene, dev)
+    fresh = ProductRun(pbf, torch, local, args.scene)
     h = [torch.empty((n, 3), dtype=torch.float32).pin_memory() for _ in range(4)]
     h_iid = torch.empty(n, dtype=torch.int32).pin_memory()
-    h[0].copy_(pos0); h[2].copy_(vel0); h_iid.copy_(iid0)
-    del pos0, vel0, iid0
+    h[0].copy_(fresh.bufs[0]); h[2].copy_(fresh.bufs[2]); h_iid.copy_(fresh.iid)
+    fresh.close()
+    del fresh
     hn = [t.numpy() for t in h]
     hi = h_iid.numpy().view(np.uint32)
     sim.setLim(sc["ulim"], sc["llim"])
@@ -249,35 +367,61 @@ def run_product(args, rank, world, dist):
     for _ in range(args.steps):
         host_step()
     e2e_s = time.perf_counter() - t0
+    e2e_digest = pbf.state_digest(hn[0], hn[2], hi)
     e2e = {"value": round(n * args.steps / e2e_s, 1), "unit": "particle-steps/s", "steps": args.steps,
            "h2d_bytes_per_step": 28 * n, "d2h_bytes_per_step": 28 * n,
+           "parity_vs_device_path": "bit_exact" if e2e_digest == digest else "MISMATCH",
            "api": "pbf_step_host (pinned host buffers; upload pos/vel/iid, step, download npos/nvel/iid), "
                   "same scene and step window as `value`, wall clock around the synchronous calls"}
+    run.close()
+    del run, h, h_iid, hn, hi
+    torch.cuda.empty_cache()
 
+    ref = read_reference_file() if world == 1 else {}
     out = {"metric": "particle-steps/s", "value": round(value, 1), "unit": "particle-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(args.scene, sc, n), "particles_per_gpu": n,
+           "config": {"workload": workload_name(pbf, args.scene, sc, n), "particles_per_gpu": n,
                       "parallelism": "single GPU" if world == 1 else "replicas x%d (one independent scene per GPU)" % world,
                       "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
                       "ms_per_step_back_to_back": round(b2b_ms, 5), "exact_pow": True,
-                      "ms_per_step_series": [round(a.elapsed_time(b), 2) for a, b in ev],
+                      "ms_per_step_series": [round(x, 2) for x in series],
                       "stage_ms": {k: round(v, 4) for k, v in sacc.items()},
                       "kernel_ms": {k: round(v, 4) for k, v in kacc.items()},
                       "stats_after_run": {k: round(v, 6) for k, v in stats.items()}},
-           "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "clocks": clocks}
+           "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "clocks": clocks,
+           "digest": hexd(digest)}
+    r = ref.get("%s/%d/%d" % (args.scene, args.steps, args.warmup))
+    if r and r.get("digest"):
+        out["parity_vs_reference"] = "bit_exact" if r["digest"] == out["digest"] else "MISMATCH"
+    # ---- the other named single-GPU sizes (BASELINE configs 1, 3, 4) ----------------------------------
+    if world == 1 and not args.no_sizes:
+        sizes = []
+        for name, steps, warmup in SIZES:
+            if name == args.scene and steps == args.steps:
+                continue
+            try:
+                q = ProductRun(pbf, torch, local, name)
+                ms, _ = timed_window(torch, q.step, steps, warmup, flush)
+                sizes.append(size_entry(pbf, name, q.sc, q.n, steps, warmup, ms, q.digest(), peak, ref))
+                q.close()
+                del q
+                torch.cuda.empty_cache()
+            except Exception as ex:   # noqa: BLE001 - an entry that failed says so, the headline stays
+                sizes.append({"scene": name, "error": repr(ex)})
+        out["sizes"] = sizes
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, n, sc)
+        out["cpu_baseline"] = cpu_baseline(args, pbf.SCENES[args.scene], n)
     return out
 
 
 # ---- N > 1: one scene across the ranks (x-slab decomposition, pbf-cuda_b200/slab.py) ----------------
 
-def slab_scene(pbf, name, world, scaling):
+def slab_scene(S, name, world, scaling):
     """Block list and box of the multi-GPU workload. weak: the scene's single block and its box are
     repeated `world` times along x (per-GPU work fixed: SURVEY.md 8d config 5 'weak'); strong: the named
     scene as it is, cut into `world` slabs."""
-    sc = dict(pbf.SCENES[name])
+    sc = dict(S.SCENES[name])
     if "blocks" not in sc:
         raise SystemExit("scene %s has no block description; multi-GPU runs need a block scene" % name)
     if scaling == "weak":
@@ -317,19 +461,15 @@ def slab_generate(pbf, slab, torch, dev, sc, planes, layer_ranges, keep=None, ch
     return tuple(torch.cat([q[i] for q in parts]) for i in range(3))
 
 
-def run_product_slab(args, rank, world, dist):
-    import torch
-    pbf = importlib.import_module("pbf-cuda_b200")   # raises if libpbf_b200.so is missing: no fallback
-    slab = importlib.import_module("pbf-cuda_b200.slab")
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
+def slab_leg(args, pbf, slab, torch, dist, rank, world, local, name, scaling, steps, warmup, full):
+    """One scene over the `world` ranks: `warmup` + `steps` SlabSimulator steps, device-timed (max over ranks),
+    then the digest of all owned particles; full = the headline leg (per-kernel / per-phase timers, e2e).
+    Afterwards rank 0 runs the same scene for the same number of steps on ONE GPU and compares digests."""
     dev = torch.device("cuda", local)
-    sc = slab_scene(pbf, args.scene, world, args.scaling)
+    sc = slab_scene(pbf, name, world, scaling)
     params = pbf.default_params()
-    h = np.float32(0.1)
-    dims = [int(np.ceil(np.float32(np.float32(u) - np.float32(l)) / h)) for u, l in zip(sc["ulim"], sc["llim"])]
-    planes = dims[0]
-    n_total = sum(int(np.prod(b[1])) for b in sc["blocks"])
+    planes = pbf.scene_dims(sc)[0]
+    n_total = pbf.scene_particles(sc)
     ghost, margin = args.ghost, args.margin
     comm = slab.TorchComm(dist, device=dev)
 
@@ -362,141 +502,207 @@ def run_product_slab(args, rank, world, dist):
         raise SystemExit("slab initialisation lost particles: %d of %d" % (sim.total_particles(), n_total))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    for _ in range(args.warmup):
-        sim.step()
-    sim.finish()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0, msgs0, bytes0 = eng.sim.launch_count(), sim.messages, sim.bytes_sent
-    dist.barrier()
-    torch.cuda.synchronize()
-    trace = os.environ.get("PBF_BENCH_TRACE") == "1"
-    for k in range(args.steps):
-        flush.zero_()
-        ev[k][0].record()
-        if trace:
-            print("TRACE rank %d step %d begins %.4f" % (rank, k, time.time()), flush=True)
-        sim.step()
-        ev[k][1].record()
-    torch.cuda.synchronize()
+    mark = {}
+
+    def before():
+        sim.finish()
+        if rank == 0 and full:
+            sampler.start()
+        mark["l"], mark["m"], mark["b"] = eng.sim.launch_count(), sim.messages, sim.bytes_sent
+        dist.barrier()
+
+    total_ms, series = timed_window(torch, sim.step, steps, warmup, flush, before)
     dist.barrier()
     sim.finish()
-    launches = eng.sim.launch_count() - launches0
-    msgs, sent = sim.messages - msgs0, sim.bytes_sent - bytes0
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.sim.launch_count() - mark["l"]
+    msgs, sent = sim.messages - mark["m"], sim.bytes_sent - mark["b"]
+    clocks = sampler.stop() if (rank == 0 and full) else None
+    own_ms = total_ms
+    # the state after exactly warmup + steps steps: every rank's owned particles, digests combined over the ranks
+    d = pbf.state_digest(*eng.state(), device=local, stream=torch.cuda.current_stream().cuda_stream)
+    dt = torch.tensor([d[0] - (1 << 64) if d[0] >= (1 << 63) else d[0], d[1] - (1 << 64) if d[1] >= (1 << 63) else d[1]],
+                      dtype=torch.int64, device=dev)
+    alld = [torch.zeros_like(dt) for _ in range(world)]
+    dist.all_gather(alld, dt)
+    digest = pbf.combine_digests([(int(q[0]) & 0xFFFFFFFFFFFFFFFF, int(q[1]) & 0xFFFFFFFFFFFFFFFF) for q in alld])
     t = torch.tensor([total_ms, float(eng.n_own), -float(eng.n_own)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, n_max, n_min = float(t[0]), int(t[1]), int(-t[2])
-    value = n_total * args.steps / (total_ms * 1e-3)
+    value = n_total * steps / (total_ms * 1e-3)
+    peak, peak_src = hbm_peak()
+    res = {"scene": name, "scaling": scaling, "workload": workload_name(pbf, name + (" x%d along x (weak)" % world if scaling == "weak" else ""), sc, n_total),
+           "particles_total": n_total, "particles_per_gpu": {"min": n_min, "max": n_max}, "steps": steps, "warmup": warmup,
+           "ms_per_step": round(total_ms / steps, 5), "value": round(value, 1), "unit": "particle-steps/s",
+           "whole_step_frac_per_gpu": round(ALG_BYTES_STEP * value / world / 1e9 / peak, 5),
+           "slab_boundaries": [int(b) for b in sim.bounds], "digest": hexd(digest)}
+    extra = {}
+    if full:
+        # per-kernel device times on this rank for the roofline (same timers as the single-GPU run)
+        eng.sim.enable_stage_timing(True)
+        kacc, reps = {}, 3
+        for _ in range(reps):
+            flush.zero_()
+            sim.step()
+            for k, v in eng.sim.kernel_ms().items():
+                kacc[k] = kacc.get(k, 0.0) + v / reps
+        eng.sim.enable_stage_timing(False)
+        n_own = eng.n_own
+        # where a step's device time goes on every rank (phase stamps on the stream), and who is slowest
+        phases = {}
+        for _ in range(reps):
+            flush.zero_()
+            for k, v in sim.profile_step().items():
+                phases[k] = phases.get(k, 0.0) + v / reps
+        names = ["raw_exchange", "keys_sort_layout", "count_allgather", "lambda", "delta_p", "update_velocity", "xsph", "halo"]
+        pt = torch.tensor([phases.get(k, 0.0) for k in names] + [own_ms / steps, float(eng.n_own)], dtype=torch.float64, device=dev)
+        allp = [torch.zeros_like(pt) for _ in range(world)]
+        dist.all_gather(allp, pt)
+        per_rank_ph = [{**{k: round(float(q[i]), 3) for i, k in enumerate(names)}, "ms_per_step": round(float(q[-2]), 3),
+                        "particles": int(q[-1])} for q in allp]
 
-    # per-kernel device times on this rank for the roofline (same timers as the single-GPU run)
-    eng.sim.enable_stage_timing(True)
-    kacc, reps = {}, 3
-    for _ in range(reps):
-        flush.zero_()
-        sim.step()
-        for k, v in eng.sim.kernel_ms().items():
-            kacc[k] = kacc.get(k, 0.0) + v / reps
-    eng.sim.enable_stage_timing(False)
-    n_own = eng.n_own
-    # where a step's device time goes on every rank (phase stamps on the stream), and who is slowest
-    phases = {}
-    for _ in range(reps):
-        flush.zero_()
-        for k, v in sim.profile_step().items():
-            phases[k] = phases.get(k, 0.0) + v / reps
-    names = ["raw_exchange", "keys_sort_layout", "count_allgather", "lambda", "delta_p", "update_velocity", "xsph", "halo"]
-    pt = torch.tensor([phases.get(k, 0.0) for k in names] + [sum(a.elapsed_time(b) for a, b in ev) / args.steps, float(eng.n_own)],
-                      dtype=torch.float64, device=dev)
-    allp = [torch.zeros_like(pt) for _ in range(world)]
-    dist.all_gather(allp, pt)
-    per_rank = [{**{k: round(float(q[i]), 3) for i, k in enumerate(names)}, "ms_per_step": round(float(q[-2]), 3),
-                 "particles": int(q[-1])} for q in allp]
-
-    # ---- end to end: every rank's state starts each step in pinned HOST memory and ends there ----------
-    e2e_steps = max(3, min(args.steps, 10))
-    cap = eng.capacity
-    hp = [torch.empty((cap, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
-    hi = torch.empty(cap, dtype=torch.int32).pin_memory()
-    n = eng.n_own
-    hp[0][:n].copy_(eng.pos[:n]); hp[1][:n].copy_(eng.vel[:n]); hi[:n].copy_(eng.iid[:n])
-    torch.cuda.synchronize()
-    dist.barrier()
-    up = down = 0
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.pos[:n].copy_(hp[0][:n], non_blocking=True); eng.vel[:n].copy_(hp[1][:n], non_blocking=True)
-        eng.iid[:n].copy_(hi[:n], non_blocking=True)
-        up += 28 * n
-        sim.step()
+        # ---- end to end: every rank's state starts each step in pinned HOST memory and ends there, the SAME number
+        # of steps as `value`. Uploads go ahead of the step on its stream; the final positions and iid are complete
+        # after the velocity update and come down on a copy stream while the XSPH sweep still runs (what
+        # pbf_step_host does on one GPU); the velocities follow the sweep.
+        cap = eng.capacity
+        hp = [torch.empty((cap, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        hi = torch.empty(cap, dtype=torch.int32).pin_memory()
         n = eng.n_own
-        hp[0][:n].copy_(eng.pos[:n], non_blocking=True); hp[1][:n].copy_(eng.vel[:n], non_blocking=True)
-        hi[:n].copy_(eng.iid[:n], non_blocking=True)
-        down += 28 * n
+        hp[0][:n].copy_(eng.pos[:n]); hp[1][:n].copy_(eng.vel[:n]); hi[:n].copy_(eng.iid[:n])
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        state = {"n": n}
+
+        def after_velocity():
+            m = int(eng.layout.own_count)
+            state["n"] = m
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                hp[0][:m].copy_(eng.npos[:m], non_blocking=True)
+
         torch.cuda.synchronize()
-    dist.barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s, float(up), float(down)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sim.finish()
-    stats = eng.sim.stats(eng.pos, eng.vel, eng.n_own)
+        dist.barrier()
+        up = down = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            n = state["n"]
+            eng.pos[:n].copy_(hp[0][:n], non_blocking=True); eng.vel[:n].copy_(hp[1][:n], non_blocking=True)
+            eng.iid[:n].copy_(hi[:n], non_blocking=True)
+            up += 28 * n
+            sim.step(after_velocity=after_velocity)
+            n = eng.n_own
+            hp[1][:n].copy_(eng.vel[:n], non_blocking=True)
+            hi[:n].copy_(eng.iid[:n], non_blocking=True)
+            down += 28 * n
+            torch.cuda.synchronize()
+        dist.barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s, float(up), float(down)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sim.finish()
+        stats = eng.sim.stats(eng.pos, eng.vel, eng.n_own)
+        dom = "lambda" if kacc["lambda"] >= kacc["delta_p"] else "delta_p"
+        achieved = ALG_BYTES[dom] * n_own / (kacc[dom] * 1e-3) / 1e9
+        step_gbs = ALG_BYTES_STEP * (value / world) / 1e9
+        extra["roofline"] = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                             "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": round(kacc[dom], 4), "algorithmic_bytes_per_particle": ALG_BYTES[dom],
+                             "particles_on_this_rank": n_own,
+                             "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved_per_gpu": round(step_gbs, 2),
+                                            "frac": round(step_gbs / peak, 5)},
+                             "note": "rank 0's kernels; the lambda / XSPH sweeps are L1-wavefront / issue bound, not HBM bound (DESIGN.md 5)"}
+        extra["e2e"] = {"value": round(n_total * steps / float(t[0]), 1), "unit": "particle-steps/s", "steps": steps,
+                        "h2d_bytes_per_step": int(float(t[1]) / steps), "d2h_bytes_per_step": int(float(t[2]) / steps),
+                        "api": "every rank uploads its slab's pos/vel/iid from pinned host memory, SlabSimulator.step, downloads the "
+                               "result (positions on a copy stream under the XSPH sweep, velocities + iid behind it); bytes are the "
+                               "largest rank's"}
+        extra["config"] = {"messages_per_step_rank0": round(msgs / steps, 1), "bytes_sent_per_step_rank0": int(sent / steps),
+                           "kernel_ms_rank0": {k: round(v, 4) for k, v in kacc.items()}, "phase_ms_per_rank": per_rank_ph,
+                           "ms_per_step_series_rank0": [round(x, 2) for x in series],
+                           "stats_rank0": {k: round(v, 6) for k, v in stats.items()},
+                           "parallelism": "x-slab decomposition over %d ranks (one scene): per step one exchange of the raw state of "
+                                          "%d planes per side, then (2*niter+1) ghost refreshes %s; ghost=%d margin=%d replan_every=%d"
+                                          % (world, ghost + margin,
+                                             "FUSED into the pass kernels (stores into the neighbour's ghost slots over NVLink peer memory "
+                                             "+ a flag handshake, no collective)" if sim.fused else "as NCCL send/recv of float4 ranges" +
+                                             (" [%s]" % sim.fused_note if sim.fused_note else ""),
+                                             ghost, margin, args.replan_every)}
+        extra["gpu_launches"] = int(launches)
+        extra["clocks"] = clocks
     torch.cuda.synchronize()
     dist.barrier()     # nobody frees arrays a neighbour may still be pushing ghost values into
     eng.close()
+    del eng, sim, flush
+    torch.cuda.empty_cache()
+    # ---- parity: ONE GPU, the same scene, the same number of steps --------------------------------------
+    if rank == 0 and not args.no_parity:
+        try:
+            q = ProductRun(pbf, torch, local, name, sc)
+            for _ in range(warmup + steps):
+                q.step()
+            single = q.digest()
+            q.close()
+            del q
+            torch.cuda.empty_cache()
+            res["parity"] = "bit_exact" if single == digest else "MISMATCH"
+            res["parity_how"] = ("digest of the %d ranks' owned particles after %d steps == digest of pbf_step on one GPU "
+                                 "after %d steps (order-independent 128-bit digest of iid, pos, vel bits)" % (world, warmup + steps, warmup + steps))
+        except Exception as ex:   # noqa: BLE001
+            res["parity"] = "unchecked: %r" % (ex,)
+    dist.barrier()
+    return res, extra
+
+
+def run_product_slab(args, rank, world, dist):
+    import torch
+    pbf = importlib.import_module("pbf-cuda_b200")   # raises if libpbf_b200.so is missing: no fallback
+    slab = importlib.import_module("pbf-cuda_b200.slab")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    head, extra = slab_leg(args, pbf, slab, torch, dist, rank, world, local, args.scene, args.scaling, args.steps, args.warmup, True)
+    legs = []
+    if not args.no_legs:
+        for name, scaling, steps, warmup, min_world in LEGS:
+            if world < min_world or (name == args.scene and scaling == args.scaling):
+                continue
+            try:
+                leg, _ = slab_leg(args, pbf, slab, torch, dist, rank, world, local, name, scaling, min(steps, args.steps), warmup, False)
+                if name == "dam_64m":
+                    leg["also"] = "identical to BASELINE config 5 WEAK at 8 GPUs: the 8 388 608-particle block per GPU (dam_8m) repeated 8 times along x"
+                legs.append(leg)
+            except SystemExit as ex:
+                legs.append({"scene": name, "scaling": scaling, "error": str(ex)})
     if rank != 0:
         return None
-    peak, peak_src = hbm_peak()
-    dom = "lambda" if kacc["lambda"] >= kacc["delta_p"] else "delta_p"
-    achieved = ALG_BYTES[dom] * n_own / (kacc[dom] * 1e-3) / 1e9
-    step_gbs = ALG_BYTES_STEP * (value / world) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
-                "kernel_ms": round(kacc[dom], 4), "algorithmic_bytes_per_particle": ALG_BYTES[dom],
-                "particles_on_this_rank": n_own,
-                "whole_step": {"algorithmic_bytes_per_particle_step": ALG_BYTES_STEP, "achieved_per_gpu": round(step_gbs, 2),
-                               "frac": round(step_gbs / peak, 5)},
-                "note": "rank 0's kernels; the lambda / XSPH sweeps are L1-wavefront / issue bound, not HBM bound (DESIGN.md 5)"}
-    e2e = {"value": round(n_total * e2e_steps / float(t[0]), 1), "unit": "particle-steps/s", "steps": e2e_steps,
-           "h2d_bytes_per_step": int(float(t[1]) / e2e_steps), "d2h_bytes_per_step": int(float(t[2]) / e2e_steps),
-           "api": "every rank uploads its slab's pos/vel/iid from pinned host memory, SlabSimulator.step, downloads "
-                  "the result; bytes are the largest rank's"}
-    return {"metric": "particle-steps/s", "value": round(value, 1), "unit": "particle-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.scene + (" x%d along x (weak)" % world if args.scaling == "weak" else ""), sc, n_total),
-                       "particles_total": n_total, "particles_per_gpu": {"min": n_min, "max": n_max},
-                       "parallelism": "x-slab decomposition over %d ranks (one scene): per step one NCCL send/recv of the raw state of "
-                                      "%d planes per side, then (2*niter+1) ghost refreshes %s; ghost=%d margin=%d replan_every=%d"
-                                      % (world, ghost + margin,
-                                         "FUSED into the pass kernels (stores into the neighbour's ghost slots over NVLink peer memory "
-                                         "+ a flag handshake, no collective)" if sim.fused else "as NCCL send/recv of float4 ranges" +
-                                         (" [%s]" % sim.fused_note if sim.fused_note else ""),
-                                         ghost, margin, args.replan_every),
-                       "slab_boundaries": [int(b) for b in sim.bounds],
-                       "messages_per_step_rank0": round(msgs / args.steps, 1), "bytes_sent_per_step_rank0": int(sent / args.steps),
-                       "l2": "flushed between timed steps (256 MB memset outside the event pairs)", "exact_pow": True,
-                       "kernel_ms_rank0": {k: round(v, 4) for k, v in kacc.items()},
-                       "phase_ms_per_rank": per_rank,
-                       "ms_per_step_series_rank0": [round(a.elapsed_time(b), 2) for a, b in ev],
-                       "stats_rank0": {k: round(v, 6) for k, v in stats.items()}},
-            "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "clocks": clocks}
+    cfg = {"workload": head["workload"], "particles_total": head["particles_total"], "particles_per_gpu": head["particles_per_gpu"],
+           "slab_boundaries": head["slab_boundaries"],
+           "l2": "flushed between timed steps (256 MB memset outside the event pairs)", "exact_pow": True}
+    cfg.update(extra["config"])
+    out = {"metric": "particle-steps/s", "value": head["value"], "unit": "particle-steps/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": cfg, "gpu_launches": extra["gpu_launches"], "e2e": extra["e2e"], "roofline": extra["roofline"],
+           "clocks": extra["clocks"], "digest": head["digest"], "parity": head.get("parity"), "parity_how": head.get("parity_how"),
+           "legs": legs}
+    return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full`, dam_1m at step ~100 — the state the
-# kernel timers above see (profiles/r01h_solver_ncu_summary.txt): the lambda pass writes the 8-byte neighbour
-# records (344 MB) the delta-p replay reads back (420 MB with its float4 gathers)
-TRAFFIC = {"lambda": 432.8e6, "delta_p": 453.8e6}
+# ncu --set full of the dominant kernels, dam_1m at step ~100 — the state the kernel timers above see
+# (profiles/r01h_solver_ncu_summary.txt): dram__bytes_read.sum + dram__bytes_write.sum per launch, issue slots busy,
+# L1 data-pipe wavefront rate, DRAM throughput. A separate run under the profiler: labelled as such in the line.
+NCU = {"source": "profiles/r01h_solver_ncu_summary.txt (ncu --set full, dam_1m, step 100)",
+       "lambda": {"traffic": 432.8e6, "issue": 0.67, "l1": 0.74, "dram": 0.12},
+       "delta_p": {"traffic": 453.8e6, "issue": 0.76, "l1": None, "dram": 0.27}}
 
 
-def cpu_baseline(args, n, sc, steps=None):
+def cpu_baseline(args, sc, n, steps=None):
     """The oracle port on the host cores: bounded sample = `steps` whole steps of the same workload."""
     import _oracle as O
     threads = os.cpu_count() or 1
-    pos, vel, iid = host_scene(args.scene, sc)
+    pos, vel, iid = host_scene(sc)
     npos, nvel = np.zeros_like(pos), np.zeros_like(vel)
     o = O.Oracle(O.default_params(), sc["ulim"], sc["llim"], n, threads=threads)
     if steps is None:
@@ -511,87 +717,122 @@ def cpu_baseline(args, n, sc, steps=None):
             "sample": "%d whole step(s) of the same workload from its initial state (%.1f s)" % (steps, dt)}
 
 
-def host_scene(name, sc):
-    import _oracle as O
-    if "blocks" in sc:
-        parts, off = [], 0
-        for origin, n3 in sc["blocks"]:
-            parts.append(O.scene_block(origin, n3, 0.05, 27, off))
-            off += int(np.prod(n3))
-        return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
-    pos, vel, iid, _, _ = O.scene_double_dam_reference()
-    return pos, vel, iid
+class ReferenceRun:
+    """One scene through the reference's own Simulator.cu (oracle/_ref/libpbf_ref.so) on cuda:0. The initial state
+    comes from the oracle's host generator; the product's library is not loaded."""
+
+    def __init__(self, S, torch, name, sc=None):
+        import _oracle as O
+        import _ref
+        self.S, self.torch = S, torch
+        sc = self.sc = sc or S.SCENES[name]
+        dev = torch.device("cuda", 0)
+        p, v, i = host_scene(sc)
+        self.n = len(i)
+        pos, vel = torch.from_numpy(p).to(dev), torch.from_numpy(v).to(dev)
+        self.iid = torch.from_numpy(i.view(np.int32)).to(dev)
+        self.bufs = [pos, torch.zeros_like(pos), vel, torch.zeros_like(vel)]
+        self.ref = _ref.RefSimulator(O.default_params(), sc.get("ulim_max", sc["ulim"]), sc["llim"], self.n)
+        self.ref.set_lim(sc["ulim"], sc["llim"])
+        self.frame = 0
+
+    def step(self):
+        lim = lim_at(self.S, self.sc, self.frame)
+        if lim is not None:
+            self.ref.set_lim(*lim)
+        b = self.bufs
+        self.ref.step(b[0], b[1], b[2], b[3], self.iid, self.n)
+        b[0], b[1] = b[1], b[0]
+        b[2], b[3] = b[3], b[2]
+        self.frame += 1
+
+    def digest(self):
+        return digest_numpy(self.bufs[0].cpu().numpy(), self.bufs[2].cpu().numpy(), self.iid.cpu().numpy())
+
+    def close(self):
+        self.ref.close()
+        self.bufs = self.iid = None
 
 
 def run_reference(args, rank, world):
-    """The reference arm: the reference's own Simulator.cu (headless, sm_100) on this scene; rank 0 only."""
+    """The reference arm: the reference's own Simulator.cu (headless, sm_100) on the same workloads; rank 0 only."""
     if rank != 0:
         return None
     import _ref
-    import _oracle as O
-    pbf_scenes = importlib.import_module("pbf-cuda_b200").SCENES   # scene table and generators only
-    sc = pbf_scenes[args.scene]
+    S = load_scenes()
+    sc = S.SCENES[args.scene]
     if not _ref.available():
-        n = len(host_scene(args.scene, sc)[2])
-        cb = cpu_baseline(args, n, sc, steps=max(1, min(args.steps, 3)))
+        n = S.scene_particles(sc)
+        cb = cpu_baseline(args, sc, n, steps=max(1, min(args.steps, 3)))
         return {"impl": "reference", "metric": "particle-steps/s", "value": cb["value"], "unit": "particle-steps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args.scene, sc, n), "note": "oracle/_ref/libpbf_ref.so absent: CPU oracle port timed"},
+                "config": {"workload": workload_name(S, args.scene, sc, n), "note": "oracle/_ref/libpbf_ref.so absent: CPU oracle port timed"},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     import torch
-    pbf = importlib.import_module("pbf-cuda_b200")
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     # N > 1: the product arm runs ONE scene over N GPUs (weak: the block repeated N times along x; strong: the
     # named scene); the single-GPU reference gets that same scene, whole, on one GPU
-    sc_n = slab_scene(pbf, args.scene, world, args.scaling) if (world > 1 and not args.replicas) else None
-    sc, n, pos, vel, iid = scene_state(pbf, torch, args.scene, dev, sc_n)   # same generator, same bits
-    npos, nvel = torch.zeros_like(pos), torch.zeros_like(vel)
-    ref = _ref.RefSimulator(O.default_params(), sc.get("ulim_max", sc["ulim"]), sc["llim"], n)
-    ref.set_lim(sc["ulim"], sc["llim"])
-    bufs = [pos, npos, vel, nvel]
-    frame = [0]
-
-    def one_step():
-        lim = lim_at(pbf, sc, frame[0])
-        if lim is not None:
-            ref.set_lim(*lim)
-        ref.step(bufs[0], bufs[1], bufs[2], bufs[3], iid, n)
-        bufs[0], bufs[1] = bufs[1], bufs[0]
-        bufs[2], bufs[3] = bufs[3], bufs[2]
-        frame[0] += 1
-
+    sc_n = slab_scene(S, args.scene, world, args.scaling) if (world > 1 and not args.replicas) else None
+    run = ReferenceRun(S, torch, args.scene, sc_n)
+    sc, n = run.sc, run.n
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(args.warmup):
-        one_step()
-    torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(0)
-    sampler.start()
-    for k in range(args.steps):
-        flush.zero_()
-        ev[k][0].record()
-        one_step()
-        ev[k][1].record()
-    torch.cuda.synchronize()
+    total_ms, _ = timed_window(torch, run.step, args.steps, args.warmup, flush, sampler.start)
     clocks = sampler.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
     value = n * args.steps / (total_ms * 1e-3)
-    return {"impl": "reference", "metric": "particle-steps/s", "value": round(value, 1), "unit": "particle-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
-            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.scene + (" x%d along x (weak)" % world if (sc_n is not None and args.scaling == "weak") else ""), sc, n),
-                       "note": "the reference's own Simulator.cu + Simulator_kernel.cuh compiled unchanged for sm_100 "
-                               "(oracle/_ref/libpbf_ref.so), Thrust sort and its cudaDeviceSynchronize fences kept, GL interop "
-                               "excluded; runs on one GPU (the reference is single-GPU, rank 0 only)",
-                       "l2": "flushed between timed steps"},
-            "cpu_baseline": {"value": round(value, 1), "unit": "particle-steps/s", "kind": "reference", "cores": 0,
-                             "sample": "all %d steps; the reference has no CPU implementation of this path — it ran its "
-                                       "CUDA path on cuda:0" % args.steps},
-            "e2e": {"value": round(value, 1), "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "clocks": clocks}
+    record = {"%s/%d/%d" % (args.scene, args.steps, args.warmup): {"value": round(value, 1), "digest": hexd(run.digest())}} if world == 1 else {}
+    run.close()
+    del run
+    torch.cuda.empty_cache()
+    out = {"impl": "reference", "metric": "particle-steps/s", "value": round(value, 1), "unit": "particle-steps/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
+           "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(S, args.scene + (" x%d along x (weak)" % world if (sc_n is not None and args.scaling == "weak") else ""), sc, n),
+                      "note": "the reference's own Simulator.cu + Simulator_kernel.cuh compiled unchanged for sm_100 "
+                              "(oracle/_ref/libpbf_ref.so), Thrust sort and its cudaDeviceSynchronize fences kept, GL interop "
+                              "excluded; runs on one GPU (the reference is single-GPU, rank 0 only); initial state from the "
+                              "oracle's host generator, libpbf_b200.so not loaded",
+                      "l2": "flushed between timed steps"},
+           "cpu_baseline": {"value": round(value, 1), "unit": "particle-steps/s", "kind": "reference", "cores": 0,
+                            "sample": "all %d steps; the reference has no CPU implementation of this path — it ran its "
+                                      "CUDA path on cuda:0" % args.steps},
+           "e2e": {"value": round(value, 1), "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "clocks": clocks}
+    # the other named sizes, the same windows as the product arm (N=1: `sizes`; N>1: the legs' scenes on ONE GPU)
+    if not args.no_sizes:
+        todo = [(nm, st, wu) for nm, st, wu in SIZES] if world == 1 else \
+               [(nm, min(st, 3) if nm == "dam_64m" else st, wu) for nm, _, st, wu, mw in LEGS if world >= mw]
+        entries = []
+        for name, steps, warmup in todo:
+            if world == 1 and name == args.scene and steps == args.steps:
+                continue
+            try:
+                q = ReferenceRun(S, torch, name)
+                ms, _ = timed_window(torch, q.step, steps, warmup, flush)
+                v = q.n * steps / (ms * 1e-3)
+                e = {"scene": name, "workload": workload_name(S, name, q.sc, q.n), "particles": q.n, "steps": steps,
+                     "warmup": warmup, "ms_per_step": round(ms / steps, 5), "value": round(v, 1), "unit": "particle-steps/s",
+                     "digest": hexd(q.digest())}
+                entries.append(e)
+                if world == 1:
+                    record["%s/%d/%d" % (name, steps, warmup)] = {"value": e["value"], "digest": e["digest"]}
+                q.close()
+                del q
+                torch.cuda.empty_cache()
+            except Exception as ex:   # noqa: BLE001
+                entries.append({"scene": name, "error": repr(ex)})
+        out["sizes" if world == 1 else "legs"] = entries
+    if record:
+        try:
+            os.makedirs(os.path.dirname(REF_FILE), exist_ok=True)
+            with open(REF_FILE, "w") as f:
+                json.dump(record, f)
+        except OSError:
+            pass
+    return out
 
 
 def main():
@@ -603,6 +844,9 @@ def main():
     ap.add_argument("--scene", default="dam_1m")
     ap.add_argument("--cpu-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sizes", action="store_true", help="N=1: skip the `sizes` entries (the other named scenes)")
+    ap.add_argument("--no-legs", action="store_true", help="N>1: skip the strong-scaling legs behind the headline")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the single-GPU digest comparison")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the scene's block repeated N times along x; strong = the named scene cut in N slabs")
     ap.add_argument("--replicas", action="store_true", help="N>1: N independent copies of the scene instead of one scene in slabs")

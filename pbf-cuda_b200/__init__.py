@@ -41,10 +41,12 @@ EXPORTS = (
     "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
     "pbf_slab_halo_sync", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
     "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count", "pbf_get_const_div_interval",
-    "pbf_get_fast_spiky", "pbf_get_trim_pow", "pbf_state_write", "pbf_state_read_info", "pbf_state_read", "pbf_checkpoint_save", "pbf_checkpoint_load",
+    "pbf_get_fast_spiky", "pbf_get_trim_pow", "pbf_set_option", "pbf_get_option", "pbf_state_digest_device",
+    "pbf_state_digest_host", "pbf_state_write", "pbf_state_read_info", "pbf_state_read", "pbf_checkpoint_save", "pbf_checkpoint_load",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
+OPT_TEAM = 0
 SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST, SLAB_FLAG_TIMEOUT = 1, 2, 4
 
 
@@ -118,6 +120,10 @@ _lib.pbf_set_option_exact_pow.argtypes = [_vp, C.c_int]
 _lib.pbf_get_grid_dim.argtypes = [_vp, C.POINTER(C.c_int32)]
 _lib.pbf_get_fast_spiky.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
 _lib.pbf_get_trim_pow.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+_lib.pbf_set_option.argtypes = [_vp, C.c_int, C.c_int]
+_lib.pbf_get_option.argtypes = [_vp, C.c_int, C.POINTER(C.c_int)]
+_lib.pbf_state_digest_device.argtypes = [C.c_int, _vp, _vp, _vp, _i64, _vp, C.POINTER(C.c_uint64)]
+_lib.pbf_state_digest_host.argtypes = [_vp, _vp, _vp, _i64, C.POINTER(C.c_uint64)]
 _lib.pbf_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.pbf_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64]
 _lib.pbf_stage_begin.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
@@ -238,6 +244,31 @@ def state_read(path):
     return info, pos, vel, iid
 
 
+def state_digest(pos, vel, iid, n=None, device=0, stream=None):
+    """Order-independent 128-bit digest (sum, xor) of a particle state (include/pbf.h pbf_state_digest_*): numpy
+    arrays -> the host routine, torch CUDA tensors / device pointers -> the kernel. Returns two Python ints."""
+    d = (C.c_uint64 * 2)()
+    if isinstance(iid, np.ndarray):
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = np.ascontiguousarray(vel, np.float32)
+        iid = np.ascontiguousarray(iid).view(np.uint32)
+        n = len(iid) if n is None else int(n)
+        _check(_lib.pbf_state_digest_host(pos.ctypes.data, vel.ctypes.data, iid.ctypes.data, n, d))
+    else:
+        n = int(iid.shape[0]) if n is None else int(n)
+        _check(_lib.pbf_state_digest_device(int(device), _ptr(pos), _ptr(vel), _ptr(iid), n, stream, d))
+    return int(d[0]), int(d[1])
+
+
+def combine_digests(digests):
+    """Digest of the union of disjoint particle sets (e.g. the slabs of G ranks)."""
+    s = x = 0
+    for a, b in digests:
+        s = (s + int(a)) & 0xFFFFFFFFFFFFFFFF
+        x ^= int(b)
+    return s, x
+
+
 def default_params():
     """Defaults the reference writes at FluidSystem.cpp:15-25."""
     p = GUIParams()
@@ -328,6 +359,14 @@ class Simulator:
         l = np.zeros(3, np.float32)
         _check(_lib.pbf_get_lim(self._h, u.ctypes.data_as(_f3), l.ctypes.data_as(_f3)))
         return u, l
+
+    def set_option(self, option, value):
+        _check(_lib.pbf_set_option(self._h, int(option), int(value)))
+
+    def get_option(self, option):
+        v = C.c_int(0)
+        _check(_lib.pbf_get_option(self._h, int(option), C.byref(v)))
+        return int(v.value)
 
     def set_exact_pow(self, on):
         _check(_lib.pbf_set_option_exact_pow(self._h, int(bool(on))))
@@ -646,28 +685,4 @@ def scene_block_slice_host(origin, n3, ix_begin, ix_end, spacing=0.05, seed=27, 
     return pos, vel, iid
 
 
-def wall_lim(ulim0, llim0, a_ulim, a_llim, w, frame, start_frame=0):
-    """Moving-wall schedule of FluidSystem::stepSimulate (FluidSystem.cpp:104-110):
-    float t = w*(frame-start); float phi = sin(t); lim = lim0 + A*phi (all float)."""
-    t = np.float32(np.float32(w) * np.float32(frame - start_frame))
-    phi = np.float32(np.sin(np.float64(t)))
-    u = np.asarray(ulim0, np.float32) + np.asarray(a_ulim, np.float32) * phi
-    l = np.asarray(llim0, np.float32) + np.asarray(a_llim, np.float32) * phi
-    return u.astype(np.float32), l.astype(np.float32)
-
-
-# The named benchmark scenes (BASELINE.md section 3 / SURVEY.md 8d).
-SCENES = {
-    "double_dam_32k": dict(ulim=(2.0, 2.0, 4.0), llim=(-2.0, -2.0, 0.0), n=32000),
-    # intermediate sizes (tuning of the small-scene kernels; same shape as dam_1m, scaled)
-    "dam_128k": dict(ulim=(8.0, 2.0, 4.8), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (64, 32, 64))]),
-    "dam_256k": dict(ulim=(8.0, 3.6, 4.8), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (64, 64, 64))]),
-    "dam_1m": dict(ulim=(16.0, 3.6, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (128, 64, 128))]),
-    "sweep_4m": dict(ulim=(19.2, 6.8, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (256, 128, 128))],
-                     wall=dict(a_ulim=(4.8, 0.0, 0.0), a_llim=(0.0, 0.0, 0.0), w=0.05), ulim_max=(24.0, 6.8, 9.6)),
-    "double_dam_16m": dict(ulim=(38.4, 38.4, 9.6), llim=(0.0, 0.0, 0.0),
-                           blocks=[((0.2, 25.4, 0.2), (256, 256, 128)), ((25.4, 0.2, 0.2), (256, 256, 128))]),
-    # per-GPU block of the 64M weak-scaling run (SURVEY.md 8d config 5 "weak": box x-extent 9.6 per GPU)
-    "dam_8m": dict(ulim=(9.6, 26.0, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (128, 512, 128))]),
-    "dam_64m": dict(ulim=(76.8, 26.0, 9.6), llim=(0.0, 0.0, 0.0), blocks=[((0.2, 0.2, 0.2), (1024, 512, 128))]),
-}
+from .scenes import SCENES, wall_lim, scene_dims, scene_particles  # noqa: E402,F401  (pure numpy: bench.py's reference arm loads that file alone)

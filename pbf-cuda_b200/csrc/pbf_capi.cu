@@ -61,6 +61,7 @@ struct pbf_sim {
     int64_t max_particles = 0;
     int64_t cell_capacity = 0;
     int exact_pow = 1;
+    SweepMode mode;   // run-time options of the neighbour sweeps (pbf_set_option)
 
     // scratch (device)
     uint32_t* keys = nullptr;
@@ -462,6 +463,8 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     // default: powf like the reference (bit-identical results); PBF_FAST_POW=1 opts into (w*w)^2
     const char* ep = getenv("PBF_FAST_POW");
     s->exact_pow = (ep && ep[0] == '1') ? 0 : 1;
+    // (environment variables only set the defaults of the handle's options, here; nothing reads them per launch)
+    if (const char* tm = getenv("PBF_TEAM")) s->mode.team = tm[0] == '1' ? 1 : tm[0] == '0' ? 0 : -1;
 
     const size_t n = (size_t)max_particles;
     s->sort_zero_capacity = sort_scratch_zero_bytes(max_particles, MAX_PASSES);
@@ -552,6 +555,23 @@ int pbf_get_params(const pbf_sim* s, pbf_params* out) {
     if (!s || !out) return fail(PBF_ERR_INVALID, "null argument");
     *out = s->p;
     return PBF_OK;
+}
+int pbf_set_option(pbf_sim* s, int option, int value) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    switch (option) {
+        case PBF_OPT_TEAM:
+            if (value < -1 || value > 1) return fail(PBF_ERR_INVALID, "PBF_OPT_TEAM takes -1, 0 or 1");
+            s->mode.team = value;
+            return PBF_OK;
+        default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
+    }
+}
+int pbf_get_option(const pbf_sim* s, int option, int* value) {
+    if (!s || !value) return fail(PBF_ERR_INVALID, "null argument");
+    switch (option) {
+        case PBF_OPT_TEAM: *value = s->mode.team; return PBF_OK;
+        default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
+    }
 }
 int pbf_set_option_exact_pow(pbf_sim* s, int on) {
     if (!s) return fail(PBF_ERR_INVALID, "null argument");
@@ -750,7 +770,7 @@ int pbf_stage_lambda(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_LAMBDA;
     return PBF_OK;
 }
@@ -760,7 +780,7 @@ int pbf_stage_delta_p(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->x[s->cur ^ 1], &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->mode, s->stream, &s->launches));
     s->pair_parity ^= 1;
     s->cur ^= 1;
     s->iters_done++;
@@ -791,7 +811,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
 
 int pbf_stage_correct_velocity(pbf_sim* s) {
     if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
-    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
 }
@@ -874,7 +894,7 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     for (int64_t k = 0; k < slices && n > 0; k++) {
         const int64_t a = n * k / slices, b = n * (k + 1) / slices;
         CUDA_TRY(launch_xsph(s->x[s->cur], s->cull, k == 0 ? s->n_local : 0, s->xl, s->cell_range, s->nvel + 3 * a,
-                             s->iid_sorted, s->iid + a, a, b - a, s->g, s->c, st, &s->launches));
+                             s->iid_sorted, s->iid + a, a, b - a, s->g, s->c, s->mode, st, &s->launches));
         CUDA_TRY(cudaEventRecord(s->host_ev, st));
         CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
         CUDA_TRY(cudaMemcpyAsync(nvel + 3 * a, s->h_nvel + 3 * a, (size_t)(b - a) * 12, cudaMemcpyDeviceToHost, s->host_copy));
@@ -1214,6 +1234,27 @@ int pbf_get_stats(pbf_sim* s, const float* npos, const float* nvel, int64_t n, p
     out->kinetic_energy = ke;
     out->max_speed = sqrt(v_max);
     out->mean_z = z_sum / (double)n;
+    return PBF_OK;
+}
+
+int pbf_state_digest_device(int device, const float* pos, const float* vel, const uint32_t* iid, int64_t n, void* stream,
+                            uint64_t digest[2]) {
+    if (!digest || n < 0) return fail(PBF_ERR_INVALID, "bad argument");
+    if (n > 0 && (!pos || !vel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned long long* dev = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dev, 16));
+    cudaError_t e = launch_digest(pos, vel, iid, n, dev, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(digest, dev, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(PBF_ERR_CUDA, "state digest: %s", cudaGetErrorString(e));
+    return PBF_OK;
+}
+int pbf_state_digest_host(const float* pos, const float* vel, const uint32_t* iid, int64_t n, uint64_t digest[2]) {
+    if (!digest || n < 0) return fail(PBF_ERR_INVALID, "bad argument");
+    if (n > 0 && (!pos || !vel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
+    digest_host(pos, vel, iid, n, digest);
     return PBF_OK;
 }
 

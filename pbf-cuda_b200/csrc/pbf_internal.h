@@ -155,6 +155,12 @@ cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* 
                            int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches);
 
+// Run-time options of the neighbour sweeps, owned by the handle (pbf_set_option): nothing on the launch path
+// reads the environment.
+struct SweepMode {
+    int team = -1;   // -1: by particle count (solver_common.cuh TEAM_MAX_PARTICLES); 0 / 1: thread / four-lane kernels
+};
+
 // solver passes (solver.cu)
 // Neighbour list the lambda pass saves for the delta-p pass of the same iteration (null = off).
 struct PairList {
@@ -172,10 +178,10 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
 // `n_slots` = every slot the handle stores (ghosts included): the sweeps' cull reads them all.
 cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
                           const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp,
-                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+                          const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
                            int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp, const GridConsts& g,
-                           const SolverConsts& c, cudaStream_t st, int64_t* launches);
+                           const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
                                    const SolverConsts& c, cudaStream_t st, int64_t* launches);
@@ -192,8 +198,8 @@ cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_rig
                              uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches);
 cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
-                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                        int64_t* launches);
+                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, const SweepMode& mode,
+                        cudaStream_t st, int64_t* launches);
 // slab.cu: first slot of every local plane in the sorted pairs (nxl + 1 entries, the last one =
 // number of particles inside the local plane range; the rest carry the discard key)
 cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,
@@ -228,6 +234,10 @@ cudaError_t launch_scene_block(const float origin[3], const int32_t n3[3], float
 void scene_block_host(const float origin[3], const int32_t n3[3], float spacing, uint32_t seed,
                       uint32_t first_iid, int32_t ix_begin, int32_t ix_end, float* pos, float* vel,
                       uint32_t* iid);
+// stats.cu: order-independent 128-bit digest of (iid, pos, vel) (include/pbf.h pbf_state_digest_device / _host)
+cudaError_t launch_digest(const float* pos, const float* vel, const uint32_t* iid, int64_t n, unsigned long long* out,
+                          cudaStream_t st);
+void digest_host(const float* pos, const float* vel, const uint32_t* iid, int64_t n, uint64_t out[2]);
 cudaError_t launch_stats(const float* rho, const float* npos, const float* nvel, int64_t n, float pho0,
                          double* partial, int nblocks, cudaStream_t st);
 

@@ -389,10 +389,9 @@ cudaError_t preload_solver() {
 static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 // Small scenes take the four-lanes-per-particle kernels of solver_team.cu (latency bound, not throughput bound).
-// PBF_TEAM=0 / 1 forces the choice (tests run the golden scenes through both, tuning experiments).
-static bool use_team(int64_t n) {
-    if (const char* e = getenv("PBF_TEAM")) return e[0] == '1';   // (read per launch: tests flip it inside one process)
-    return n < TEAM_MAX_PARTICLES;
+// The handle's PBF_OPT_TEAM forces the choice (tests run the golden scenes through both, tuning experiments).
+static bool use_team(const SweepMode& mode, int64_t n) {
+    return mode.team < 0 ? n < TEAM_MAX_PARTICLES : mode.team == 1;
 }
 
 // the cull's coordinate arrays must mirror `x`: nothing to do if the producer of `x` wrote them along
@@ -415,12 +414,12 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
 
 cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
                           const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp,
-                          const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+                          const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
     if (pe != cudaSuccess) return pe;
     const CullSoA soa = soa_of(cs);
-    if (use_team(n)) {
+    if (use_team(mode, n)) {
         launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, pl.js ? pl.ovf_flag + (parity & 1) : nullptr, hp, g, c, st);
         if (launches) (*launches)++;
         return cudaGetLastError();
@@ -441,7 +440,7 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
 // (`cs` holds the positions the lambda pass of this iteration packed: the same ones xl carries)
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
                            int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp, const GridConsts& g,
-                           const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+                           const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     const CullSoA soa = soa_of(cs);   // this iteration's coordinates: what the overflow kernel culls on
     const CullOut co = out_of(cs);    // the other set receives the coordinates of x_out
@@ -455,7 +454,7 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
 #define PBF_DP_LAUNCH(POW)                                                                                                    \
     do {                                                                                                                      \
         if (pl.js) {                                                                                                          \
-            if (use_team(n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c, POW, st);              \
+            if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c, POW, st);              \
             else delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c);    \
             delta_p_kernel<POW, true><<<nb_ovf, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n,    \
                                                                                   pl.cnt, f_read, f_clear, hp, g, c);          \
@@ -494,14 +493,14 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
 // n_slots > 0: refresh the cull's coordinate arrays first; 0: they are current (a further chunk of the same sweep)
 cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
-                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, cudaStream_t st,
-                        int64_t* launches) {
+                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, const SweepMode& mode,
+                        cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     if (n_slots > 0) {
         cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
         if (pe != cudaSuccess) return pe;
     }
-    if (use_team(n)) {
+    if (use_team(mode, n)) {
         launch_xsph_team(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c, st);
         if (launches) (*launches)++;
         return cudaGetLastError();

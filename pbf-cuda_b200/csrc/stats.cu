@@ -10,6 +10,21 @@ namespace pbf {
 
 constexpr int ST_THREADS = 256;
 
+// splitmix64's finaliser; particle_hash chains it over (iid, the six state words as three 64-bit words)
+__host__ __device__ inline uint64_t digest_mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline uint64_t particle_hash(uint32_t iid, uint32_t px, uint32_t py, uint32_t pz, uint32_t vx,
+                                                  uint32_t vy, uint32_t vz) {
+    uint64_t h = digest_mix64((uint64_t)iid);
+    h = digest_mix64(h ^ ((uint64_t)px | ((uint64_t)py << 32)));
+    h = digest_mix64(h ^ ((uint64_t)pz | ((uint64_t)vx << 32)));
+    return digest_mix64(h ^ ((uint64_t)vy | ((uint64_t)vz << 32)));
+}
+
 // partial[b*5 + k]: k = 0 sum|rho/rho0-1|, 1 max(rho/rho0-1), 2 sum 0.5|v|^2, 3 max |v|^2, 4 sum z
 __global__ void __launch_bounds__(ST_THREADS)
 stats_kernel(const float* __restrict__ rho, const float* __restrict__ npos, const float* __restrict__ nvel,
@@ -145,9 +160,59 @@ cudaError_t verify_pow4(float top, unsigned long long* mismatches, cudaStream_t 
     return e;
 }
 
+// ---- order-independent digest of a particle state (include/pbf.h pbf_state_digest_*) ---------------------
+// One 64-bit hash per particle over (iid, pos bits, vel bits); the digest is {sum, xor of a second mix} of the
+// hashes, both commutative: two states holding the same particles in ANY order (one GPU's cell-sorted order, the
+// concatenation of G slabs) have the same digest, and digests of disjoint parts combine by + and ^.
+__global__ void __launch_bounds__(256)
+digest_kernel(const float* __restrict__ pos, const float* __restrict__ vel, const uint32_t* __restrict__ iid, int64_t n,
+              unsigned long long* __restrict__ out) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(pos);
+    const uint32_t* v = reinterpret_cast<const uint32_t*>(vel);
+    unsigned long long sum = 0, x = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const uint64_t h = particle_hash(iid[i], p[3 * i], p[3 * i + 1], p[3 * i + 2], v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        sum += h;
+        x ^= digest_mix64(h);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        x ^= __shfl_xor_sync(0xffffffffu, x, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, sum);
+        atomicXor(out + 1, x);
+    }
+}
+
+cudaError_t launch_digest(const float* pos, const float* vel, const uint32_t* iid, int64_t n, unsigned long long* out,
+                          cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(out, 0, 16, st);
+    if (e != cudaSuccess || n <= 0) return e;
+    int64_t nb = (n + 255) / 256;
+    if (nb > 148 * 8) nb = 148 * 8;
+    digest_kernel<<<(unsigned)nb, 256, 0, st>>>(pos, vel, iid, n, out);
+    return cudaGetLastError();
+}
+
+void digest_host(const float* pos, const float* vel, const uint32_t* iid, int64_t n, uint64_t out[2]) {
+    uint64_t sum = 0, x = 0;
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t w[6];
+        memcpy(w, pos + 3 * i, 12);
+        memcpy(w + 3, vel + 3 * i, 12);
+        const uint64_t h = particle_hash(iid[i], w[0], w[1], w[2], w[3], w[4], w[5]);
+        sum += h;
+        x ^= digest_mix64(h);
+    }
+    out[0] = sum;
+    out[1] = x;
+}
+
 cudaError_t preload_stats() {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, const_div_check_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&a, digest_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, const_div_check_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spiky_check_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pow4_check_kernel);
     return e != cudaSuccess ? e : cudaFuncGetAttributes(&a, stats_kernel);

@@ -493,7 +493,10 @@ class SlabSimulator:
         if self._mark:
             self._mark(name)
 
-    def step(self):
+    def step(self, after_velocity=None):
+        """One step of this rank. after_velocity: optional callable run once the velocity update is enqueued —
+        the step's positions (engine.npos[:layout.own_count]) are final from that point of the stream on, so a
+        caller that wants them on the host can start the download under the XSPH sweep (bench.py's e2e leg)."""
         e, r, w = self.e, self.rank, self.world
         old = self.bounds
         new = old
@@ -539,6 +542,8 @@ class SlabSimulator:
             self._gather_counts()
         e.update_velocity()
         self._m("update_velocity")
+        if after_velocity is not None:
+            after_velocity()
         self._halo(HALO_VELOCITY)
         self._m("halo")
         e.xsph()

@@ -101,3 +101,43 @@ def test_emitter_source_schedule_on_host_buffers(pbf):
     small = pbf.EmitterSource((0, 0, 0), 4, 5, 0.05, (1, 0, 0), 1, 10 ** 6)
     assert [small.initialize(pos, vel, iid, 45)] + [small.update(pos, vel, iid, 45) for _ in range(3)] == [20, 40, 40, 40]
     assert src.reset(pos, vel, iid, cap) == 20
+
+
+def test_state_digest_is_order_independent_and_matches_the_numpy_restatement(pbf):
+    """pbf_state_digest_host (include/pbf.h): the same particles in any order give the same 128 bits, disjoint parts
+    combine by + and ^, one flipped bit changes it — and bench.py's numpy restatement (what the reference arm
+    uses, which must not load the product's library) computes the same value."""
+    import bench
+    rng = np.random.RandomState(5)
+    n = 4097
+    pos = rng.randn(n, 3).astype(np.float32)
+    vel = rng.randn(n, 3).astype(np.float32)
+    iid = rng.permutation(n).astype(np.uint32)
+    d = pbf.state_digest(pos, vel, iid)
+    assert d == bench.digest_numpy(pos, vel, iid)
+    p = rng.permutation(n)
+    assert pbf.state_digest(pos[p], vel[p], iid[p]) == d
+    parts = [pbf.state_digest(pos[a:b], vel[a:b], iid[a:b]) for a, b in ((0, 1000), (1000, 1001), (1001, n))]
+    assert pbf.combine_digests(parts) == d
+    q = pos.copy()
+    q.view(np.uint32)[17, 2] ^= 1
+    assert pbf.state_digest(q, vel, iid) != d
+    w = iid.copy()
+    w[[3, 4]] = w[[4, 3]]                      # two particles swap their ids: a different state
+    assert pbf.state_digest(pos, vel, w) != d
+    assert pbf.state_digest(pos[:0], vel[:0], iid[:0]) == (0, 0) == bench.digest_numpy(pos[:0], vel[:0], iid[:0])
+
+
+def test_scene_table_loads_without_the_library():
+    """bench.py's reference arm reads scenes.py by path, so that the arm that times the reference never maps
+    libpbf_b200.so; the table it sees is the package's."""
+    import importlib
+    import bench
+    S = bench.load_scenes()
+    pkg = importlib.import_module("pbf-cuda_b200")
+    assert S.SCENES == pkg.SCENES
+    assert S.scene_particles(S.SCENES["double_dam_16m"]) == 16777216 and S.scene_particles(S.SCENES["double_dam_32k"]) == 32000
+    assert S.scene_dims(S.SCENES["dam_64m"]) == [768, 260, 96]
+    u, l = S.wall_lim((19.2, 6.8, 9.6), (0, 0, 0), (4.8, 0, 0), (0, 0, 0), 0.05, 31)
+    u2, l2 = pkg.wall_lim((19.2, 6.8, 9.6), (0, 0, 0), (4.8, 0, 0), (0, 0, 0), 0.05, 31)
+    assert np.array_equal(u, u2) and np.array_equal(l, l2)

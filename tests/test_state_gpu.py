@@ -155,3 +155,66 @@ def test_emitter_source_grows_the_scene_and_matches_the_harness(pbf, torch, tmp_
     assert (g_pos >= np.asarray(llim, np.float32) + 1e-3 - 1e-6).all() and (g_pos <= np.asarray(ulim, np.float32) - 1e-3 + 1e-6).all()
     assert np.isfinite(g_vel).all() and g_pos[:, 0].max() > -1.0   # the jet travelled
     sim.close()
+
+
+def test_device_digest_equals_host_digest_and_ignores_the_order(pbf, torch):
+    """pbf_state_digest_device (the kernel bench.py's `parity` key uses on every rank) == pbf_state_digest_host on the
+    downloaded arrays; a step's cell-sorted output and the same particles shuffled have the same digest."""
+    pos, vel, iid, ulim, llim = pbf.scene_double_dam_reference()
+    n = len(iid)
+    dev = torch.device("cuda:0")
+    d = [torch.from_numpy(pos).to(dev), torch.zeros((n, 3), device=dev), torch.from_numpy(vel).to(dev), torch.zeros((n, 3), device=dev)]
+    d_iid = torch.from_numpy(iid.astype(np.int64)).to(dev).to(torch.int32)
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    for _ in range(3):
+        sim.step(d[0], d[1], d[2], d[3], d_iid, n)
+        d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+    torch.cuda.synchronize()
+    on_device = pbf.state_digest(d[0], d[2], d_iid, n)
+    on_host = pbf.state_digest(d[0].cpu().numpy(), d[2].cpu().numpy(), d_iid.cpu().numpy().view(np.uint32))
+    assert on_device == on_host and on_device != (0, 0)
+    perm = torch.randperm(n, device=dev)
+    assert pbf.state_digest(d[0][perm].contiguous(), d[2][perm].contiguous(), d_iid[perm].contiguous(), n) == on_device
+    assert pbf.state_digest(d[0], d[2], d_iid, 0) == (0, 0)
+    # digests of disjoint parts combine
+    parts = [pbf.state_digest(d[0][a:b], d[2][a:b], d_iid[a:b], b - a) for a, b in ((0, 12345), (12345, n))]
+    assert pbf.combine_digests(parts) == on_device
+    sim.close()
+
+
+def test_kernel_family_is_a_handle_option_not_an_environment_lookup(pbf, torch, monkeypatch):
+    """PBF_OPT_TEAM (include/pbf.h): the family of sweep kernels is a property of the handle — set at create from
+    PBF_TEAM, changed with pbf_set_option — and both families give the same bits; changing the environment after
+    create changes nothing."""
+    pos, vel, iid, ulim, llim = pbf.scene_double_dam_reference()
+    n = len(iid)
+    dev = torch.device("cuda:0")
+
+    def run(sim):
+        d = [torch.from_numpy(pos).to(dev), torch.zeros((n, 3), device=dev), torch.from_numpy(vel).to(dev), torch.zeros((n, 3), device=dev)]
+        d_iid = torch.from_numpy(iid.astype(np.int64)).to(dev).to(torch.int32)
+        for _ in range(2):
+            sim.step(d[0], d[1], d[2], d[3], d_iid, n)
+            d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+        torch.cuda.synchronize()
+        return pbf.state_digest(d[0], d[2], d_iid, n)
+
+    monkeypatch.delenv("PBF_TEAM", raising=False)
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+    assert sim.get_option(pbf.OPT_TEAM) == -1
+    auto = run(sim)
+    monkeypatch.setenv("PBF_TEAM", "0")            # after create: ignored
+    assert sim.get_option(pbf.OPT_TEAM) == -1
+    sim.set_option(pbf.OPT_TEAM, 0)
+    thread = run(sim)
+    sim.set_option(pbf.OPT_TEAM, 1)
+    team = run(sim)
+    assert auto == thread == team
+    with pytest.raises(pbf.PbfError):
+        sim.set_option(pbf.OPT_TEAM, 7)
+    with pytest.raises(pbf.PbfError):
+        sim.set_option(99, 0)
+    sim.close()
+    sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)   # PBF_TEAM=0 in the environment now: the default of a NEW handle
+    assert sim.get_option(pbf.OPT_TEAM) == 0
+    sim.close()
