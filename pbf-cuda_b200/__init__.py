@@ -46,7 +46,7 @@ EXPORTS = (
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
-OPT_TEAM = 0
+OPT_TEAM, OPT_REBIN = 0, 1
 SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST, SLAB_FLAG_TIMEOUT = 1, 2, 4
 
 

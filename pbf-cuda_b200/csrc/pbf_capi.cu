@@ -465,6 +465,7 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     s->exact_pow = (ep && ep[0] == '1') ? 0 : 1;
     // (environment variables only set the defaults of the handle's options, here; nothing reads them per launch)
     if (const char* tm = getenv("PBF_TEAM")) s->mode.team = tm[0] == '1' ? 1 : tm[0] == '0' ? 0 : -1;
+    if (const char* rb = getenv("PBF_REBIN")) s->mode.rebin = rb[0] == '1' ? 1 : 0;
 
     const size_t n = (size_t)max_particles;
     s->sort_zero_capacity = sort_scratch_zero_bytes(max_particles, MAX_PASSES);
@@ -563,6 +564,9 @@ int pbf_set_option(pbf_sim* s, int option, int value) {
             if (value < -1 || value > 1) return fail(PBF_ERR_INVALID, "PBF_OPT_TEAM takes -1, 0 or 1");
             s->mode.team = value;
             return PBF_OK;
+        case PBF_OPT_REBIN:
+            s->mode.rebin = value ? 1 : 0;
+            return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
     }
 }
@@ -570,6 +574,7 @@ int pbf_get_option(const pbf_sim* s, int option, int* value) {
     if (!s || !value) return fail(PBF_ERR_INVALID, "null argument");
     switch (option) {
         case PBF_OPT_TEAM: *value = s->mode.team; return PBF_OK;
+        case PBF_OPT_REBIN: *value = s->mode.rebin; return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
     }
 }
@@ -770,6 +775,7 @@ int pbf_stage_lambda(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
+    s->mode.moved = s->iters_done > 0;   // the first iteration runs on the positions the sort keyed on
     KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_LAMBDA;
     return PBF_OK;
@@ -811,6 +817,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
 
 int pbf_stage_correct_velocity(pbf_sim* s) {
     if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
+    s->mode.moved = s->iters_done > 0;
     KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
@@ -891,6 +898,7 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     const int64_t slices = n >= 4 * 131072 ? 4 : n >= 2 * 131072 ? 2 : 1;
     if (s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "step_host: velocity update missing");
     if ((rc = kernel_event(s, PBF_KERNEL_XSPH, 0))) return rc;
+    s->mode.moved = s->iters_done > 0;
     for (int64_t k = 0; k < slices && n > 0; k++) {
         const int64_t a = n * k / slices, b = n * (k + 1) / slices;
         CUDA_TRY(launch_xsph(s->x[s->cur], s->cull, k == 0 ? s->n_local : 0, s->xl, s->cell_range, s->nvel + 3 * a,

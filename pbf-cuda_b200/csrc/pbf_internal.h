@@ -159,6 +159,9 @@ cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* 
 // reads the environment.
 struct SweepMode {
     int team = -1;   // -1: by particle count (solver_common.cuh TEAM_MAX_PARTICLES); 0 / 1: thread / four-lane kernels
+    int rebin = 0;   // thread kernels: re-deal a block's particles by CURRENT home cell once the iterate has moved
+                     // (measured: no gain, DESIGN.md 3.7 — off by default, kept selectable for the A/B)
+    bool moved = false;   // set per launch by the stage functions: the iterate is not the one the sort keyed on
 };
 
 // solver passes (solver.cu)

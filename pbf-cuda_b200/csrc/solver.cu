@@ -18,7 +18,16 @@
 // neighbour list of the lambda pass handed to the delta-p pass of the same iteration.
 #include "solver_common.cuh"
 
+#ifndef PBF_CULL_IDX
+#define PBF_CULL_IDX 0
+#endif
+#ifndef PBF_CULL_UNROLL
+#define PBF_CULL_UNROLL 1
+#endif
+
 namespace pbf {
+
+constexpr int CULL_UNROLL = PBF_CULL_UNROLL;
 
 // Two-phase gather of one particle (one thread), the core of all three neighbour sweeps.
 //
@@ -105,16 +114,31 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             for (uint32_t b = start & ~3u; b < end; b += 32) {   // words start at multiples of four slots
                 const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
                 const uint32_t groups = (cnt + 3) >> 2;
+                uint32_t hits = 0;
+#if PBF_CULL_IDX
+                // one 32-bit group index against the three (uniform) array bases instead of three 64-bit pointers
+                // that are each advanced per trip: 6 integer instructions fewer per four candidates
+                const float4* const xs4 = reinterpret_cast<const float4*>(soa.xs);
+                const float4* const ys4 = reinterpret_cast<const float4*>(soa.ys);
+                const float4* const zs4 = reinterpret_cast<const float4*>(soa.zs);
+                const uint32_t q_end = (b >> 2) + groups;
+#pragma unroll 1
+                for (uint32_t q = b >> 2; q < q_end; q++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
+                    const float4 X = __ldg(xs4 + q), Y = __ldg(ys4 + q), Z = __ldg(zs4 + q);
+                    hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
+                    hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
+                }
+#else
                 const float4* xp = reinterpret_cast<const float4*>(soa.xs + b);
                 const float4* yp = reinterpret_cast<const float4*>(soa.ys + b);
                 const float4* zp = reinterpret_cast<const float4*>(soa.zs + b);
-                uint32_t hits = 0;
-#pragma unroll 1
+#pragma unroll CULL_UNROLL
                 for (uint32_t gi = 0; gi < groups; gi++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
                     const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
                     hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
                     hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
                 }
+#endif
                 // first slot to the top bit; drop the slots before the run and what was read past its end
                 hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt)) & (0xffffffffu >> (b < start ? start - b : 0));
                 *tail = make_uint2(b, hits);
@@ -138,6 +162,50 @@ pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restr
     zs[i] = q.z;
 }
 
+// ---- re-binning a block's particles by their CURRENT home cell -------------------------------------------
+// The reference re-derives a particle's home cell from the current iterate (Simulator_kernel.cuh:70,148,212), so
+// after the first Jacobi iteration 12-17 % of the particles per axis search the neighbourhood of a cell that is
+// not their sorted cell any more. Threads of a warp that handle consecutive sorted slots then walk DIFFERENT
+// runs, and one cull load of the warp touches ~8.5 cache lines instead of ~3 (ncu, profiles/r01h: the sweeps
+// sit on the L1 wavefront rate). Which thread computes which particle is free, though: every particle is still
+// accumulated by ONE thread in ascending slot order and written to its own slot, so no bit changes. The block
+// therefore re-deals its GATHER_THREADS particles to its threads in the order of (current home cell, slot):
+// lanes of a warp share home cells again, as in the first iteration.
+// Rank by counting over 32-bit words (cell key relative to the block's smallest, clamped to 25 bits | local
+// slot): ~290 instructions per thread against ~5000 of the sweep. A key beyond the clamp only groups worse.
+// Returns the local index (0..GATHER_THREADS-1) of the particle this thread takes; all threads of the block call.
+__device__ __forceinline__ uint32_t rebin_block(const float4* __restrict__ x, int64_t first, int64_t n, const GridConsts& g,
+                                                uint32_t* __restrict__ s_re /* GATHER_THREADS + 4 words */) {
+    const uint32_t tid = threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + tid;
+    uint32_t key = 0x3fffffffu;   // past the end of the range: sorts last
+    if (t < n) {
+        const float4 p = x[first + t];
+        const int3 cc = cell_of(p.x, p.y, p.z, g);
+        key = (uint32_t)(cc.x * g.dyz + cc.y * g.dim[2] + cc.z);
+    }
+    const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
+    if ((tid & 31u) == 0) s_re[GATHER_THREADS + (tid >> 5)] = wmin;
+    __syncthreads();
+    uint32_t kmin = s_re[GATHER_THREADS];
+#pragma unroll
+    for (int w = 1; w < GATHER_THREADS / 32; w++) kmin = min(kmin, s_re[GATHER_THREADS + w]);
+    const uint32_t v = (min(key - kmin, 0x1ffffffu) << 7) | tid;
+    s_re[tid] = v;
+    __syncthreads();
+    uint32_t rank = 0;
+    const uint4* s4 = reinterpret_cast<const uint4*>(s_re);
+#pragma unroll 8
+    for (int j = 0; j < GATHER_THREADS / 4; j++) {
+        const uint4 q = s4[j];
+        rank += (q.x < v) + (q.y < v) + (q.z < v) + (q.w < v);
+    }
+    __syncthreads();
+    s_re[rank] = tid;
+    __syncthreads();
+    return s_re[tid];
+}
+
 // ---- neighbour-list reuse between the two passes of one Jacobi iteration ------------------------
 // The lambda and delta-p passes of an iteration read the SAME positions (the reference runs
 // computeLambda and computetpos on the same dc_npos, Simulator.cu:222-245), so their in-range
@@ -152,7 +220,7 @@ pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restr
 // entries are contiguous 8-byte (slot, s) records. A particle with more than PAIR_CAP neighbours
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
 
-template <bool SAVE_PAIRS, bool FAST_SPIKY>
+template <bool SAVE_PAIRS, bool FAST_SPIKY, bool REBIN>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
@@ -160,7 +228,9 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
               const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
               const __grid_constant__ SolverConsts c) {
     extern __shared__ uint2 s_words[];
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
+    const uint32_t local = REBIN ? rebin_block(x, first, n, g, s_re) : threadIdx.x;   // which particle of the block
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + local;
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 p = x[i];
@@ -202,8 +272,8 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     xl[i] = out;
     halo_push(hp, t, out);
     rho_out[i] = rho;
-    if (SAVE_PAIRS) {
-        pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
+    if (SAVE_PAIRS) {   // the list lives in THIS THREAD's column (coalesced records); the word says whose it is
+        pair_cnt[(int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x] = pair_word(n_pairs, local);
         if (n_pairs > PAIR_CAP) *ovf_flag = 1u;   // (every writer stores the same value)
     }
 }
@@ -228,10 +298,12 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                       const uint2* __restrict__ pair_js,
                       const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
                       const __grid_constant__ SolverConsts c) {
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
-    if (t >= n) return;
-    const uint32_t cnt = pair_cnt[t];
-    if (cnt & PAIR_OVERFLOW) return;   // the gather kernel's particle
+    const int64_t col = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;   // list column; its word names the particle
+    if (col >= n) return;
+    const uint32_t cw = pair_cnt[col];
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + pair_local(cw);
+    if ((cw & PAIR_OVERFLOW) || t >= n) return;   // the gather kernel's particle / a column past the end
+    const uint32_t cnt = pair_count(cw);
     const int64_t i = first + t;
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
@@ -255,7 +327,7 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
     halo_push(hp, t, out);
 }
 
-template <int POW, bool ONLY_OVERFLOW>
+template <int POW, bool ONLY_OVERFLOW, bool REBIN>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restrict__ x_out, const CullOut co,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n,
@@ -263,15 +335,25 @@ delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restr
                uint32_t* __restrict__ flag_clear, const __grid_constant__ HaloPush hp,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint2 s_words[];
-    // ONLY_OVERFLOW: a small grid that strides over the particles — and leaves at once when no list of this
-    // iteration overflowed, which is the normal case (see PairList::ovf_flag)
+    __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
+    static_assert(!(ONLY_OVERFLOW && REBIN), "the overflow kernel strides over list columns; it does not re-bin");
+    // ONLY_OVERFLOW: a small grid that strides over the list columns — and leaves at once when no list of this
+    // iteration overflowed, which is the normal case (see PairList::ovf_flag). Otherwise one block of particles
+    // per CTA (the launcher sizes the grid), re-dealt by current home cell if REBIN (rebin_block).
     if (ONLY_OVERFLOW) {
         const bool any = *flag_read != 0;
         if (blockIdx.x == 0 && threadIdx.x == 0) *flag_clear = 0u;
         if (!any) return;
     }
-    for (int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x; t < n; t += (int64_t)gridDim.x * GATHER_THREADS) {
-        if (ONLY_OVERFLOW && !(pair_cnt[t] & PAIR_OVERFLOW)) continue;
+    const uint32_t local = REBIN ? rebin_block(xl, first, n, g, s_re) : threadIdx.x;
+    for (int64_t col = (int64_t)blockIdx.x * GATHER_THREADS + local; col < n; col += (int64_t)gridDim.x * GATHER_THREADS) {
+        int64_t t = col;
+        if (ONLY_OVERFLOW) {   // the column's word names the particle (the lambda pass may have re-binned its block)
+            const uint32_t cw = pair_cnt[col];
+            if (!(cw & PAIR_OVERFLOW)) continue;
+            t = col - (col % GATHER_THREADS) + pair_local(cw);
+            if (t >= n) continue;
+        }
         const int64_t i = first + t;
         const float4 p = xl[i];
         float ax = 0.f, ay = 0.f, az = 0.f;
@@ -289,6 +371,7 @@ delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restr
         x_out[i] = out;
         co.store(i, out);   // (reads of this iteration's coordinates go to `soa` = the OTHER set of arrays)
         halo_push(hp, t, out);
+        if (REBIN) break;   // (one block per CTA: the grid is not strided)
     }
 }
 
@@ -315,13 +398,16 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
     store_f3(npos_io, t, q.x, q.y, q.z);
 }
 
+template <bool REBIN>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
             const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     extern __shared__ uint2 s_words[];
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
+    const uint32_t local = REBIN ? rebin_block(x, first, n, g, s_re) : threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + local;
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 p = x[i];
@@ -362,24 +448,33 @@ neighbor_count_kernel(const float4* __restrict__ x, const CullSoA soa, const uin
 cudaError_t preload_solver() {
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<0>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<2>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<3>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, update_velocity_kernel);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, neighbor_count_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_kernel);
     if (e == cudaSuccess) e = preload_solver_team();
@@ -425,14 +520,21 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
         return cudaGetLastError();
     }
     const unsigned nb = nblocks(n, GATHER_THREADS);
-    if (!pl.js && !c.fast_spiky)
-        lambda_kernel<false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
-    else if (!pl.js)
-        lambda_kernel<false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
-    else if (!c.fast_spiky)
-        lambda_kernel<true, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, pl.ovf_flag + (parity & 1), hp, g, c);
-    else
-        lambda_kernel<true, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, pl.ovf_flag + (parity & 1), hp, g, c);
+    uint32_t* const flag = pl.js ? pl.ovf_flag + (parity & 1) : nullptr;
+#define PBF_LAMBDA_LAUNCH(SAVE, FAST)                                                                                          \
+    do {                                                                                                                       \
+        if (mode.rebin && mode.moved)                                                                                          \
+            lambda_kernel<SAVE, FAST, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n,       \
+                                                                                 pl.js, pl.cnt, flag, hp, g, c);             \
+        else                                                                                                                   \
+            lambda_kernel<SAVE, FAST, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n,      \
+                                                                                  pl.js, pl.cnt, flag, hp, g, c);            \
+    } while (0)
+    if (!pl.js && !c.fast_spiky) PBF_LAMBDA_LAUNCH(false, false);
+    else if (!pl.js) PBF_LAMBDA_LAUNCH(false, true);
+    else if (!c.fast_spiky) PBF_LAMBDA_LAUNCH(true, false);
+    else PBF_LAMBDA_LAUNCH(true, true);
+#undef PBF_LAMBDA_LAUNCH
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -456,12 +558,15 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
         if (pl.js) {                                                                                                          \
             if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c, POW, st);              \
             else delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c);    \
-            delta_p_kernel<POW, true><<<nb_ovf, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n,    \
-                                                                                  pl.cnt, f_read, f_clear, hp, g, c);          \
+            delta_p_kernel<POW, true, false><<<nb_ovf, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n, \
+                                                                                         pl.cnt, f_read, f_clear, hp, g, c);   \
             if (launches) (*launches)++;                                                                                      \
+        } else if (mode.rebin && mode.moved) {                                                                                \
+            delta_p_kernel<POW, false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n, \
+                                                                                     nullptr, nullptr, nullptr, hp, g, c);    \
         } else {                                                                                                              \
-            delta_p_kernel<POW, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n,       \
-                                                                               nullptr, nullptr, nullptr, hp, g, c);          \
+            delta_p_kernel<POW, false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n, \
+                                                                                      nullptr, nullptr, nullptr, hp, g, c);   \
         }                                                                                                                     \
     } while (0)
     if (pow_mode == 3) PBF_DP_LAUNCH(3);
@@ -505,7 +610,10 @@ cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const
         if (launches) (*launches)++;
         return cudaGetLastError();
     }
-    xsph_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+    if (mode.rebin && mode.moved)
+        xsph_kernel<true><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+    else
+        xsph_kernel<false><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -24,6 +24,15 @@ constexpr int PAIR_CAP = PBF_PAIR_CAP;  // neighbours per particle the lambda pa
 constexpr size_t LIST_SMEM = (size_t)WORD_CAP * GATHER_THREADS * sizeof(uint2);  // 15 KB per CTA
 
 constexpr uint32_t PAIR_OVERFLOW = 1u << 31;   // pair_cnt: more than PAIR_CAP neighbours, the delta-p pass gathers
+// pair_cnt word of list column c of a block: bits 0-7 the number of records, bits 8-14 WHICH of the block's
+// GATHER_THREADS particles the column belongs to (the re-binned sweeps deal a block's particles to its threads in the
+// order of their current home cell, see rebin_block in solver.cu; otherwise it is c itself), bit 31 PAIR_OVERFLOW.
+static_assert(PAIR_CAP < 256 && GATHER_THREADS <= 128, "pair_cnt word: 8 bits of count, 7 bits of particle");
+__device__ __forceinline__ uint32_t pair_word(int n_pairs, uint32_t local) {
+    return (n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW) | (local << 8);
+}
+__device__ __forceinline__ uint32_t pair_count(uint32_t w) { return w & 0xffu; }
+__device__ __forceinline__ uint32_t pair_local(uint32_t w) { return (w >> 8) & 0x7fu; }
 
 // Cull-side copy of the positions: three float arrays (structure of arrays), written along with the float4
 // iterate by the kernels that produce it (CullOut below; by pack_kernel in slab mode, where the neighbours

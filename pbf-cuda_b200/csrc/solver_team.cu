@@ -189,7 +189,7 @@ lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __re
     halo_push(hp, t, out);
     rho_out[i] = rho;
     if (SAVE_PAIRS) {
-        pair_cnt[t] = n_pairs <= PAIR_CAP ? (uint32_t)n_pairs : PAIR_OVERFLOW;
+        pair_cnt[t] = pair_word(n_pairs, (uint32_t)(t % GATHER_THREADS));
         if (n_pairs > PAIR_CAP) *ovf_flag = 1u;   // see PairList::ovf_flag
     }
 }
@@ -204,8 +204,9 @@ delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x
     const Team tm = team_of();
     const int64_t t = (int64_t)blockIdx.x * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;
-    const uint32_t cnt = pair_cnt[t];
-    if (cnt & PAIR_OVERFLOW) return;   // the gather kernel's particle
+    const uint32_t cw = pair_cnt[t];   // (the team kernels do not re-bin: column t % GATHER_THREADS is particle t)
+    if (cw & PAIR_OVERFLOW) return;    // the gather kernel's particle
+    const uint32_t cnt = pair_count(cw);
     const int64_t i = first + t;
     const float4 p = xl[i];
     const size_t pair0 = (size_t)(t / GATHER_THREADS) * PAIR_CAP * GATHER_THREADS + (size_t)(t % GATHER_THREADS);

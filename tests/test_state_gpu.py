@@ -218,3 +218,39 @@ def test_kernel_family_is_a_handle_option_not_an_environment_lookup(pbf, torch, 
     sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)   # PBF_TEAM=0 in the environment now: the default of a NEW handle
     assert sim.get_option(pbf.OPT_TEAM) == 0
     sim.close()
+
+
+def test_rebinned_sweeps_give_the_same_bits(pbf, torch):
+    """PBF_OPT_REBIN: which thread of a block computes which particle (consecutive slots, or the block's particles
+    re-dealt in the order of their current home cell) must not change a bit — on a scene large enough for the
+    thread-per-particle kernels, with a ragged last block, through the neighbour list and without it."""
+    dev = torch.device("cuda:0")
+    n3 = (48, 40, 37)                                   # 71 040 particles: 555 blocks of 128
+    n = n3[0] * n3[1] * n3[2]
+    ulim, llim = (4.0, 3.0, 4.0), (0.0, 0.0, 0.0)
+
+    def run(rebin, steps=6):
+        pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        vel = torch.empty_like(pos)
+        iid = torch.empty(n, dtype=torch.int32, device=dev)
+        pbf.scene_block_device((0.2, 0.2, 0.2), n3, pos, vel, iid)
+        d = [pos, torch.zeros_like(pos), vel, torch.zeros_like(vel)]
+        sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+        sim.set_option(pbf.OPT_TEAM, 0)
+        sim.set_option(pbf.OPT_REBIN, rebin)
+        assert sim.get_option(pbf.OPT_REBIN) == rebin
+        for _ in range(steps):
+            sim.step(d[0], d[1], d[2], d[3], iid, n)
+            d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+        torch.cuda.synchronize()
+        out = pbf.state_digest(d[0], d[2], iid, n)
+        sim.close()
+        return out
+
+    plain = run(0)
+    assert run(1) == plain
+    os.environ["PBF_NO_PAIR_REUSE"] = "1"               # (read at create): the full-gather delta-p kernels
+    try:
+        assert run(1) == plain and run(0) == plain
+    finally:
+        del os.environ["PBF_NO_PAIR_REUSE"]
