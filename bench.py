@@ -270,6 +270,9 @@ def run_product(args, rank, world, dist):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # a stream of its own (torch's default is the legacy stream 0, which cannot be captured into a CUDA graph:
+    # pbf_step replays small scenes from a graph, include/pbf.h PBF_OPT_GRAPH); events, flushes and steps all go here
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     run = ProductRun(pbf, torch, local, args.scene)
     sc, n, sim = run.sc, run.n, run.sim
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -662,6 +665,7 @@ def run_product_slab(args, rank, world, dist):
     slab = importlib.import_module("pbf-cuda_b200.slab")
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    torch.cuda.set_stream(torch.cuda.Stream(device=torch.device("cuda", local)))
     head, extra = slab_leg(args, pbf, slab, torch, dist, rank, world, local, args.scene, args.scaling, args.steps, args.warmup, True)
     legs = []
     if not args.no_legs:

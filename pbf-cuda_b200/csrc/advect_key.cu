@@ -7,13 +7,14 @@
 // from pos/vel with the same two fma (bit-identical), which saves 24 B/particle of HBM writes and
 // 24 B/particle of reads.
 //
-// HBM traffic: R 24 B (pos, vel) + W 4 B (key) per particle.
+// HBM traffic: R 24 B (pos, vel) + W 4 B (key) per particle, + W 8 B per cell (the cell table is emptied here).
 //
 // Slab mode (multi-GPU, slab.cu): the caller's arrays hold [own | from left | from right]; keys are
 // written in the sort's logical order [from left | own | from right] (SlabInput), particles that
 // land outside the planes this rank stores get the discard key (one past the last local cell, so
 // the sort parks them behind everything else), and an own particle that a neighbour rank needed
 // but was not in the range sent to it raises PBF_SLAB_FLAG_MIGRATION.
+#include "launch.cuh"
 #include "pbf_math.cuh"
 
 namespace pbf {
@@ -22,14 +23,20 @@ constexpr int AK_THREADS = 256;
 
 __global__ void __launch_bounds__(AK_THREADS)
 advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
-                  uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, int64_t n, int npass,
+                  uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, uint4* __restrict__ cell_clear,
+                  int64_t n, int npass,
                   const __grid_constant__ SlabInput si, const __grid_constant__ GridConsts g,
                   const __grid_constant__ SolverConsts c) {
+    pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
     for (int k = threadIdx.x; k < npass * RADIX; k += AK_THREADS) s_hist[k] = 0;
     __syncthreads();
 
     const int64_t i = (int64_t)blockIdx.x * AK_THREADS + threadIdx.x;
+    // the cell table the reorder pass fills next is emptied here (the reference's two cudaMemset, Simulator.cu:
+    // 201-203): its last reader was the previous step's XSPH sweep. Two cells per 16-byte store.
+    if (cell_clear)
+        for (int64_t k = i; k < (int64_t)(g.ncell + 1) / 2; k += (int64_t)gridDim.x * AK_THREADS) cell_clear[k] = make_uint4(0u, 0u, 0u, 0u);
     const bool valid = i < n;
     uint32_t key = 0;
     if (valid) {
@@ -69,12 +76,12 @@ cudaError_t preload_advect_key() {
     return e;
 }
 
-cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist,
+cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist, uint2* cell_clear,
                               int64_t n, int npass, const SlabInput& si, const GridConsts& g,
                               const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     unsigned blocks = (unsigned)((n + AK_THREADS - 1) / AK_THREADS);
-    advect_key_kernel<<<blocks, AK_THREADS, 0, st>>>(pos, vel, keys, hist, n, npass, si, g, c);
+    PBF_LAUNCH((advect_key_kernel), blocks, AK_THREADS, 0, st, pos, vel, keys, hist, reinterpret_cast<uint4*>(cell_clear), n, npass, si, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -14,9 +14,14 @@
 
 #include <new>
 
+#include "launch.cuh"
 #include "pbf_internal.h"
 
 using namespace pbf;
+
+namespace pbf {
+thread_local bool tl_pdl = true;   // launch.cuh: set from the handle's PBF_OPT_PDL by every stage function
+}
 
 namespace {
 
@@ -52,6 +57,25 @@ __global__ void extract_words_kernel(const uint32_t* __restrict__ src, int strid
 
 enum Stage { ST_IDLE = 0, ST_BOUND, ST_ADVECTED, ST_GRID, ST_LAMBDA, ST_DENSITY, ST_VELOCITY, ST_XSPH };
 
+constexpr int GRAPH_SLOTS = 4;
+constexpr int64_t GRAPH_AUTO_MAX = 256 * 1024;   // PBF_OPT_GRAPH = -1: graphs below this many particles
+
+// what a step's launches depend on (key) and what the stage functions leave in the handle (post)
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t used = 0;
+    const void* ptr[5] = {};
+    int64_t n = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t consts_hash = 0;
+    int niter = 0, team = 0, rebin = 0, pdl = 0;
+    int64_t launches = 0;
+    // post-step handle state
+    int sorted_buf = 0, cur = 0, iters_done = 0, cull_cur = 0;
+    const float4* cull_holds = nullptr;
+    float4* v4 = nullptr;
+};
+
 }  // namespace
 
 struct pbf_sim {
@@ -65,16 +89,21 @@ struct pbf_sim {
 
     // scratch (device)
     uint32_t* keys = nullptr;
-    uint32_t* sort_zero = nullptr;  // [hist | tile counters | tile descriptors], zeroed per step
+    // [hist | tile counters | tile descriptors] of the sort. Invariant: all zero whenever no sort is in flight —
+    // zeroed at create, and whoever sorts cleans up behind itself (the step: inside the reorder kernel)
+    uint32_t* sort_zero = nullptr;
     size_t sort_zero_capacity = 0;
+    bool sort_dirty = false;        // advect_key ran, the cleaning reorder has not yet (a step abandoned half-way)
     KeyIdx* pairs[2] = {nullptr, nullptr};
     float4* x[2] = {nullptr, nullptr};
-    float4* xl = nullptr;   // (x, y, z, lambda); reused as (vx, vy, vz, rho) after the last delta-p pass
+    float4* xl = nullptr;   // (x, y, z, lambda); reused as (vx, vy, vz, rho) by a separate velocity update
+    float4* v4 = nullptr;   // where (vx, vy, vz, rho) of the step in flight is: xl, or — when the velocity update rode
+                            // along with the last delta-p pass — the iterate buffer that pass no longer read
+    bool fuse_velocity = false;   // set by pbf_step for its last Jacobi iteration
     float* rho = nullptr;
     uint32_t* iid_sorted = nullptr;
     uint2* cell_range = nullptr;
     PairList pairs_list;            // lambda -> delta-p neighbour list (null when disabled / too large)
-    int pair_parity = 0;            // parity of the Jacobi iteration count since create (PairList::ovf_flag)
     CullScratch cull;               // coordinate arrays of the sweeps' cull (solver.cu pack_kernel)
     uint32_t* count_scratch = nullptr;
     uint32_t* read_scratch = nullptr;
@@ -149,6 +178,14 @@ struct pbf_sim {
     float pow4_top = 0.f;
     int pow4_ok = 0;
     unsigned long long pow4_mismatches = 0;
+
+    // pbf_step as a CUDA graph (PBF_OPT_GRAPH): a few instantiated graphs keyed by everything a step's launches
+    // depend on — the caller's pointers (two keys under the caller's ping-pong), n, the stream, the constants
+    StepGraph graphs[GRAPH_SLOTS];
+    uint64_t graph_clock = 0;
+    int graph_misses = 0;      // consecutive steps that had to capture
+    int graph_holdoff = 0;     // steps to run without graphs after the key kept changing (a moving wall)
+    bool graph_broken = false; // capture failed once on this handle: plain launches from then on
 
     int64_t launches = 0;
     bool timing = false;
@@ -311,9 +348,11 @@ int refresh_consts(pbf_sim* s) {
 }
 
 void free_all(pbf_sim* s) {
+    for (auto& gq : s->graphs)
+        if (gq.exec) { cudaGraphExecDestroy(gq.exec); gq.exec = nullptr; }
     cudaFree(s->keys); cudaFree(s->sort_zero); cudaFree(s->pairs[0]); cudaFree(s->pairs[1]);
     cudaFree(s->x[0]); cudaFree(s->x[1]); cudaFree(s->xl); cudaFree(s->rho); cudaFree(s->iid_sorted);
-    cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt); cudaFree(s->pairs_list.ovf_flag);
+    cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt);
     for (int k = 0; k < 2; k++) { cudaFree(s->cull.xs[k]); cudaFree(s->cull.ys[k]); cudaFree(s->cull.zs[k]); }
     cudaFree(s->cell_range); cudaFree(s->count_scratch); cudaFree(s->read_scratch); cudaFree(s->stats_partial);
     cudaFree(s->h_pos); cudaFree(s->h_npos); cudaFree(s->h_vel); cudaFree(s->h_nvel); cudaFree(s->h_iid);
@@ -466,13 +505,16 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     // (environment variables only set the defaults of the handle's options, here; nothing reads them per launch)
     if (const char* tm = getenv("PBF_TEAM")) s->mode.team = tm[0] == '1' ? 1 : tm[0] == '0' ? 0 : -1;
     if (const char* rb = getenv("PBF_REBIN")) s->mode.rebin = rb[0] == '1' ? 1 : 0;
+    if (const char* pd = getenv("PBF_PDL")) s->mode.pdl = pd[0] == '0' ? 0 : 1;
+    if (const char* gr = getenv("PBF_GRAPH")) s->mode.graph = gr[0] == '1' ? 1 : gr[0] == '0' ? 0 : -1;
 
     const size_t n = (size_t)max_particles;
     s->sort_zero_capacity = sort_scratch_zero_bytes(max_particles, MAX_PASSES);
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&s->keys, n * 4);
-    A((void**)&s->sort_zero, s->sort_zero_capacity);
+    A((void**)&s->sort_zero, s->sort_zero_capacity + 16);
+    if (e == cudaSuccess) e = cudaMemset(s->sort_zero, 0, s->sort_zero_capacity + 16);
     A((void**)&s->pairs[0], n * sizeof(KeyIdx));
     A((void**)&s->pairs[1], n * sizeof(KeyIdx));
     // (+8: the cull of the neighbour sweeps reads runs in groups of four, up to 3 slots past their end)
@@ -491,7 +533,7 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     }
     A((void**)&s->rho, n * 4);
     A((void**)&s->iid_sorted, n * 4);
-    A((void**)&s->cell_range, (size_t)cap * sizeof(uint2));
+    A((void**)&s->cell_range, (size_t)(cap + 1) * sizeof(uint2));   // (+1: emptied two cells per store)
     A((void**)&s->stats_partial, 1024 * 5 * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->stats_host, 1024 * 5 * sizeof(double));
     // slab mode: plane table (every plane the box can have, x2 for a moving wall) + flag word
@@ -521,10 +563,8 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
         if (!(np && np[0] == '1') && need <= free_b / 10 * 4) {
             cudaError_t pe = cudaMalloc((void**)&s->pairs_list.js, jb);
             if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.cnt, cb);
-            if (pe == cudaSuccess) pe = cudaMalloc((void**)&s->pairs_list.ovf_flag, 2 * sizeof(uint32_t));
-            if (pe == cudaSuccess) pe = cudaMemset(s->pairs_list.ovf_flag, 0, 2 * sizeof(uint32_t));
             if (pe != cudaSuccess) {
-                cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt); cudaFree(s->pairs_list.ovf_flag);
+                cudaFree(s->pairs_list.js); cudaFree(s->pairs_list.cnt);
                 s->pairs_list = PairList();
                 cudaGetLastError();
             }
@@ -567,6 +607,14 @@ int pbf_set_option(pbf_sim* s, int option, int value) {
         case PBF_OPT_REBIN:
             s->mode.rebin = value ? 1 : 0;
             return PBF_OK;
+        case PBF_OPT_PDL:
+            s->mode.pdl = value ? 1 : 0;
+            return PBF_OK;
+        case PBF_OPT_GRAPH:
+            if (value < -1 || value > 1) return fail(PBF_ERR_INVALID, "PBF_OPT_GRAPH takes -1, 0 or 1");
+            s->mode.graph = value;
+            s->graph_holdoff = s->graph_misses = 0;
+            return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
     }
 }
@@ -575,6 +623,8 @@ int pbf_get_option(const pbf_sim* s, int option, int* value) {
     switch (option) {
         case PBF_OPT_TEAM: *value = s->mode.team; return PBF_OK;
         case PBF_OPT_REBIN: *value = s->mode.rebin; return PBF_OK;
+        case PBF_OPT_PDL: *value = s->mode.pdl; return PBF_OK;
+        case PBF_OPT_GRAPH: *value = s->mode.graph; return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
     }
 }
@@ -624,6 +674,9 @@ int pbf_get_grid_dim(const pbf_sim* s, int32_t dim[3]) {
 int64_t pbf_launch_count(const pbf_sim* s) { return s ? s->launches : 0; }
 
 /* ---- stages ------------------------------------------------------------------------------- */
+
+// (every stage function: the launchers read the thread-local PDL switch, and stages may be called from any thread)
+#define STAGE_ENTER(s) do { if (s) tl_pdl = (s)->mode.pdl != 0; } while (0)
 
 static int stage_event(pbf_sim* s, int k) {
     if (s->timing) CUDA_TRY(cudaEventRecord(s->ev[k], s->stream));
@@ -712,6 +765,7 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
     if (n < 0 || n > s->max_particles) return fail(PBF_ERR_CAPACITY, "n=%lld exceeds max_particles=%lld", (long long)n, (long long)s->max_particles);
     if (n > 0 && (!pos || !npos || !vel || !nvel || !iid)) return fail(PBF_ERR_INVALID, "null particle buffer");
     CUDA_TRY(cudaSetDevice(s->device));
+    tl_pdl = s->mode.pdl != 0;
     s->pos = pos; s->npos = npos; s->vel = vel; s->nvel = nvel; s->iid = iid; s->n = n;
     s->stream = (cudaStream_t)stream;
     s->reorder_wait = nullptr;
@@ -732,18 +786,22 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
 }
 
 int pbf_stage_advect(pbf_sim* s) {
+    STAGE_ENTER(s);
     if (!s || s->stage != ST_BOUND) return fail(PBF_ERR_STATE, "advect: call pbf_stage_begin first");
     int rc = stage_event(s, 0);
     if (rc) return rc;
-    const size_t zero_bytes = sort_scratch_zero_bytes(s->n, s->npass);
-    CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, zero_bytes, s->stream));
-    s->launches++;
-    KTIMED(PBF_KERNEL_ADVECT_KEY, launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->si, s->g, s->c, s->stream, &s->launches));
+    if (s->sort_dirty) {   // the previous step never reached its reorder pass: restore the invariant
+        CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, s->sort_zero_capacity, s->stream));
+        s->launches++;
+    }
+    s->sort_dirty = s->n > 0;
+    KTIMED(PBF_KERNEL_ADVECT_KEY, launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->cell_range, s->n, s->npass, s->si, s->g, s->c, s->stream, &s->launches));
     s->stage = ST_ADVECTED;
     return stage_event(s, 1);
 }
 
 int pbf_stage_build_grid(pbf_sim* s) {
+    STAGE_ENTER(s);
     if (!s || s->stage != ST_ADVECTED) return fail(PBF_ERR_STATE, "build_grid: advect first");
     SortScratch sc;
     sc.hist = s->sort_zero;
@@ -762,7 +820,8 @@ int pbf_stage_build_grid(pbf_sim* s) {
         s->reorder_wait = nullptr;
     }
     KTIMED(PBF_KERNEL_REORDER, launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->cull, s->npos, s->iid_sorted,
-                                              s->cell_range, s->n_local, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
+                                              s->cell_range, s->sort_zero, sort_scratch_zero_bytes(s->n, s->npass), s->n_local, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
+    s->sort_dirty = false;   // (the reorder kernel left the sort's scratch zeroed)
     s->cur = 0;
     s->pos0_in_npos = true;
     s->stage = ST_GRID;
@@ -770,27 +829,41 @@ int pbf_stage_build_grid(pbf_sim* s) {
 }
 
 int pbf_stage_lambda(pbf_sim* s) {
+    STAGE_ENTER(s);
     if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "lambda: build_grid first");
     // (each iteration overwrites the slot: the timers report the LAST iteration of the step)
     HaloPush hp;
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
     s->mode.moved = s->iters_done > 0;   // the first iteration runs on the positions the sort keyed on
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->mode, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_LAMBDA;
     return PBF_OK;
 }
 
 int pbf_stage_delta_p(pbf_sim* s) {
+    STAGE_ENTER(s);
     if (!s || s->stage != ST_LAMBDA) return fail(PBF_ERR_STATE, "delta_p: lambda first");
     HaloPush hp;
     int prc = make_push(s, s->x[s->cur ^ 1], &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, s->pair_parity, hp, s->g, s->c, s->mode, s->stream, &s->launches));
-    s->pair_parity ^= 1;
+    // pbf_step's last iteration on a single GPU: the velocity update rides along (VelTail, pbf_internal.h); the
+    // velocities go to the iterate buffer this pass does not read any more (it works from xl)
+    VelTail vt;
+    const bool fused = s->fuse_velocity && !s->slab_on && !s->timing;
+    if (fused) {
+        vt.rho = s->rho; vt.pos_out = s->pos; vt.npos_io = s->npos; vt.vel_out = s->vel; vt.v4 = s->x[s->cur];
+        vt.inv_dt = s->c.inv_dt;
+    }
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, vt, s->g, s->c, s->mode, s->stream, &s->launches));
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;
+    if (fused) {   // what pbf_stage_update_velocity leaves behind
+        s->v4 = s->x[s->cur ^ 1];
+        s->pos0_in_npos = false;
+        s->stage = ST_VELOCITY;
+    }
     return PBF_OK;
 }
 
@@ -802,6 +875,7 @@ int pbf_stage_correct_density(pbf_sim* s) {
 }
 
 int pbf_stage_update_velocity(pbf_sim* s) {
+    STAGE_ENTER(s);
     if (!s || (s->stage != ST_GRID && s->stage != ST_DENSITY)) return fail(PBF_ERR_STATE, "update_velocity: build_grid first");
     int rc = stage_event(s, 3);
     if (rc) return rc;
@@ -810,20 +884,23 @@ int pbf_stage_update_velocity(pbf_sim* s) {
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
     KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, hp, s->c, s->stream, &s->launches));
+    s->v4 = s->xl;
     s->pos0_in_npos = false;
     s->stage = ST_VELOCITY;
     return stage_event(s, 4);
 }
 
 int pbf_stage_correct_velocity(pbf_sim* s) {
+    STAGE_ENTER(s);
     if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
     s->mode.moved = s->iters_done > 0;
-    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->xl, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->mode, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->v4, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
 }
 
 int pbf_stage_end(pbf_sim* s) {
+    STAGE_ENTER(s);
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
     s->stage = ST_IDLE;
     // fused mode: tell the neighbours that this step's state is complete — they pull from it next step
@@ -835,16 +912,116 @@ int pbf_stage_end(pbf_sim* s) {
     return PBF_OK;
 }
 
-int pbf_step(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
+static int step_direct(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
     int rc = pbf_stage_begin(s, pos, npos, vel, nvel, iid, n, stream);
     if (rc) return rc;
     if ((rc = pbf_stage_advect(s))) return rc;
     if ((rc = pbf_stage_build_grid(s))) return rc;
-    for (int i = 0; i < s->p.niter; i++)
-        if ((rc = pbf_stage_correct_density(s))) return rc;
-    if ((rc = pbf_stage_update_velocity(s))) return rc;
+    for (int i = 0; i < s->p.niter; i++) {
+        s->fuse_velocity = i == s->p.niter - 1;   // (pbf_stage_delta_p decides; off again right away: the stage
+        rc = pbf_stage_correct_density(s);        //  entry points called one by one keep the stages apart)
+        s->fuse_velocity = false;
+        if (rc) return rc;
+    }
+    if (s->stage != ST_VELOCITY && (rc = pbf_stage_update_velocity(s))) return rc;
     if ((rc = pbf_stage_correct_velocity(s))) return rc;
     return pbf_stage_end(s);
+}
+
+static uint64_t hash_bytes(uint64_t h, const void* p, size_t bytes) { return fnv1a64(h, p, bytes); }
+
+// pbf_step replayed from an instantiated CUDA graph: the 20-odd launches of a step become ONE submission, and the
+// programmatic-dependent-launch edges between its kernels (launch.cuh) are kept. Worth it where a step is short
+// (the reference's own 32 000-particle scene: 22 launches in 0.2 ms). A step is captured the first time its key
+// is seen; the caller's ping-pong gives two keys. A key that keeps changing (a wall that moves every step
+// changes the constants) would re-capture every step: after three misses in a row graphs pause for 32 steps.
+static int step_graph(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
+    uint64_t hc = 14695981039346656037ull;
+    hc = hash_bytes(hc, &s->g, sizeof(s->g));
+    hc = hash_bytes(hc, &s->c, sizeof(s->c));
+    hc = hash_bytes(hc, &s->npass, sizeof(s->npass));
+    const void* ptr[5] = {pos, npos, vel, nvel, iid};
+    StepGraph* hit = nullptr;
+    StepGraph* lru = nullptr;   // where a new graph goes: a free slot, else the least recently used one
+    for (auto& gq : s->graphs) {
+        if (gq.exec && gq.n == n && gq.stream == (cudaStream_t)stream && gq.consts_hash == hc &&
+            gq.niter == s->p.niter && gq.team == s->mode.team && gq.rebin == s->mode.rebin && gq.pdl == s->mode.pdl &&
+            memcmp(gq.ptr, ptr, sizeof(ptr)) == 0) {
+            hit = &gq;
+            break;
+        }
+        if (!lru || (lru->exec && (!gq.exec || gq.used < lru->used))) lru = &gq;
+    }
+    s->graph_clock++;
+    if (!hit) {
+        if (++s->graph_misses > 3 && s->mode.graph < 1) {   // the key will not settle: stop paying for captures
+            s->graph_misses = 0;
+            s->graph_holdoff = 32;
+            return step_direct(s, pos, npos, vel, nvel, iid, n, stream);
+        }
+        CUDA_TRY(cudaSetDevice(s->device));
+        const int64_t l0 = s->launches;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            s->graph_broken = true;
+            return step_direct(s, pos, npos, vel, nvel, iid, n, stream);
+        }
+        const int rc = step_direct(s, pos, npos, vel, nvel, iid, n, stream);
+        e = cudaStreamEndCapture((cudaStream_t)stream, &graph);
+        if (rc != PBF_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            s->graph_broken = true;
+            s->launches = l0;
+            if (rc != PBF_OK) return rc;   // (an argument error: the same with or without a graph)
+            return step_direct(s, pos, npos, vel, nvel, iid, n, stream);
+        }
+        if (lru->exec) { cudaGraphExecDestroy(lru->exec); lru->exec = nullptr; }
+        e = cudaGraphInstantiate(&lru->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            lru->exec = nullptr;
+            s->graph_broken = true;
+            s->launches = l0;
+            return step_direct(s, pos, npos, vel, nvel, iid, n, stream);
+        }
+        memcpy(lru->ptr, ptr, sizeof(ptr));
+        lru->n = n; lru->stream = (cudaStream_t)stream; lru->consts_hash = hc;
+        lru->niter = s->p.niter; lru->team = s->mode.team; lru->rebin = s->mode.rebin; lru->pdl = s->mode.pdl;
+        lru->launches = s->launches - l0;
+        lru->sorted_buf = s->sorted_buf; lru->cur = s->cur; lru->iters_done = s->iters_done;
+        lru->cull_cur = s->cull.cur; lru->cull_holds = s->cull.holds; lru->v4 = s->v4;
+        s->launches = l0;   // (counted below, when the graph runs)
+        hit = lru;
+    } else {
+        s->graph_misses = 0;
+        // the handle's view of the step in flight, as the stage functions would have left it
+        int rc = pbf_stage_begin(s, pos, npos, vel, nvel, iid, n, stream);
+        if (rc) return rc;
+        s->sorted_buf = hit->sorted_buf; s->cur = hit->cur; s->iters_done = hit->iters_done;
+        s->cull.cur = hit->cull_cur; s->cull.holds = hit->cull_holds; s->v4 = hit->v4;
+        s->pos0_in_npos = false;
+        s->stage = ST_IDLE;
+    }
+    hit->used = s->graph_clock;
+    CUDA_TRY(cudaGraphLaunch(hit->exec, (cudaStream_t)stream));
+    s->launches += hit->launches;
+    return PBF_OK;
+}
+
+int pbf_step(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n, void* stream) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    // a graph needs a capturable stream (not the legacy default stream) and a step without event timers
+    const bool capturable = stream != nullptr && (cudaStream_t)stream != cudaStreamLegacy && (cudaStream_t)stream != cudaStreamPerThread;
+    const bool wanted = s->mode.graph > 0 || (s->mode.graph < 0 && n < GRAPH_AUTO_MAX);
+    if (wanted && capturable && !s->timing && !s->graph_broken && n > 0) {
+        if (s->graph_holdoff > 0) s->graph_holdoff--;
+        else return step_graph(s, pos, npos, vel, nvel, iid, n, stream);
+    }
+    return step_direct(s, pos, npos, vel, nvel, iid, n, stream);
 }
 
 int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n) {
@@ -884,9 +1061,13 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     if (n > 0) s->reorder_wait = s->host_iid_ev;
     if ((rc = pbf_stage_advect(s))) return rc;
     if ((rc = pbf_stage_build_grid(s))) return rc;
-    for (int i = 0; i < s->p.niter; i++)
-        if ((rc = pbf_stage_correct_density(s))) return rc;
-    if ((rc = pbf_stage_update_velocity(s))) return rc;
+    for (int i = 0; i < s->p.niter; i++) {
+        s->fuse_velocity = i == s->p.niter - 1;
+        rc = pbf_stage_correct_density(s);
+        s->fuse_velocity = false;
+        if (rc) return rc;
+    }
+    if (s->stage != ST_VELOCITY && (rc = pbf_stage_update_velocity(s))) return rc;
     if (n > 0) {
         CUDA_TRY(cudaEventRecord(s->host_ev, st));
         CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
@@ -901,7 +1082,7 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     s->mode.moved = s->iters_done > 0;
     for (int64_t k = 0; k < slices && n > 0; k++) {
         const int64_t a = n * k / slices, b = n * (k + 1) / slices;
-        CUDA_TRY(launch_xsph(s->x[s->cur], s->cull, k == 0 ? s->n_local : 0, s->xl, s->cell_range, s->nvel + 3 * a,
+        CUDA_TRY(launch_xsph(s->x[s->cur], s->cull, k == 0 ? s->n_local : 0, s->v4, s->cell_range, s->nvel + 3 * a,
                              s->iid_sorted, s->iid + a, a, b - a, s->g, s->c, s->mode, st, &s->launches));
         CUDA_TRY(cudaEventRecord(s->host_ev, st));
         CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
@@ -1115,8 +1296,9 @@ static int slab_sort_state_impl(pbf_sim* s, int32_t x_begin, int32_t x_end, int3
     // keys from the positions as they are: advect with dt = 0 is the identity (fma(0, v, p) == p)
     SolverConsts c0 = s->c;
     c0.dt = 0.f; c0.gravity = 0.f;
-    CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, sort_scratch_zero_bytes(s->n, s->npass), s->stream));
-    CUDA_TRY(launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, s->n, s->npass, s->si, s->g, c0, s->stream, &s->launches));
+    if (s->sort_dirty) CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, s->sort_zero_capacity, s->stream));
+    s->sort_dirty = false;
+    CUDA_TRY(launch_advect_key(s->pos, s->vel, s->keys, s->sort_zero, nullptr, s->n, s->npass, s->si, s->g, c0, s->stream, &s->launches));
     SortScratch sc;
     sc.hist = s->sort_zero;
     sc.tile_counter = s->sort_zero + MAX_PASSES * RADIX;
@@ -1125,6 +1307,8 @@ static int slab_sort_state_impl(pbf_sim* s, int32_t x_begin, int32_t x_end, int3
     sc.bufs[1] = s->pairs[1];
     sc.tile_desc_words = 0;
     CUDA_TRY(launch_sort(s->keys, sc, s->n, s->npass, s->si, &s->sorted_buf, s->stream, &s->launches));
+    // (no reorder pass follows here: clean the sort's scratch by hand, see pbf_sim::sort_zero)
+    CUDA_TRY(cudaMemsetAsync(s->sort_zero, 0, sort_scratch_zero_bytes(s->n, s->npass), s->stream));
     if ((rc = slab_learn_layout(s))) return rc;
     s->stage = ST_IDLE;
     if (!n_kept && (s->layout.own_count != n || s->layout.own_first != 0))
@@ -1208,7 +1392,7 @@ int pbf_read(pbf_sim* s, int what, void* dst, int64_t count) {
             return extract(s->pos0_in_npos ? s->npos : s->pos, 3, 0, 3);
         case PBF_READ_VEL:
             if (s->stage != ST_VELOCITY && s->stage != ST_XSPH) return fail(PBF_ERR_STATE, "velocity not computed yet");
-            return extract(s->xl, 4, 0, 3);
+            return extract(s->v4, 4, 0, 3);
         case PBF_READ_NEIGHBOR_COUNT: {
             if (!s->count_scratch) CUDA_TRY(cudaMalloc((void**)&s->count_scratch, (size_t)s->max_particles * 4));
             CUDA_TRY(launch_neighbor_count(s->x[s->cur], s->cull, s->cell_range, s->count_scratch, s->n_local, s->g, s->c, s->stream));

@@ -114,14 +114,15 @@ __device__ __forceinline__ void halo_push(const HaloPush& hp, int64_t t, const f
 // ---- launchers (each returns the CUDA error of its launches) ---------------------------
 
 // advect + cell key + per-pass digit histograms, in input order (advect_key.cu)
-cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist,
+// cell_clear: the cell table to empty along the way (g.ncell entries, allocation padded to an even count), or null
+cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys, uint32_t* hist, uint2* cell_clear,
                               int64_t n, int npass, const SlabInput& si, const GridConsts& g,
                               const SolverConsts& c, cudaStream_t st, int64_t* launches);
 
 // onesweep LSD radix sort of (key, idx) (radix_sort.cu). `keys` is consumed by pass 0 with the
 // implicit index; result ends in bufs[result_buf].
 struct SortScratch {
-    uint32_t* hist;          // [MAX_PASSES][RADIX] digit counts -> exclusive prefix in place
+    uint32_t* hist;          // [MAX_PASSES][RADIX] digit counts (raw: every tile scans its pass's 256 counts)
     uint32_t* tile_counter;  // [MAX_PASSES]
     uint32_t* tile_desc;     // [npass][ntiles][RADIX] decoupled look-back state
     KeyIdx* bufs[2];
@@ -152,8 +153,21 @@ struct CullScratch {
 // [own_first, own_first + own_count) only, at slot - own_first.
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                            float4* x0, CullScratch& cs, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
-                           int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
+                           uint32_t* sort_zero, size_t sort_zero_bytes, int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches);
+
+// The velocity update (h_updateVelocity, Simulator.cu:127-137, 267-274) as the tail of the LAST delta-p pass of a
+// step: the thread that has just produced a particle's final position also forms vel = (npos - pos) * inv_dt and
+// writes what update_velocity_kernel writes — one launch and one read of the iterate fewer. v4 == null: not the
+// last pass (or the caller wants the stages apart). Single-GPU steps only (slab mode pushes two halos here).
+struct VelTail {
+    const float* rho = nullptr;   // density of the last lambda pass, by slot
+    float* pos_out = nullptr;     // caller's pos  <- step-input position (parked in npos by the reorder pass)
+    float* npos_io = nullptr;     // caller's npos: step-input position in, final position out
+    float* vel_out = nullptr;     // caller's vel  <- new velocity (pre-XSPH, what the reference leaves there)
+    float4* v4 = nullptr;         // (vx, vy, vz, rho) by slot, what the XSPH sweep gathers
+    float inv_dt = 0.f;
+};
 
 // Run-time options of the neighbour sweeps, owned by the handle (pbf_set_option): nothing on the launch path
 // reads the environment.
@@ -161,6 +175,8 @@ struct SweepMode {
     int team = -1;   // -1: by particle count (solver_common.cuh TEAM_MAX_PARTICLES); 0 / 1: thread / four-lane kernels
     int rebin = 0;   // thread kernels: re-deal a block's particles by CURRENT home cell once the iterate has moved
                      // (measured: no gain, DESIGN.md 3.7 — off by default, kept selectable for the A/B)
+    int pdl = 1;     // programmatic dependent launch between the step's kernels (launch.cuh)
+    int graph = -1;  // pbf_step replayed from a CUDA graph: -1 below 256 K particles, 0 never, 1 always (pbf_capi.cu)
     bool moved = false;   // set per launch by the stage functions: the iterate is not the one the sort keyed on
 };
 
@@ -168,11 +184,7 @@ struct SweepMode {
 // Neighbour list the lambda pass saves for the delta-p pass of the same iteration (null = off).
 struct PairList {
     uint2* js = nullptr;      // (slot of the k-th in-range neighbour, spiky scale of that pair as bits)
-    uint32_t* cnt = nullptr;  // per particle: number of entries, or the overflow flag
-    // two words: "some list of this iteration overflowed", one per iteration parity. The lambda pass of
-    // iteration k raises flag[k & 1]; the delta-p pass's overflow kernel of iteration k leaves at once if it is
-    // down, and clears flag[(k + 1) & 1] — the one nobody reads until the lambda pass of iteration k + 1 sets it.
-    uint32_t* ovf_flag = nullptr;
+    uint32_t* cnt = nullptr;  // per list column: records | owner particle << 8 | PAIR_OVERFLOW (solver_common.cuh pair_word)
 };
 size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes);
 // The passes compute slots [first, first + n) (slab mode: the owned slots; single GPU: 0, n) and
@@ -180,10 +192,10 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
 // slot; caller-facing arrays (pos/npos/vel/nvel/iid) and the pair list by slot - first.
 // `n_slots` = every slot the handle stores (ghosts included): the sweeps' cull reads them all.
 cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
-                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
-                           int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp, const GridConsts& g,
+                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const VelTail& vt, const GridConsts& g,
                            const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,

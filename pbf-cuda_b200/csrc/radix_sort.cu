@@ -6,7 +6,8 @@
 // afterwards (reorder.cu).
 //
 // Algorithm (Adinets & Merrill "Onesweep", restated from the paper, not from CUB's sources):
-//   - digit histograms of ALL passes are produced up front by advect_key.cu;
+//   - digit histograms of ALL passes are produced up front by advect_key.cu (raw counts; every tile scans the
+//     256 counts of its pass itself);
 //   - one kernel per 8-bit digit: each CTA takes a tile through an atomic ticket (so that every
 //     tile it may wait on is already resident), ranks its keys with warp-level match_any
 //     (stable: items are visited in memory order), publishes its per-digit counts, resolves its
@@ -15,6 +16,7 @@
 //   - stable, deterministic, no temporary allocation.
 //
 // HBM traffic per pass: R 8 B + W 8 B per particle (pass 0 reads the 4 B key only).
+#include "launch.cuh"
 #include "pbf_internal.h"
 
 namespace pbf {
@@ -37,47 +39,23 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// counts -> exclusive prefix, one CTA of RADIX threads per pass.
-__global__ void __launch_bounds__(RADIX) hist_scan_kernel(uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s_wsum[RADIX / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t* h = hist + blockIdx.x * RADIX;
-    const uint32_t cnt = h[tid];
-    uint32_t v = cnt;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
-        if (lane >= off) v += t;
-    }
-    if (lane == 31) s_wsum[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = lane < RADIX / 32 ? s_wsum[lane] : 0, iw = w;
-#pragma unroll
-        for (int off = 1; off < RADIX / 32; off <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, iw, off);
-            if (lane >= off) iw += t;
-        }
-        if (lane < RADIX / 32) s_wsum[lane] = iw - w;
-    }
-    __syncthreads();
-    h[tid] = v - cnt + s_wsum[warp];
-}
-
 template <bool FIRST>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__ pairs_in,
-                KeyIdx* __restrict__ out, const uint32_t* __restrict__ hist_excl,
+                KeyIdx* __restrict__ out, const uint32_t* __restrict__ hist,
                 uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ tile_desc, int64_t n,
                 int shift, const __grid_constant__ SlabInput si) {
+    pdl_wait();
     __shared__ KeyIdx s_pairs[SORT_TILE];
     __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];
     __shared__ uint32_t s_digit_start[RADIX];
     __shared__ uint32_t s_global_base[RADIX];
     __shared__ uint32_t s_wsum[SORT_WARPS];
+    __shared__ uint32_t s_gsum[SORT_WARPS];
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t total = hist[tid];   // (global count of digit `tid` in this pass; needed after the look-back)
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; w++) s_warp_hist[w][tid] = 0;
@@ -153,28 +131,31 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
         st_volatile(my_desc + tid, (excl + count) | FLAG_PREFIX);
     }
 
-    // ---- exclusive scan of the tile counts over the digits -> position in the tile-sorted order
-    uint32_t v = count;
+    // ---- exclusive scans over the digits, two at once: of the tile counts (-> position in the tile-sorted
+    // order) and of the pass's global digit counts (-> first global slot of a digit; every tile redoes this
+    // 256-element scan, which is cheaper than a separate kernel in front of every sort)
+    uint32_t v = count, gv = total;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
-        if (lane >= off) v += t;
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, off), gt = __shfl_up_sync(0xffffffffu, gv, off);
+        if (lane >= off) { v += t; gv += gt; }
     }
-    if (lane == 31) s_wsum[warp] = v;
+    if (lane == 31) { s_wsum[warp] = v; s_gsum[warp] = gv; }
     __syncthreads();
     if (warp == 0) {
         uint32_t w = lane < SORT_WARPS ? s_wsum[lane] : 0, iw = w;
+        uint32_t gw = lane < SORT_WARPS ? s_gsum[lane] : 0, igw = gw;
 #pragma unroll
         for (int off = 1; off < SORT_WARPS; off <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, iw, off);
-            if (lane >= off) iw += t;
+            uint32_t t = __shfl_up_sync(0xffffffffu, iw, off), gt = __shfl_up_sync(0xffffffffu, igw, off);
+            if (lane >= off) { iw += t; igw += gt; }
         }
-        if (lane < SORT_WARPS) s_wsum[lane] = iw - w;
+        if (lane < SORT_WARPS) { s_wsum[lane] = iw - w; s_gsum[lane] = igw - gw; }
     }
     __syncthreads();
     const uint32_t dstart = v - count + s_wsum[warp];
     s_digit_start[tid] = dstart;
-    s_global_base[tid] = hist_excl[tid] + excl - dstart;  // + position in tile order = global slot
+    s_global_base[tid] = (gv - total + s_gsum[warp]) + excl - dstart;  // + position in tile order = global slot
     __syncthreads();
 
     // ---- reorder the tile through shared memory
@@ -203,7 +184,6 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
 cudaError_t preload_sort() {
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hist_scan_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<false>);
     return e;
@@ -218,15 +198,13 @@ cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npa
                         int* result_buf, cudaStream_t st, int64_t* launches) {
     if (n <= 0) { *result_buf = 0; return cudaSuccess; }
     const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    hist_scan_kernel<<<npass, RADIX, 0, st>>>(s.hist);
-    if (launches) (*launches)++;
     for (int p = 0; p < npass; p++) {
         uint32_t* desc = s.tile_desc + (size_t)p * tiles * RADIX;
         const uint32_t* h = s.hist + p * RADIX;
         if (p == 0)
-            onesweep_kernel<true><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
+            PBF_LAUNCH((onesweep_kernel<true>), (unsigned)tiles, SORT_THREADS, 0, st, keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
         else
-            onesweep_kernel<false><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
+            PBF_LAUNCH((onesweep_kernel<false>), (unsigned)tiles, SORT_THREADS, 0, st, nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
         if (launches) (*launches)++;
     }
     *result_buf = (npass - 1) & 1;

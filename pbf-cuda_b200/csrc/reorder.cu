@@ -1,7 +1,8 @@
 // reorder.cu — gather the particle state into cell-sorted SoA and build the cell table.
 //
 // Replaces (a) the payload movement inside the reference's sort_by_key (Simulator.cu:196-198),
-// (b) the two cudaMemset + computeGridRange (Simulator.cu:200-204, Simulator_kernel.cuh:21-50).
+// (b) computeGridRange (Simulator.cu:204, Simulator_kernel.cuh:21-50) — the two cudaMemset in front of it
+//     (Simulator.cu:201-203) are folded into advect_key.cu.
 // For sorted slot s with source index j:
 //   x0[s]      = (advect(pos[j], vel[j]), 0)      float4, the iterate the solver works on
 //   xs/ys/zs[s] = the same coordinates as three arrays, what the sweeps' cull reads
@@ -18,6 +19,7 @@
 //
 // HBM traffic: R 8 (pair) + 28 (gathered pos, vel, iid; near-sequential because the input is
 // last step's sorted order) ; W 16 + 12 + 12 + 4 per particle, + 8 B per occupied cell.
+#include "launch.cuh"
 #include "pbf_math.cuh"
 
 namespace pbf {
@@ -29,9 +31,14 @@ reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
                const float* __restrict__ vel, const uint32_t* __restrict__ iid,
                float4* __restrict__ x0, float* __restrict__ xs, float* __restrict__ ys, float* __restrict__ zs,
                float* __restrict__ pos0_out, uint32_t* __restrict__ iid_sorted,
-               uint2* __restrict__ cell_range, int64_t n, int64_t own_first, int64_t own_count,
+               uint2* __restrict__ cell_range, uint4* __restrict__ sort_zero, int64_t sort_zero_quads,
+               int64_t n, int64_t own_first, int64_t own_count,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
     const int64_t s = (int64_t)blockIdx.x * RO_THREADS + threadIdx.x;
+    // the sort is done: leave its histograms, tickets and look-back descriptors zeroed for the next one
+    // (the invariant of pbf_sim::sort_zero), instead of a memset in front of every step
+    for (int64_t k = s; k < sort_zero_quads; k += (int64_t)gridDim.x * RO_THREADS) sort_zero[k] = make_uint4(0u, 0u, 0u, 0u);
     if (s >= n) return;
     const KeyIdx e = sorted[s];
     const uint32_t prev = s == 0 ? 0xffffffffu : sorted[s - 1].key;
@@ -61,15 +68,12 @@ cudaError_t preload_reorder() {
 
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                            float4* x0, CullScratch& cs, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
-                           int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
+                           uint32_t* sort_zero, size_t sort_zero_bytes, int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     cs.holds = nullptr;
-    cudaError_t e = cudaMemsetAsync(cell_range, 0, sizeof(uint2) * (size_t)g.ncell, st);
-    if (e != cudaSuccess) return e;
-    if (launches) (*launches)++;
-    if (n <= 0) return cudaSuccess;
+    if (n <= 0) return cudaSuccess;   // (nothing was sorted and nothing will be read)
     unsigned blocks = (unsigned)((n + RO_THREADS - 1) / RO_THREADS);
-    reorder_kernel<<<blocks, RO_THREADS, 0, st>>>(sorted, pos, vel, iid, x0, cs.xs[0], cs.ys[0], cs.zs[0], pos0_out, iid_sorted, cell_range, n, own_first, own_count, g, c);
+    PBF_LAUNCH((reorder_kernel), blocks, RO_THREADS, 0, st, sorted, pos, vel, iid, x0, cs.xs[0], cs.ys[0], cs.zs[0], pos0_out, iid_sorted, cell_range, reinterpret_cast<uint4*>(sort_zero), (int64_t)((sort_zero_bytes + 15) / 16), n, own_first, own_count, g, c);
     if (launches) (*launches)++;
     cs.cur = 0;
     cs.holds = x0;   // every stored slot

@@ -11,6 +11,7 @@
 // is a copy of one contiguous float4 range straight out of / into the solver's own arrays.
 #include <stdio.h>
 
+#include "launch.cuh"
 #include "pbf_internal.h"
 
 namespace pbf {
@@ -21,6 +22,7 @@ namespace {
 // key (== ncell == nxl*dyz) is behind every local cell, so plane_start[nxl] = particles kept.
 __global__ void plane_table_kernel(const KeyIdx* __restrict__ sorted, int64_t n,
                                    int64_t* __restrict__ plane_start, int nxl, int dyz) {
+    pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p > nxl) return;
     const uint32_t want = (uint32_t)p * (uint32_t)dyz;
@@ -37,6 +39,7 @@ gather_state_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__
                     const float* __restrict__ vel, const uint32_t* __restrict__ iid,
                     float* __restrict__ npos, float* __restrict__ nvel, uint32_t* __restrict__ iid_out,
                     int64_t n) {
+    pdl_wait();
     const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (s >= n) return;
     const uint32_t j = sorted[s].idx;
@@ -52,6 +55,7 @@ gather_state_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__
 // remote stores are performed), the wait blocks the stream until the neighbours' words arrive.
 __global__ void halo_signal_kernel(const int64_t* tail_src, int64_t* peer_right_tail, uint32_t* peer_word_left,
                                    uint32_t* peer_word_right, uint32_t seq) {
+    pdl_wait();
     if (peer_right_tail) *(volatile int64_t*)peer_right_tail = *tail_src;
     __threadfence_system();
     if (peer_word_left) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_word_left), "r"(seq) : "memory");
@@ -72,6 +76,7 @@ __device__ __forceinline__ uint64_t global_ns() {
 // (int32 difference: the sequence number may wrap)
 __global__ void halo_wait_kernel(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
                                  uint64_t timeout_ns, uint32_t* flags) {
+    pdl_wait();
     const uint64_t t0 = global_ns();
     for (int side = 0; side < 2; side++) {
         const uint32_t* w = side == 0 ? word_left : word_right;
@@ -105,7 +110,7 @@ cudaError_t preload_slab() {
 cudaError_t launch_halo_signal(uint32_t* peer_word_left, uint32_t* peer_word_right, uint32_t seq, cudaStream_t st,
                                int64_t* launches) {
     if (!peer_word_left && !peer_word_right) return cudaSuccess;
-    halo_signal_kernel<<<1, 1, 0, st>>>(nullptr, nullptr, peer_word_left, peer_word_right, seq);
+    PBF_LAUNCH((halo_signal_kernel), 1, 1, 0, st, nullptr, nullptr, peer_word_left, peer_word_right, seq);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -113,7 +118,7 @@ cudaError_t launch_halo_signal(uint32_t* peer_word_left, uint32_t* peer_word_rig
 cudaError_t launch_halo_publish(const int64_t* tail_src, int64_t* peer_right_tail, uint32_t* peer_word_left,
                                 uint32_t* peer_word_right, uint32_t seq, cudaStream_t st, int64_t* launches) {
     if (!peer_word_left && !peer_word_right) return cudaSuccess;
-    halo_signal_kernel<<<1, 1, 0, st>>>(tail_src, peer_right_tail, peer_word_left, peer_word_right, seq);
+    PBF_LAUNCH((halo_signal_kernel), 1, 1, 0, st, tail_src, peer_right_tail, peer_word_left, peer_word_right, seq);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -121,7 +126,7 @@ cudaError_t launch_halo_publish(const int64_t* tail_src, int64_t* peer_right_tai
 cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_right, uint32_t seq,
                              uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches) {
     if (!word_left && !word_right) return cudaSuccess;
-    halo_wait_kernel<<<1, 1, 0, st>>>(word_left, word_right, seq, timeout_ns, flags);
+    PBF_LAUNCH((halo_wait_kernel), 1, 1, 0, st, word_left, word_right, seq, timeout_ns, flags);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -129,7 +134,7 @@ cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_rig
 cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,
                                cudaStream_t st, int64_t* launches) {
     const int threads = 128;
-    plane_table_kernel<<<(g.nxl + 1 + threads - 1) / threads, threads, 0, st>>>(sorted, n, plane_start, g.nxl, g.dyz);
+    PBF_LAUNCH((plane_table_kernel), (g.nxl + 1 + threads - 1) / threads, threads, 0, st, sorted, n, plane_start, g.nxl, g.dyz);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -138,7 +143,7 @@ cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const fl
                                 float* npos, float* nvel, uint32_t* iid_out, int64_t n, cudaStream_t st,
                                 int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    gather_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted, pos, vel, iid, npos, nvel, iid_out, n);
+    PBF_LAUNCH((gather_state_kernel), (unsigned)((n + 255) / 256), 256, 0, st, sorted, pos, vel, iid, npos, nvel, iid_out, n);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -16,6 +16,7 @@
 // (sqrt, 4 IEEE divisions, pow) only for the pairs that passed — candidates outside h contribute
 // exact zeros in the reference, so skipping them does not change a single bit — with the
 // neighbour list of the lambda pass handed to the delta-p pass of the same iteration.
+#include "launch.cuh"
 #include "solver_common.cuh"
 
 #ifndef PBF_CULL_IDX
@@ -154,6 +155,7 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
 // million particles, HBM bound (16 B read, 12 B written per particle)
 __global__ void __launch_bounds__(256)
 pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restrict__ ys, float* __restrict__ zs, int64_t n) {
+    pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const float4 q = x[i];
@@ -224,9 +226,10 @@ template <bool SAVE_PAIRS, bool FAST_SPIKY, bool REBIN>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-              uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt, uint32_t* __restrict__ ovf_flag,
+              uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
               const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
               const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     extern __shared__ uint2 s_words[];
     __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
     const uint32_t local = REBIN ? rebin_block(x, first, n, g, s_re) : threadIdx.x;   // which particle of the block
@@ -274,15 +277,14 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     rho_out[i] = rho;
     if (SAVE_PAIRS) {   // the list lives in THIS THREAD's column (coalesced records); the word says whose it is
         pair_cnt[(int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x] = pair_word(n_pairs, local);
-        if (n_pairs > PAIR_CAP) *ovf_flag = 1u;   // (every writer stores the same value)
     }
 }
 
 // The delta-p pass comes as two kernels. The REPLAY kernel walks the neighbour list the lambda pass saved:
 // no cell table, no shared-memory list, few registers — it is latency / HBM bound, so it is compiled for
-// 16 CTAs per SM instead of 8 (32 registers, no spills; measured 0.28 -> 0.20 ms in the compressed state). Particles whose list overflowed
-// (more than PAIR_CAP neighbours) are left to the GATHER kernel, which re-runs the full two-phase gather
-// for them only (ONLY_OVERFLOW) — or for everybody when there is no list at all.
+// 16 CTAs per SM instead of 8 (32 registers, no spills; measured 0.28 -> 0.20 ms in the compressed state). A particle whose list overflowed
+// (more than PAIR_CAP neighbours) takes delta_p_one (solver_common.cuh) inside the replay kernel; the GATHER kernel
+// below runs only when there is no list at all.
 #ifndef PBF_REPLAY_MINBLOCKS
 #define PBF_REPLAY_MINBLOCKS 16
 #endif
@@ -296,15 +298,25 @@ template <int POW>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
 delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                       const uint2* __restrict__ pair_js,
-                      const uint32_t* __restrict__ pair_cnt, const __grid_constant__ HaloPush hp,
-                      const __grid_constant__ SolverConsts c) {
+                      const uint32_t* __restrict__ pair_cnt, const uint2* __restrict__ cell_range,
+                      const __grid_constant__ HaloPush hp, const __grid_constant__ VelTail vt,
+                      const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     const int64_t col = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;   // list column; its word names the particle
     if (col >= n) return;
     const uint32_t cw = pair_cnt[col];
     const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + pair_local(cw);
-    if ((cw & PAIR_OVERFLOW) || t >= n) return;   // the gather kernel's particle / a column past the end
-    const uint32_t cnt = pair_count(cw);
+    if (t >= n) return;   // (a column past the end)
     const int64_t i = first + t;
+    if (cw & PAIR_OVERFLOW) {   // more neighbours than the list holds: the plain pass for this one particle
+        const float4 out = delta_p_one<POW>(xl, (uint32_t)i, cell_range, g, c);
+        x_out[i] = out;
+        co.store(i, out);
+        halo_push(hp, t, out);
+        if (vt.v4) velocity_tail(vt, t, i, out);
+        return;
+    }
+    const uint32_t cnt = pair_count(cw);
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
@@ -325,54 +337,41 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
     x_out[i] = out;
     co.store(i, out);
     halo_push(hp, t, out);
+    if (vt.v4) velocity_tail(vt, t, i, out);   // the step's last pass: the velocity update rides along
 }
 
-template <int POW, bool ONLY_OVERFLOW, bool REBIN>
+// The delta-p pass WITHOUT a neighbour list (the list is optional scratch: PBF_NO_PAIR_REUSE=1, or a handle too
+// large for it): the full two-phase gather for every particle.
+template <int POW, bool REBIN>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restrict__ x_out, const CullOut co,
-               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-               const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__ flag_read,
-               uint32_t* __restrict__ flag_clear, const __grid_constant__ HaloPush hp,
-               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+               const uint2* __restrict__ cell_range, int64_t first, int64_t n, const __grid_constant__ HaloPush hp,
+               const __grid_constant__ VelTail vt, const __grid_constant__ GridConsts g,
+               const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     extern __shared__ uint2 s_words[];
     __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
-    static_assert(!(ONLY_OVERFLOW && REBIN), "the overflow kernel strides over list columns; it does not re-bin");
-    // ONLY_OVERFLOW: a small grid that strides over the list columns — and leaves at once when no list of this
-    // iteration overflowed, which is the normal case (see PairList::ovf_flag). Otherwise one block of particles
-    // per CTA (the launcher sizes the grid), re-dealt by current home cell if REBIN (rebin_block).
-    if (ONLY_OVERFLOW) {
-        const bool any = *flag_read != 0;
-        if (blockIdx.x == 0 && threadIdx.x == 0) *flag_clear = 0u;
-        if (!any) return;
-    }
     const uint32_t local = REBIN ? rebin_block(xl, first, n, g, s_re) : threadIdx.x;
-    for (int64_t col = (int64_t)blockIdx.x * GATHER_THREADS + local; col < n; col += (int64_t)gridDim.x * GATHER_THREADS) {
-        int64_t t = col;
-        if (ONLY_OVERFLOW) {   // the column's word names the particle (the lambda pass may have re-binned its block)
-            const uint32_t cw = pair_cnt[col];
-            if (!(cw & PAIR_OVERFLOW)) continue;
-            t = col - (col % GATHER_THREADS) + pair_local(cw);
-            if (t >= n) continue;
-        }
-        const int64_t i = first + t;
-        const float4 p = xl[i];
-        float ax = 0.f, ay = 0.f, az = 0.f;
-        gather<true>(p, (uint32_t)i, c.h2_cull, xl, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
-            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-            const float r2 = sumsq(dx, dy, dz);
-            const float pw = pow_ncorr<POW>(poly6(r2, c), c);
-            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-            const float s = spiky_scale(r2, c);
-            ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
-            ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
-            az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
-        });
-        const float4 out = delta_p_finish(p, ax, ay, az, c);
-        x_out[i] = out;
-        co.store(i, out);   // (reads of this iteration's coordinates go to `soa` = the OTHER set of arrays)
-        halo_push(hp, t, out);
-        if (REBIN) break;   // (one block per CTA: the grid is not strided)
-    }
+    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + local;
+    if (t >= n) return;
+    const int64_t i = first + t;
+    const float4 p = xl[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    gather<true>(p, (uint32_t)i, c.h2_cull, xl, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
+        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+        const float r2 = sumsq(dx, dy, dz);
+        const float pw = pow_ncorr<POW>(poly6(r2, c), c);
+        const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+        const float s = spiky_scale(r2, c);
+        ax = __fmaf_rn(sc, __fmul_rn(dx, s), ax);
+        ay = __fmaf_rn(sc, __fmul_rn(dy, s), ay);
+        az = __fmaf_rn(sc, __fmul_rn(dz, s), az);
+    });
+    const float4 out = delta_p_finish(p, ax, ay, az, c);
+    x_out[i] = out;
+    co.store(i, out);   // (reads of this iteration's coordinates go to `soa` = the OTHER set of arrays)
+    halo_push(hp, t, out);
+    if (vt.v4) velocity_tail(vt, t, i, out);
 }
 
 // vel = (npos - pos) * inv_dt, plus everything the caller-facing buffers need from this point:
@@ -382,6 +381,7 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
                        float* __restrict__ pos_out, float* __restrict__ npos_io,
                        float* __restrict__ vel_out, float4* __restrict__ v4, int64_t first, int64_t n,
                        const __grid_constant__ HaloPush hp, const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= n) return;
     const int64_t i = first + t;
@@ -404,6 +404,7 @@ xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __res
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
             const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     extern __shared__ uint2 s_words[];
     __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
     const uint32_t local = REBIN ? rebin_block(x, first, n, g, s_re) : threadIdx.x;
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(GATHER_THREADS)
 neighbor_count_kernel(const float4* __restrict__ x, const CullSoA soa, const uint2* __restrict__ cell_range,
                       uint32_t* __restrict__ count, int64_t n, const __grid_constant__ GridConsts g,
                       const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     extern __shared__ uint2 s_words[];
     const int64_t i = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
     if (i >= n) return;
@@ -460,18 +462,14 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<2>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<3>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, true, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, true, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, true, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, true, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false, false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false, true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, update_velocity_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<true>);
@@ -492,7 +490,7 @@ static bool use_team(const SweepMode& mode, int64_t n) {
 // the cull's coordinate arrays must mirror `x`: nothing to do if the producer of `x` wrote them along
 static cudaError_t launch_pack(const float4* x, CullScratch& cs, int64_t n_slots, cudaStream_t st, int64_t* launches) {
     if (cs.holds == x) return cudaSuccess;
-    pack_kernel<<<nblocks(n_slots, 256), 256, 0, st>>>(x, cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur], n_slots);
+    PBF_LAUNCH((pack_kernel), nblocks(n_slots, 256), 256, 0, st, x, cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur], n_slots);
     if (launches) (*launches)++;
     cs.holds = x;
     return cudaGetLastError();
@@ -508,27 +506,26 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
 }
 
 cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
-                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
     if (pe != cudaSuccess) return pe;
     const CullSoA soa = soa_of(cs);
     if (use_team(mode, n)) {
-        launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, pl.js ? pl.ovf_flag + (parity & 1) : nullptr, hp, g, c, st);
+        launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c, st);
         if (launches) (*launches)++;
         return cudaGetLastError();
     }
     const unsigned nb = nblocks(n, GATHER_THREADS);
-    uint32_t* const flag = pl.js ? pl.ovf_flag + (parity & 1) : nullptr;
 #define PBF_LAMBDA_LAUNCH(SAVE, FAST)                                                                                          \
     do {                                                                                                                       \
         if (mode.rebin && mode.moved)                                                                                          \
-            lambda_kernel<SAVE, FAST, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n,       \
-                                                                                 pl.js, pl.cnt, flag, hp, g, c);             \
+            PBF_LAUNCH((lambda_kernel<SAVE, FAST, true>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n,       \
+                                                                                 pl.js, pl.cnt, hp, g, c);                   \
         else                                                                                                                   \
-            lambda_kernel<SAVE, FAST, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n,      \
-                                                                                  pl.js, pl.cnt, flag, hp, g, c);            \
+            PBF_LAUNCH((lambda_kernel<SAVE, FAST, false>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n,      \
+                                                                                  pl.js, pl.cnt, hp, g, c);                  \
     } while (0)
     if (!pl.js && !c.fast_spiky) PBF_LAMBDA_LAUNCH(false, false);
     else if (!pl.js) PBF_LAMBDA_LAUNCH(false, true);
@@ -541,7 +538,7 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
 
 // (`cs` holds the positions the lambda pass of this iteration packed: the same ones xl carries)
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
-                           int64_t first, int64_t n, const PairList& pl, int parity, const HaloPush& hp, const GridConsts& g,
+                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const VelTail& vt, const GridConsts& g,
                            const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     const CullSoA soa = soa_of(cs);   // this iteration's coordinates: what the overflow kernel culls on
@@ -550,23 +547,16 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
     // exponent folded (same bits; when 3 did not verify or is switched off); 1: powf, any exponent; 0: (w*w)^2
     const int pow_mode = c.n_corr == 4.0f ? (c.exact_pow ? (c.trim_pow ? 3 : 2) : 0) : 1;
     const unsigned nb = nblocks(n, GATHER_THREADS);
-    const unsigned nb_ovf = nb < 148u * PBF_GATHER_MINBLOCKS ? nb : 148u * PBF_GATHER_MINBLOCKS;
-    uint32_t* const f_read = pl.js ? pl.ovf_flag + (parity & 1) : nullptr;
-    uint32_t* const f_clear = pl.js ? pl.ovf_flag + ((parity & 1) ^ 1) : nullptr;
 #define PBF_DP_LAUNCH(POW)                                                                                                    \
     do {                                                                                                                      \
         if (pl.js) {                                                                                                          \
-            if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c, POW, st);              \
-            else delta_p_replay_kernel<POW><<<nb, GATHER_THREADS, 0, st>>>(xl, x_out, co, first, n, pl.js, pl.cnt, hp, c);    \
-            delta_p_kernel<POW, true, false><<<nb_ovf, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n, \
-                                                                                         pl.cnt, f_read, f_clear, hp, g, c);   \
-            if (launches) (*launches)++;                                                                                      \
+            if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, cell_range, hp, vt, g, c, POW, st); \
+            else PBF_LAUNCH((delta_p_replay_kernel<POW>), nb, GATHER_THREADS, 0, st, xl, x_out, co, first, n, pl.js, pl.cnt,  \
+                            cell_range, hp, vt, g, c);                                                                       \
         } else if (mode.rebin && mode.moved) {                                                                                \
-            delta_p_kernel<POW, false, true><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n, \
-                                                                                     nullptr, nullptr, nullptr, hp, g, c);    \
+            PBF_LAUNCH((delta_p_kernel<POW, true>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, vt, g, c); \
         } else {                                                                                                              \
-            delta_p_kernel<POW, false, false><<<nb, GATHER_THREADS, LIST_SMEM, st>>>(xl, soa, x_out, co, cell_range, first, n, \
-                                                                                      nullptr, nullptr, nullptr, hp, g, c);   \
+            PBF_LAUNCH((delta_p_kernel<POW, false>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, vt, g, c); \
         }                                                                                                                     \
     } while (0)
     if (pow_mode == 3) PBF_DP_LAUNCH(3);
@@ -590,7 +580,7 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
                                    const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    update_velocity_kernel<<<nblocks(n, 256), 256, 0, st>>>(x, rho, pos_out, npos_io, vel_out, v4, first, n, hp, c);
+    PBF_LAUNCH((update_velocity_kernel), nblocks(n, 256), 256, 0, st, x, rho, pos_out, npos_io, vel_out, v4, first, n, hp, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -611,9 +601,9 @@ cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const
         return cudaGetLastError();
     }
     if (mode.rebin && mode.moved)
-        xsph_kernel<true><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+        PBF_LAUNCH((xsph_kernel<true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
     else
-        xsph_kernel<false><<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+        PBF_LAUNCH((xsph_kernel<false>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -623,7 +613,7 @@ cudaError_t launch_neighbor_count(const float4* x, CullScratch& cs, const uint2*
     if (n <= 0) return cudaSuccess;
     cudaError_t pe = launch_pack(x, cs, n, st, nullptr);
     if (pe != cudaSuccess) return pe;
-    neighbor_count_kernel<<<nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st>>>(x, soa_of(cs), cell_range, count, n, g, c);
+    PBF_LAUNCH((neighbor_count_kernel), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), cell_range, count, n, g, c);
     return cudaGetLastError();
 }
 

@@ -116,6 +116,63 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
     return make_float4(qx, qy, qz, 0.f);
 }
 
+// VelTail (pbf_internal.h): the velocity update of particle t (slot i) right behind its final position `q`
+__device__ __forceinline__ void velocity_tail(const VelTail& vt, int64_t t, int64_t i, const float4 q) {
+    const float3 p0 = load_f3(vt.npos_io, t);
+    const float vx = __fmul_rn(__fsub_rn(q.x, p0.x), vt.inv_dt);
+    const float vy = __fmul_rn(__fsub_rn(q.y, p0.y), vt.inv_dt);
+    const float vz = __fmul_rn(__fsub_rn(q.z, p0.z), vt.inv_dt);
+    vt.v4[i] = make_float4(vx, vy, vz, vt.rho[i]);
+    store_f3(vt.vel_out, t, vx, vy, vz);
+    store_f3(vt.pos_out, t, p0.x, p0.y, p0.z);
+    store_f3(vt.npos_io, t, q.x, q.y, q.z);
+}
+
+// The delta-p pass of ONE particle the plain way — every candidate of the 27 cells in the reference's visiting
+// order, the exact pair arithmetic for those in range — for the rare particle whose neighbour list did not fit
+// PAIR_CAP records (a collapsing cluster): the replay kernels call it instead of a second, list-less kernel
+// that every Jacobi iteration would have to launch just to find nothing to do. Candidates outside h contribute
+// exact zeros in the reference (computetpos, Simulator_kernel.cuh:150-170), so skipping them changes no bit.
+// Not inlined: the replay kernels keep their 32 registers.
+template <int POW>
+__device__ __noinline__ float4 delta_p_one(const float4* __restrict__ xl, uint32_t i, const uint2* __restrict__ cell_range,
+                                           const GridConsts& g, const SolverConsts& c) {
+    const float4 p = xl[i];
+    const int3 cc = cell_of(p.x, p.y, p.z, g);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int dx = -1; dx <= 1; dx++) {
+        const int cx = cc.x + dx, lx = cx - g.xoff;
+        if (cx < 0 || cx >= g.dim[0]) continue;
+        if (lx < 0 || lx >= g.nxl) {   // the search leaves the stored planes (slab mode): say so, see gather()
+            if (g.flags) atomicOr(g.flags, (uint32_t)PBF_SLAB_FLAG_GHOST);
+            continue;
+        }
+        for (int dy = -1; dy <= 1; dy++) {
+            const int cy = cc.y + dy;
+            if (cy < 0 || cy >= g.dim[1]) continue;
+            for (int dz = -1; dz <= 1; dz++) {
+                const int cz = cc.z + dz;
+                if (cz < 0 || cz >= g.dim[2]) continue;
+                const uint2 r = __ldg(&cell_range[lx * g.dyz + cy * g.dim[2] + cz]);
+                for (uint32_t j = r.x; j < r.y; j++) {
+                    if (j == i) continue;
+                    const float4 q = __ldg(&xl[j]);
+                    const float ddx = __fsub_rn(p.x, q.x), ddy = __fsub_rn(p.y, q.y), ddz = __fsub_rn(p.z, q.z);
+                    const float r2 = sumsq(ddx, ddy, ddz);
+                    if (!(r2 < c.h2_cull)) continue;
+                    const float pw = pow_ncorr<POW>(poly6(r2, c), c);
+                    const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+                    const float s = spiky_scale(r2, c);
+                    ax = __fmaf_rn(sc, __fmul_rn(ddx, s), ax);
+                    ay = __fmaf_rn(sc, __fmul_rn(ddy, s), ay);
+                    az = __fmaf_rn(sc, __fmul_rn(ddz, s), az);
+                }
+            }
+        }
+    }
+    return delta_p_finish(p, ax, ay, az, c);
+}
+
 // solver_team.cu: the same sweeps with four lanes per particle, for scenes too small to fill the machine
 // Measured (B200, ms per step, thread-per-particle vs team): 32 K 0.380 vs 0.282; 131 K 0.599 vs 0.871; 262 K 0.893 vs
 // 1.490 — the team kernels stop being latency bound near 45 K particles and cost ~1.6x the instruction slots from
@@ -123,11 +180,11 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
 constexpr int64_t TEAM_MAX_PARTICLES = 48 * 1024;
 cudaError_t preload_solver_team();
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, uint32_t* ovf_flag, const HaloPush& hp,
+                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp,
                         const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut co, int64_t first, int64_t n, const uint2* pair_js,
-                                const uint32_t* pair_cnt, const HaloPush& hp, const SolverConsts& c, int pow_mode,
-                                cudaStream_t st);
+                                const uint32_t* pair_cnt, const uint2* cell_range, const HaloPush& hp, const VelTail& vt,
+                                const GridConsts& g, const SolverConsts& c, int pow_mode, cudaStream_t st);
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
                       const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, const GridConsts& g,
                       const SolverConsts& c, cudaStream_t st);

@@ -15,6 +15,7 @@
 // never becomes -0.
 // More instruction slots per pair than solver.cu (shuffles, the list expansion), so the launchers take these
 // kernels only below TEAM_MAX_PARTICLES, where latency, not throughput, is the bound.
+#include "launch.cuh"
 #include "solver_common.cuh"
 
 namespace pbf {
@@ -135,9 +136,10 @@ template <bool SAVE_PAIRS, bool FAST_SPIKY>
 __global__ void __launch_bounds__(TEAM_THREADS, 8)
 lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
                    const uint2* __restrict__ cell_range, int64_t first, int64_t n,
-                   uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt, uint32_t* __restrict__ ovf_flag,
+                   uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
                    const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
                    const __grid_constant__ SolverConsts c) {
+    pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
     extern __shared__ uint32_t s_list[];
     const Team tm = team_of();
     const int64_t t = (int64_t)blockIdx.x * TEAM_PARTICLES + (threadIdx.x >> 2);
@@ -190,7 +192,6 @@ lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __re
     rho_out[i] = rho;
     if (SAVE_PAIRS) {
         pair_cnt[t] = pair_word(n_pairs, (uint32_t)(t % GATHER_THREADS));
-        if (n_pairs > PAIR_CAP) *ovf_flag = 1u;   // see PairList::ovf_flag
     }
 }
 
@@ -200,14 +201,26 @@ template <int POW>
 __global__ void __launch_bounds__(TEAM_THREADS, 16)
 delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                            const uint2* __restrict__ pair_js, const uint32_t* __restrict__ pair_cnt,
-                           const __grid_constant__ HaloPush hp, const __grid_constant__ SolverConsts c) {
+                           const uint2* __restrict__ cell_range, const __grid_constant__ HaloPush hp,
+                           const __grid_constant__ VelTail vt, const __grid_constant__ GridConsts g,
+                           const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     const Team tm = team_of();
     const int64_t t = (int64_t)blockIdx.x * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;
     const uint32_t cw = pair_cnt[t];   // (the team kernels do not re-bin: column t % GATHER_THREADS is particle t)
-    if (cw & PAIR_OVERFLOW) return;    // the gather kernel's particle
-    const uint32_t cnt = pair_count(cw);
     const int64_t i = first + t;
+    if (cw & PAIR_OVERFLOW) {          // more neighbours than the list holds: the plain pass, on the team's first lane
+        if (tm.lane == 0) {
+            const float4 out = delta_p_one<POW>(xl, (uint32_t)i, cell_range, g, c);
+            x_out[i] = out;
+            co.store(i, out);
+            halo_push(hp, t, out);
+            if (vt.v4) velocity_tail(vt, t, i, out);
+        }
+        return;
+    }
+    const uint32_t cnt = pair_count(cw);
     const float4 p = xl[i];
     const size_t pair0 = (size_t)(t / GATHER_THREADS) * PAIR_CAP * GATHER_THREADS + (size_t)(t % GATHER_THREADS);
     float ax = 0.f, ay = 0.f, az = 0.f;
@@ -238,6 +251,7 @@ delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x
     x_out[i] = out;
     co.store(i, out);
     halo_push(hp, t, out);
+    if (vt.v4) velocity_tail(vt, t, i, out);
 }
 
 // ---- XSPH ----------------------------------------------------------------------------------------------------
@@ -247,6 +261,7 @@ xsph_team_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* 
                  const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
                  const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
                  const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();
     extern __shared__ uint32_t s_list[];
     const Team tm = team_of();
     const int64_t t = (int64_t)blockIdx.x * TEAM_PARTICLES + (threadIdx.x >> 2);
@@ -300,33 +315,33 @@ cudaError_t preload_solver_team() {
 }
 
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, uint32_t* ovf_flag, const HaloPush& hp,
+                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp,
                         const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
     const unsigned nb = team_blocks(n);
     if (!pair_js && !c.fast_spiky)
-        lambda_team_kernel<false, false><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<false, false>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
     else if (!pair_js)
-        lambda_team_kernel<false, true><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, nullptr, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<false, true>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
     else if (!c.fast_spiky)
-        lambda_team_kernel<true, false><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, ovf_flag, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<true, false>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, g, c);
     else
-        lambda_team_kernel<true, true><<<nb, TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, ovf_flag, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<true, true>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, g, c);
 }
 
 void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut co, int64_t first, int64_t n, const uint2* pair_js,
-                                const uint32_t* pair_cnt, const HaloPush& hp, const SolverConsts& c, int pow_mode,
-                                cudaStream_t st) {
+                                const uint32_t* pair_cnt, const uint2* cell_range, const HaloPush& hp, const VelTail& vt,
+                                const GridConsts& g, const SolverConsts& c, int pow_mode, cudaStream_t st) {
     const unsigned nb = team_blocks(n);
-    if (pow_mode == 3) delta_p_replay_team_kernel<3><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
-    else if (pow_mode == 2) delta_p_replay_team_kernel<2><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
-    else if (pow_mode == 1) delta_p_replay_team_kernel<1><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
-    else delta_p_replay_team_kernel<0><<<nb, TEAM_THREADS, 0, st>>>(xl, x_out, co, first, n, pair_js, pair_cnt, hp, c);
+    if (pow_mode == 3) PBF_LAUNCH((delta_p_replay_team_kernel<3>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
+    else if (pow_mode == 2) PBF_LAUNCH((delta_p_replay_team_kernel<2>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
+    else if (pow_mode == 1) PBF_LAUNCH((delta_p_replay_team_kernel<1>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
+    else PBF_LAUNCH((delta_p_replay_team_kernel<0>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
 }
 
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
                       const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, const GridConsts& g,
                       const SolverConsts& c, cudaStream_t st) {
-    xsph_team_kernel<<<team_blocks(n), TEAM_THREADS, TEAM_SMEM, st>>>(x, soa, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+    PBF_LAUNCH((xsph_team_kernel), team_blocks(n), TEAM_THREADS, TEAM_SMEM, st, x, soa, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
 }
 
 }  // namespace pbf

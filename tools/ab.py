@@ -20,6 +20,7 @@ def child(scene, warm, steps):
     import torch
     bench = importlib.import_module("bench")
     pbf = importlib.import_module("pbf-cuda_b200")
+    torch.cuda.set_stream(torch.cuda.Stream())   # (a capturable stream: PBF_OPT_GRAPH)
     run = bench.ProductRun(pbf, torch, 0, scene)
     for _ in range(warm):
         run.step()
