@@ -163,6 +163,11 @@ struct pbf_sim {
     uint32_t* sync_words = nullptr;   // device: [0] raised by the left neighbour, [1] by the right one,
                                       // [2..3] int64 published by the left neighbour: its first right-ghost slot
     uint32_t halo_seq = 0;
+    // in-kernel handshakes of the fused halo (HaloSync, pbf_internal.h)
+    uint32_t* halo_done = nullptr;   // device: edge blocks finished, left / right (zero between kernels)
+    int64_t edge_left = 0, edge_right_first = 0;   // owned particles t < / >= these form the slab's two edges (HaloSync)
+    uint32_t wait_seq = 0;           // the handshake number of the last pushing pass: what the next reader waits for
+    bool wait_valid = false;
     uint64_t halo_timeout_ns = 10ull * 1000 * 1000 * 1000;
 
     // verified constant division (refresh_consts)
@@ -368,6 +373,7 @@ void free_all(pbf_sim* s) {
         for (void* b : pr.ipc_base)
             if (b) cudaIpcCloseMemHandle(b);
     cudaFree(s->sync_words);
+    cudaFree(s->halo_done);
     if (s->ev_valid) {
         for (auto& e : s->ev) cudaEventDestroy(e);
         for (auto& e : s->kev) cudaEventDestroy(e);
@@ -506,6 +512,7 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (const char* tm = getenv("PBF_TEAM")) s->mode.team = tm[0] == '1' ? 1 : tm[0] == '0' ? 0 : -1;
     if (const char* rb = getenv("PBF_REBIN")) s->mode.rebin = rb[0] == '1' ? 1 : 0;
     if (const char* pd = getenv("PBF_PDL")) s->mode.pdl = pd[0] == '0' ? 0 : 1;
+    if (const char* hk = getenv("PBF_HALO_INKERNEL")) s->mode.halo_inkernel = hk[0] == '0' ? 0 : 1;
     if (const char* gr = getenv("PBF_GRAPH")) s->mode.graph = gr[0] == '1' ? 1 : gr[0] == '0' ? 0 : -1;
 
     const size_t n = (size_t)max_particles;
@@ -544,6 +551,8 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (e == cudaSuccess) { *s->flags_host = 0; e = cudaHostGetDevicePointer((void**)&s->flags_dev, s->flags_host, 0); }
     A((void**)&s->sync_words, 8 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(s->sync_words, 0, 8 * sizeof(uint32_t));
+    A((void**)&s->halo_done, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->halo_done, 0, 2 * sizeof(uint32_t));
     // (the memset runs on the legacy stream; a neighbour's first flag store comes from a non-blocking
     //  stream and must not be overtaken by it)
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -610,6 +619,9 @@ int pbf_set_option(pbf_sim* s, int option, int value) {
         case PBF_OPT_PDL:
             s->mode.pdl = value ? 1 : 0;
             return PBF_OK;
+        case PBF_OPT_HALO_INKERNEL:
+            s->mode.halo_inkernel = value ? 1 : 0;
+            return PBF_OK;
         case PBF_OPT_GRAPH:
             if (value < -1 || value > 1) return fail(PBF_ERR_INVALID, "PBF_OPT_GRAPH takes -1, 0 or 1");
             s->mode.graph = value;
@@ -625,6 +637,7 @@ int pbf_get_option(const pbf_sim* s, int option, int* value) {
         case PBF_OPT_REBIN: *value = s->mode.rebin; return PBF_OK;
         case PBF_OPT_PDL: *value = s->mode.pdl; return PBF_OK;
         case PBF_OPT_GRAPH: *value = s->mode.graph; return PBF_OK;
+        case PBF_OPT_HALO_INKERNEL: *value = s->mode.halo_inkernel; return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
     }
 }
@@ -731,6 +744,15 @@ static int slab_learn_layout(pbf_sim* s) {
     L.send_left_count = ps[gl + gw_l] - ps[gl];
     L.send_right_count = ps[gl + nx] - ps[gl + nx - gw_r];
     L.flags = *s->flags_host;
+    // the edges of the in-kernel handshake: every owned particle whose neighbour search can reach a ghost plane.
+    // A particle drifts at most one cell per Jacobi iteration from the cell it was sorted into (MAX_DP, helper.h:9)
+    // and searches one cell further: niter + 1 planes — and at least the planes the neighbours mirror.
+    {
+        int w = s->p.niter + 1 > sl.ghost ? s->p.niter + 1 : sl.ghost;
+        if (w > nx) w = nx;
+        s->edge_left = sl.has_left ? ps[gl + w] - ps[gl] : 0;
+        s->edge_right_first = sl.has_right ? ps[gl + nx - w] - ps[gl] : L.own_count;
+    }
     s->n_local = L.n_local;
     s->own_first = L.own_first;
     s->own_count = L.own_count;
@@ -759,6 +781,55 @@ static int make_push(pbf_sim* s, const float4* a, HaloPush* hp) {
     return PBF_OK;
 }
 
+// The in-kernel handshake of one pass (HaloSync): `consumer` = its edge blocks read ghost slots the neighbours
+// filled in the last pushing pass; `producer` = it pushes boundary values itself, under a fresh handshake number.
+// Empty unless the neighbours are attached and PBF_OPT_HALO_INKERNEL is on.
+static bool inkernel_halo(const pbf_sim* s) {
+    return s->slab_on && s->mode.halo_inkernel && (s->peer[0].on || s->peer[1].on);
+}
+static void make_sync(pbf_sim* s, bool consumer, bool producer, HaloSync* hs) {
+    *hs = HaloSync();
+    if (!inkernel_halo(s) || !s->layout_valid) return;
+    const pbf_slab_layout& L = s->layout;
+    hs->edge_left = s->peer[0].on ? s->edge_left : 0;
+    hs->edge_right_first = s->peer[1].on ? s->edge_right_first : INT64_MAX;
+    (void)L;
+    hs->done = s->halo_done;
+    hs->timeout_ns = s->halo_timeout_ns;
+    hs->flags = s->flags_dev;
+    if (consumer && s->wait_valid) {
+        hs->wait_left = s->peer[0].on ? s->sync_words + 0 : nullptr;
+        hs->wait_right = s->peer[1].on ? s->sync_words + 1 : nullptr;
+        hs->wait_seq = s->wait_seq;
+    }
+    if (producer) {
+        s->halo_seq++;
+        // I am my left neighbour's RIGHT neighbour: its word [1]; and my right neighbour's word [0]
+        hs->peer_left = s->peer[0].on ? s->peer[0].sync + 1 : nullptr;
+        hs->peer_right = s->peer[1].on ? s->peer[1].sync + 0 : nullptr;
+        hs->signal_seq = s->halo_seq;
+        s->wait_seq = s->halo_seq;
+        s->wait_valid = true;
+    }
+}
+// A side whose edge is empty has no block that could raise the neighbour's word: a one-thread kernel does it.
+static int signal_empty_edges(pbf_sim* s, const HaloSync& hs) {
+    if (!hs.peer_left && !hs.peer_right) return PBF_OK;
+    const bool none = s->own_count <= 0;
+    uint32_t* l = hs.peer_left && (none || hs.edge_left <= 0) ? hs.peer_left : nullptr;
+    uint32_t* r = hs.peer_right && (none || hs.edge_right_first >= s->own_count) ? hs.peer_right : nullptr;
+    if (l || r) CUDA_TRY(launch_halo_signal(l, r, hs.signal_seq, s->stream, &s->launches));
+    return PBF_OK;
+}
+// the ghost slots' coordinates for the cull (the owned slots' came with the pass that produced `x`)
+static int pack_ghosts_if_needed(pbf_sim* s, const float4* x) {
+    if (!inkernel_halo(s) || s->cull.holds == x || !s->wait_valid) return PBF_OK;
+    HaloSync hs;
+    make_sync(s, true, false, &hs);
+    CUDA_TRY(launch_pack_ghosts(x, s->cull, s->n_local, s->own_first, s->own_count, hs, s->stream, &s->launches));
+    return PBF_OK;
+}
+
 int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, uint32_t* iid, int64_t n,
                     void* stream) {
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
@@ -778,6 +849,7 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
     s->si.n_own = n;
     s->n_local = n; s->own_first = 0; s->own_count = n;
     s->layout_valid = false;
+    s->wait_valid = false;
     s->cur = 0;
     s->iters_done = 0;
     s->pos0_in_npos = false;
@@ -836,7 +908,11 @@ int pbf_stage_lambda(pbf_sim* s) {
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
     s->mode.moved = s->iters_done > 0;   // the first iteration runs on the positions the sort keyed on
-    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, s->g, s->c, s->mode, s->stream, &s->launches));
+    if (s->iters_done > 0 && (prc = pack_ghosts_if_needed(s, s->x[s->cur]))) return prc;
+    HaloSync hs;
+    make_sync(s, false, true, &hs);
+    KTIMED(PBF_KERNEL_LAMBDA, launch_lambda(s->x[s->cur], s->cull, s->n_local, s->xl, s->rho, s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, hs, s->g, s->c, s->mode, s->stream, &s->launches));
+    if ((prc = signal_empty_edges(s, hs))) return prc;
     s->stage = ST_LAMBDA;
     return PBF_OK;
 }
@@ -855,7 +931,10 @@ int pbf_stage_delta_p(pbf_sim* s) {
         vt.rho = s->rho; vt.pos_out = s->pos; vt.npos_io = s->npos; vt.vel_out = s->vel; vt.v4 = s->x[s->cur];
         vt.inv_dt = s->c.inv_dt;
     }
-    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, vt, s->g, s->c, s->mode, s->stream, &s->launches));
+    HaloSync hs;
+    make_sync(s, true, true, &hs);
+    KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, hs, vt, s->g, s->c, s->mode, s->stream, &s->launches));
+    if ((prc = signal_empty_edges(s, hs))) return prc;
     s->cur ^= 1;
     s->iters_done++;
     s->stage = ST_DENSITY;
@@ -883,7 +962,12 @@ int pbf_stage_update_velocity(pbf_sim* s) {
     HaloPush hp;
     int prc = make_push(s, s->xl, &hp);
     if (prc) return prc;
-    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, hp, s->c, s->stream, &s->launches));
+    // (a reader too: its pushes overwrite the (x, y, z, lambda) the neighbours' last delta-p pass gathered from
+    //  their ghost slots, so its edge blocks wait for that pass's completion word first)
+    HaloSync hs;
+    make_sync(s, true, true, &hs);
+    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, hp, hs, s->c, s->stream, &s->launches));
+    if ((prc = signal_empty_edges(s, hs))) return prc;
     s->v4 = s->xl;
     s->pos0_in_npos = false;
     s->stage = ST_VELOCITY;
@@ -894,7 +978,11 @@ int pbf_stage_correct_velocity(pbf_sim* s) {
     STAGE_ENTER(s);
     if (!s || s->stage != ST_VELOCITY) return fail(PBF_ERR_STATE, "correct_velocity: update_velocity first");
     s->mode.moved = s->iters_done > 0;
-    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->v4, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, s->g, s->c, s->mode, s->stream, &s->launches));
+    int prc = s->iters_done > 0 ? pack_ghosts_if_needed(s, s->x[s->cur]) : PBF_OK;
+    if (prc) return prc;
+    HaloSync hs;
+    make_sync(s, true, false, &hs);
+    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->v4, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, hs, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
 }
@@ -1083,7 +1171,7 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     for (int64_t k = 0; k < slices && n > 0; k++) {
         const int64_t a = n * k / slices, b = n * (k + 1) / slices;
         CUDA_TRY(launch_xsph(s->x[s->cur], s->cull, k == 0 ? s->n_local : 0, s->v4, s->cell_range, s->nvel + 3 * a,
-                             s->iid_sorted, s->iid + a, a, b - a, s->g, s->c, s->mode, st, &s->launches));
+                             s->iid_sorted, s->iid + a, a, b - a, HaloSync(), s->g, s->c, s->mode, st, &s->launches));
         CUDA_TRY(cudaEventRecord(s->host_ev, st));
         CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
         CUDA_TRY(cudaMemcpyAsync(nvel + 3 * a, s->h_nvel + 3 * a, (size_t)(b - a) * 12, cudaMemcpyDeviceToHost, s->host_copy));
@@ -1265,6 +1353,7 @@ static int peers_signal(pbf_sim* s) {
 int pbf_slab_halo_sync(pbf_sim* s) {
     if (!s) return fail(PBF_ERR_INVALID, "null handle");
     if (!s->peer[0].on && !s->peer[1].on) return PBF_OK;
+    if (inkernel_halo(s)) return PBF_OK;   // the pass kernels signalled, the next reader's edge blocks wait (HaloSync)
     int rc = peers_signal(s);
     if (rc) return rc;
     CUDA_TRY(launch_halo_wait(s->peer[0].on ? s->sync_words + 0 : nullptr, s->peer[1].on ? s->sync_words + 1 : nullptr,

@@ -111,6 +111,48 @@ __device__ __forceinline__ void halo_push(const HaloPush& hp, int64_t t, const f
     if (hp.right && t >= hp.right_first) hp.right[t - hp.right_first] = v;
 }
 
+// In-kernel handshake of the fused halo (slab mode with attached peers; everything zero / null otherwise).
+// Only the particles of a slab's first and last `ghost` planes — its two EDGES — exchange anything with a
+// neighbour: they are the ones whose results are pushed into the neighbour's ghost slots, and the only ones whose
+// neighbour search can reach this rank's own ghost slots. So
+//   * a pass kernel runs its edge blocks FIRST (left edge, right edge, then the interior): the values the
+//     neighbours are waiting for leave at the start of the kernel, not at its end;
+//   * when the last edge block of a side has pushed, that block tells the neighbour of that side "refresh
+//     signal_seq complete" (a release store over NVLink) — no signalling kernel;
+//   * before an edge block reads ghost slots it waits until that side's neighbour has reported wait_seq (an
+//     acquire spin with a time-out) — no waiting kernel; interior blocks never wait, so a late neighbour is hidden
+//     behind interior work.
+// Correctness of the ghost slots' reuse (a neighbour overwrites them in the next pass): a side is signalled only
+// after this rank's edge blocks of that side — the only readers of those ghost slots — have finished.
+struct HaloSync {
+    int64_t edge_left = 0;                  // owned t <  edge_left        : left edge  (0: none)
+    int64_t edge_right_first = INT64_MAX;   // owned t >= edge_right_first : right edge
+    const uint32_t* wait_left = nullptr;    // local words the neighbours raise (consumer side), or null
+    const uint32_t* wait_right = nullptr;
+    uint32_t wait_seq = 0;
+    uint32_t* peer_left = nullptr;          // the neighbours' words this rank raises (producer side), or null
+    uint32_t* peer_right = nullptr;
+    uint32_t signal_seq = 0;
+    uint32_t* done = nullptr;               // two device counters (left, right edge blocks finished), zero between kernels
+    uint64_t timeout_ns = 0;
+    uint32_t* flags = nullptr;              // PBF_SLAB_FLAG_TIMEOUT goes here
+    // filled by the launcher for its block size (particles per block)
+    uint32_t nb = 0, nb_left = 0, nb_right = 0;
+    bool on() const { return wait_left || wait_right || peer_left || peer_right; }
+};
+// blocks of `per_block` particles over n owned particles: which are edges. A slab so thin that the edges meet
+// makes every block both.
+inline void halo_sync_blocks(HaloSync& hs, int64_t n, int per_block) {
+    hs.nb = hs.nb_left = hs.nb_right = 0;
+    if (!hs.on() || n <= 0) return;
+    const int64_t nb = (n + per_block - 1) / per_block;
+    int64_t l = hs.edge_left > 0 ? (hs.edge_left + per_block - 1) / per_block : 0;
+    int64_t r = hs.edge_right_first < n ? nb - (hs.edge_right_first < 0 ? 0 : hs.edge_right_first / per_block) : 0;
+    if (l > nb) l = nb;
+    if (l + r > nb) l = r = nb;
+    hs.nb = (uint32_t)nb; hs.nb_left = (uint32_t)l; hs.nb_right = (uint32_t)r;
+}
+
 // ---- launchers (each returns the CUDA error of its launches) ---------------------------
 
 // advect + cell key + per-pass digit histograms, in input order (advect_key.cu)
@@ -176,6 +218,7 @@ struct SweepMode {
     int rebin = 0;   // thread kernels: re-deal a block's particles by CURRENT home cell once the iterate has moved
                      // (measured: no gain, DESIGN.md 3.7 — off by default, kept selectable for the A/B)
     int pdl = 1;     // programmatic dependent launch between the step's kernels (launch.cuh)
+    int halo_inkernel = 1;   // fused halo: handshakes inside the pass kernels (HaloSync) instead of two one-thread kernels per refresh
     int graph = -1;  // pbf_step replayed from a CUDA graph: -1 below 256 K particles, 0 never, 1 always (pbf_capi.cu)
     bool moved = false;   // set per launch by the stage functions: the iterate is not the one the sort keyed on
 };
@@ -192,14 +235,14 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
 // slot; caller-facing arrays (pos/npos/vel/nvel/iid) and the pair list by slot - first.
 // `n_slots` = every slot the handle stores (ghosts included): the sweeps' cull reads them all.
 cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
-                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const HaloSync& hs,
                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
-                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const VelTail& vt, const GridConsts& g,
-                           const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
+                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const HaloSync& hs, const VelTail& vt,
+                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
-                                   const SolverConsts& c, cudaStream_t st, int64_t* launches);
+                                   const HaloSync& hs, const SolverConsts& c, cudaStream_t st, int64_t* launches);
 // slab.cu: flag handshake of a fused halo refresh. signal: store `seq` (release, system scope) to
 // a word in a peer's memory; wait: spin until the local word reaches `seq`, give up after
 // `timeout_ns` and raise PBF_SLAB_FLAG_TIMEOUT instead of hanging the device.
@@ -213,8 +256,13 @@ cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_rig
                              uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches);
 cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
-                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, const SweepMode& mode,
-                        cudaStream_t st, int64_t* launches);
+                        int64_t first, int64_t n, const HaloSync& hs, const GridConsts& g, const SolverConsts& c,
+                        const SweepMode& mode, cudaStream_t st, int64_t* launches);
+// slab mode with in-kernel halo handshakes: the cull's coordinates of the GHOST slots [0, own_first) and
+// [own_first + own_count, n_slots) of `x` (the owned slots were written by the pass that produced x); its blocks
+// wait for the neighbours' wait_seq first
+cudaError_t launch_pack_ghosts(const float4* x, CullScratch& cs, int64_t n_slots, int64_t own_first, int64_t own_count,
+                               const HaloSync& hs, cudaStream_t st, int64_t* launches);
 // slab.cu: first slot of every local plane in the sorted pairs (nxl + 1 entries, the last one =
 // number of particles inside the local plane range; the rest carry the discard key)
 cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,

@@ -164,6 +164,27 @@ pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restr
     zs[i] = q.z;
 }
 
+// the same for the GHOST slots only — [0, own_first) and [own_first + own_count, n) — once the neighbours have
+// reported that their pushes into them are complete (HaloSync; every block waits for both sides: the signal
+// left the neighbours' kernels long ago, see the block order there)
+__global__ void __launch_bounds__(256)
+pack_ghosts_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restrict__ ys, float* __restrict__ zs,
+                   int64_t own_first, int64_t own_count, int64_t n, const __grid_constant__ HaloSync hs) {
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        if (hs.wait_left) halo_spin(hs.wait_left, hs.wait_seq, hs.timeout_ns, hs.flags);
+        if (hs.wait_right) halo_spin(hs.wait_right, hs.wait_seq, hs.timeout_ns, hs.flags);
+    }
+    __syncthreads();
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t i = k < own_first ? k : k + own_count;
+    if (i >= n) return;
+    const float4 q = x[i];
+    xs[i] = q.x;
+    ys[i] = q.y;
+    zs[i] = q.z;
+}
+
 // ---- re-binning a block's particles by their CURRENT home cell -------------------------------------------
 // The reference re-derives a particle's home cell from the current iterate (Simulator_kernel.cuh:70,148,212), so
 // after the first Jacobi iteration 12-17 % of the particles per axis search the neighbourhood of a cell that is
@@ -176,10 +197,10 @@ pack_kernel(const float4* __restrict__ x, float* __restrict__ xs, float* __restr
 // Rank by counting over 32-bit words (cell key relative to the block's smallest, clamped to 25 bits | local
 // slot): ~290 instructions per thread against ~5000 of the sweep. A key beyond the clamp only groups worse.
 // Returns the local index (0..GATHER_THREADS-1) of the particle this thread takes; all threads of the block call.
-__device__ __forceinline__ uint32_t rebin_block(const float4* __restrict__ x, int64_t first, int64_t n, const GridConsts& g,
-                                                uint32_t* __restrict__ s_re /* GATHER_THREADS + 4 words */) {
+__device__ __forceinline__ uint32_t rebin_block(const float4* __restrict__ x, int64_t first, int64_t n, uint32_t block,
+                                                const GridConsts& g, uint32_t* __restrict__ s_re /* GATHER_THREADS + 4 words */) {
     const uint32_t tid = threadIdx.x;
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + tid;
+    const int64_t t = (int64_t)block * GATHER_THREADS + tid;
     uint32_t key = 0x3fffffffu;   // past the end of the range: sorts last
     if (t < n) {
         const float4 p = x[first + t];
@@ -227,13 +248,14 @@ __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
               uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
-              const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
-              const __grid_constant__ SolverConsts c) {
+              const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
+              const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     pdl_wait();
     extern __shared__ uint2 s_words[];
     __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
-    const uint32_t local = REBIN ? rebin_block(x, first, n, g, s_re) : threadIdx.x;   // which particle of the block
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + local;
+    const uint32_t lb = halo_block(hs);   // (slab mode: the edge blocks first; blockIdx.x otherwise)
+    const uint32_t local = REBIN ? rebin_block(x, first, n, lb, g, s_re) : threadIdx.x;   // which particle of the block
+    const int64_t t = (int64_t)lb * GATHER_THREADS + local;
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 p = x[i];
@@ -242,7 +264,7 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     // nothing else (spiky is 0 below KERNAL_EPS, and gradj skips j == i). Taking it out of the
     // general path keeps three 0/rho0 divisions off IEEE division's slow path in every warp.
     const float w_self = poly6_in(0.f, c);
-    const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
+    const size_t pair0 = (size_t)lb * PAIR_CAP * GATHER_THREADS + threadIdx.x;
     int n_pairs = 0;
     gather<false>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
         if (j == (uint32_t)i) {
@@ -276,8 +298,9 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     halo_push(hp, t, out);
     rho_out[i] = rho;
     if (SAVE_PAIRS) {   // the list lives in THIS THREAD's column (coalesced records); the word says whose it is
-        pair_cnt[(int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x] = pair_word(n_pairs, local);
+        pair_cnt[(int64_t)lb * GATHER_THREADS + threadIdx.x] = pair_word(n_pairs, local);
     }
+    halo_exit(hs, lb);
 }
 
 // The delta-p pass comes as two kernels. The REPLAY kernel walks the neighbour list the lambda pass saved:
@@ -299,45 +322,46 @@ __global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
 delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                       const uint2* __restrict__ pair_js,
                       const uint32_t* __restrict__ pair_cnt, const uint2* __restrict__ cell_range,
-                      const __grid_constant__ HaloPush hp, const __grid_constant__ VelTail vt,
-                      const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+                      const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
+                      const __grid_constant__ VelTail vt, const __grid_constant__ GridConsts g,
+                      const __grid_constant__ SolverConsts c) {
     pdl_wait();
-    const int64_t col = (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;   // list column; its word names the particle
+    const uint32_t lb = halo_block(hs);
+    halo_enter(hs, lb);   // (edge blocks: the neighbours' lambdas of this iteration are in the ghost slots of xl)
+    const int64_t col = (int64_t)lb * GATHER_THREADS + threadIdx.x;   // list column; its word names the particle
     if (col >= n) return;
     const uint32_t cw = pair_cnt[col];
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + pair_local(cw);
-    if (t >= n) return;   // (a column past the end)
+    const int64_t t = (int64_t)lb * GATHER_THREADS + pair_local(cw);
+    if (t >= n) return;   // (cannot happen: a column below n names a particle below n)
     const int64_t i = first + t;
+    float4 out;
     if (cw & PAIR_OVERFLOW) {   // more neighbours than the list holds: the plain pass for this one particle
-        const float4 out = delta_p_one<POW>(xl, (uint32_t)i, cell_range, g, c);
-        x_out[i] = out;
-        co.store(i, out);
-        halo_push(hp, t, out);
-        if (vt.v4) velocity_tail(vt, t, i, out);
-        return;
-    }
-    const uint32_t cnt = pair_count(cw);
-    const float4 p = xl[i];
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    const size_t pair0 = (size_t)blockIdx.x * PAIR_CAP * GATHER_THREADS + threadIdx.x;
+        out = delta_p_one<POW>(xl, (uint32_t)i, cell_range, g, c);
+    } else {
+        const uint32_t cnt = pair_count(cw);
+        const float4 p = xl[i];
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        const size_t pair0 = (size_t)lb * PAIR_CAP * GATHER_THREADS + threadIdx.x;
 #pragma unroll (POW == 3 ? REPLAY_UNROLL3 : 4)
-    for (uint32_t k = 0; k < cnt; k++) {
-        const size_t e = pair0 + (size_t)k * GATHER_THREADS;
-        const uint2 js = __ldg(&pair_js[e]);
-        const float4 q = __ldg(&xl[js.x]);
-        const float sj = __uint_as_float(js.y);  // spiky scale of the pair, saved by the lambda pass
-        const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-        const float pw = pow_ncorr<POW>(poly6(sumsq(dx, dy, dz), c), c);
-        const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-        ax = __fmaf_rn(sc, __fmul_rn(dx, sj), ax);
-        ay = __fmaf_rn(sc, __fmul_rn(dy, sj), ay);
-        az = __fmaf_rn(sc, __fmul_rn(dz, sj), az);
+        for (uint32_t k = 0; k < cnt; k++) {
+            const size_t e = pair0 + (size_t)k * GATHER_THREADS;
+            const uint2 js = __ldg(&pair_js[e]);
+            const float4 q = __ldg(&xl[js.x]);
+            const float sj = __uint_as_float(js.y);  // spiky scale of the pair, saved by the lambda pass
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            const float pw = pow_ncorr<POW>(poly6(sumsq(dx, dy, dz), c), c);
+            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+            ax = __fmaf_rn(sc, __fmul_rn(dx, sj), ax);
+            ay = __fmaf_rn(sc, __fmul_rn(dy, sj), ay);
+            az = __fmaf_rn(sc, __fmul_rn(dz, sj), az);
+        }
+        out = delta_p_finish(p, ax, ay, az, c);
     }
-    const float4 out = delta_p_finish(p, ax, ay, az, c);
     x_out[i] = out;
     co.store(i, out);
     halo_push(hp, t, out);
     if (vt.v4) velocity_tail(vt, t, i, out);   // the step's last pass: the velocity update rides along
+    halo_exit(hs, lb);
 }
 
 // The delta-p pass WITHOUT a neighbour list (the list is optional scratch: PBF_NO_PAIR_REUSE=1, or a handle too
@@ -346,13 +370,15 @@ template <int POW, bool REBIN>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restrict__ x_out, const CullOut co,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n, const __grid_constant__ HaloPush hp,
-               const __grid_constant__ VelTail vt, const __grid_constant__ GridConsts g,
-               const __grid_constant__ SolverConsts c) {
+               const __grid_constant__ HaloSync hs, const __grid_constant__ VelTail vt,
+               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     pdl_wait();
     extern __shared__ uint2 s_words[];
     __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
-    const uint32_t local = REBIN ? rebin_block(xl, first, n, g, s_re) : threadIdx.x;
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + local;
+    const uint32_t lb = halo_block(hs);
+    halo_enter(hs, lb);
+    const uint32_t local = REBIN ? rebin_block(xl, first, n, lb, g, s_re) : threadIdx.x;
+    const int64_t t = (int64_t)lb * GATHER_THREADS + local;
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 p = xl[i];
@@ -372,6 +398,7 @@ delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restr
     co.store(i, out);   // (reads of this iteration's coordinates go to `soa` = the OTHER set of arrays)
     halo_push(hp, t, out);
     if (vt.v4) velocity_tail(vt, t, i, out);
+    halo_exit(hs, lb);
 }
 
 // vel = (npos - pos) * inv_dt, plus everything the caller-facing buffers need from this point:
@@ -380,9 +407,12 @@ __global__ void __launch_bounds__(256)
 update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ rho,
                        float* __restrict__ pos_out, float* __restrict__ npos_io,
                        float* __restrict__ vel_out, float4* __restrict__ v4, int64_t first, int64_t n,
-                       const __grid_constant__ HaloPush hp, const __grid_constant__ SolverConsts c) {
+                       const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
+                       const __grid_constant__ SolverConsts c) {
     pdl_wait();
-    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t lb = halo_block(hs);
+    halo_enter(hs, lb);   // (edge blocks: the neighbours are done with what this kernel's pushes overwrite)
+    const int64_t t = (int64_t)lb * 256 + threadIdx.x;
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 q = x[i];
@@ -396,6 +426,7 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
     store_f3(vel_out, t, vx, vy, vz);
     store_f3(pos_out, t, p0.x, p0.y, p0.z);
     store_f3(npos_io, t, q.x, q.y, q.z);
+    halo_exit(hs, lb);
 }
 
 template <bool REBIN>
@@ -403,12 +434,15 @@ __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
-            const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+            const __grid_constant__ HaloSync hs, const __grid_constant__ GridConsts g,
+            const __grid_constant__ SolverConsts c) {
     pdl_wait();
     extern __shared__ uint2 s_words[];
     __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
-    const uint32_t local = REBIN ? rebin_block(x, first, n, g, s_re) : threadIdx.x;
-    const int64_t t = (int64_t)blockIdx.x * GATHER_THREADS + local;
+    const uint32_t lb = halo_block(hs);
+    halo_enter(hs, lb);   // (edge blocks: the neighbours' velocities are in the ghost slots of v4)
+    const uint32_t local = REBIN ? rebin_block(x, first, n, lb, g, s_re) : threadIdx.x;
+    const int64_t t = (int64_t)lb * GATHER_THREADS + local;
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 p = x[i];
@@ -475,6 +509,7 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, neighbor_count_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_ghosts_kernel);
     if (e == cudaSuccess) e = preload_solver_team();
     return e;
 }
@@ -495,6 +530,19 @@ static cudaError_t launch_pack(const float4* x, CullScratch& cs, int64_t n_slots
     cs.holds = x;
     return cudaGetLastError();
 }
+cudaError_t launch_pack_ghosts(const float4* x, CullScratch& cs, int64_t n_slots, int64_t own_first, int64_t own_count,
+                               const HaloSync& hs, cudaStream_t st, int64_t* launches) {
+    // the pass that produced x wrote the owned slots' coordinates into the OTHER set: switch to it, add the ghosts
+    cs.cur ^= 1;
+    cs.holds = x;
+    // (launched even without ghost slots: its wait is also what lets this rank's NEXT pass overwrite the
+    //  neighbours' ghost slots — they have finished reading them)
+    const int64_t ghosts = n_slots - own_count > 0 ? n_slots - own_count : 1;
+    PBF_LAUNCH((pack_ghosts_kernel), nblocks(ghosts, 256), 256, 0, st, x, cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur], own_first, own_count,
+               n_slots, hs);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
 static inline CullSoA soa_of(const CullScratch& cs) { return CullSoA{cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur]}; }
 static inline CullOut out_of(const CullScratch& cs) { return CullOut{cs.xs[cs.cur ^ 1], cs.ys[cs.cur ^ 1], cs.zs[cs.cur ^ 1]}; }
 
@@ -506,26 +554,28 @@ size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_byte
 }
 
 cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, float4* xl, float* rho,
-                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp,
+                          const uint2* cell_range, int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const HaloSync& hs_in,
                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
     if (pe != cudaSuccess) return pe;
     const CullSoA soa = soa_of(cs);
     if (use_team(mode, n)) {
-        launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, g, c, st);
+        launch_lambda_team(x, soa, xl, rho, cell_range, first, n, pl.js, pl.cnt, hp, hs_in, g, c, st);
         if (launches) (*launches)++;
         return cudaGetLastError();
     }
     const unsigned nb = nblocks(n, GATHER_THREADS);
+    HaloSync hs = hs_in;
+    halo_sync_blocks(hs, n, GATHER_THREADS);
 #define PBF_LAMBDA_LAUNCH(SAVE, FAST)                                                                                          \
     do {                                                                                                                       \
         if (mode.rebin && mode.moved)                                                                                          \
             PBF_LAUNCH((lambda_kernel<SAVE, FAST, true>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n,       \
-                                                                                 pl.js, pl.cnt, hp, g, c);                   \
+                                                                                 pl.js, pl.cnt, hp, hs, g, c);               \
         else                                                                                                                   \
             PBF_LAUNCH((lambda_kernel<SAVE, FAST, false>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n,      \
-                                                                                  pl.js, pl.cnt, hp, g, c);                  \
+                                                                                  pl.js, pl.cnt, hp, hs, g, c);              \
     } while (0)
     if (!pl.js && !c.fast_spiky) PBF_LAMBDA_LAUNCH(false, false);
     else if (!pl.js) PBF_LAMBDA_LAUNCH(false, true);
@@ -538,8 +588,8 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
 
 // (`cs` holds the positions the lambda pass of this iteration packed: the same ones xl carries)
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
-                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const VelTail& vt, const GridConsts& g,
-                           const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
+                           int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const HaloSync& hs_in, const VelTail& vt,
+                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     const CullSoA soa = soa_of(cs);   // this iteration's coordinates: what the overflow kernel culls on
     const CullOut co = out_of(cs);    // the other set receives the coordinates of x_out
@@ -547,16 +597,18 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
     // exponent folded (same bits; when 3 did not verify or is switched off); 1: powf, any exponent; 0: (w*w)^2
     const int pow_mode = c.n_corr == 4.0f ? (c.exact_pow ? (c.trim_pow ? 3 : 2) : 0) : 1;
     const unsigned nb = nblocks(n, GATHER_THREADS);
+    HaloSync hs = hs_in;
+    halo_sync_blocks(hs, n, GATHER_THREADS);
 #define PBF_DP_LAUNCH(POW)                                                                                                    \
     do {                                                                                                                      \
         if (pl.js) {                                                                                                          \
-            if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, cell_range, hp, vt, g, c, POW, st); \
+            if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, cell_range, hp, hs_in, vt, g, c, POW, st); \
             else PBF_LAUNCH((delta_p_replay_kernel<POW>), nb, GATHER_THREADS, 0, st, xl, x_out, co, first, n, pl.js, pl.cnt,  \
-                            cell_range, hp, vt, g, c);                                                                       \
+                            cell_range, hp, hs, vt, g, c);                                                                   \
         } else if (mode.rebin && mode.moved) {                                                                                \
-            PBF_LAUNCH((delta_p_kernel<POW, true>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, vt, g, c); \
+            PBF_LAUNCH((delta_p_kernel<POW, true>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, hs, vt, g, c); \
         } else {                                                                                                              \
-            PBF_LAUNCH((delta_p_kernel<POW, false>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, vt, g, c); \
+            PBF_LAUNCH((delta_p_kernel<POW, false>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, hs, vt, g, c); \
         }                                                                                                                     \
     } while (0)
     if (pow_mode == 3) PBF_DP_LAUNCH(3);
@@ -571,16 +623,18 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
         cs.cur ^= 1;
         cs.holds = x_out;
     } else {
-        cs.holds = nullptr;
+        cs.holds = nullptr;   // (slab mode: launch_pack_ghosts, or a full pack, completes the set before the next sweep)
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
-                                   const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+                                   const HaloSync& hs_in, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
-    PBF_LAUNCH((update_velocity_kernel), nblocks(n, 256), 256, 0, st, x, rho, pos_out, npos_io, vel_out, v4, first, n, hp, c);
+    HaloSync hs = hs_in;
+    halo_sync_blocks(hs, n, 256);
+    PBF_LAUNCH((update_velocity_kernel), nblocks(n, 256), 256, 0, st, x, rho, pos_out, npos_io, vel_out, v4, first, n, hp, hs, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -588,22 +642,24 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
 // n_slots > 0: refresh the cull's coordinate arrays first; 0: they are current (a further chunk of the same sweep)
 cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
-                        int64_t first, int64_t n, const GridConsts& g, const SolverConsts& c, const SweepMode& mode,
-                        cudaStream_t st, int64_t* launches) {
+                        int64_t first, int64_t n, const HaloSync& hs_in, const GridConsts& g, const SolverConsts& c,
+                        const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     if (n_slots > 0) {
         cudaError_t pe = launch_pack(x, cs, n_slots, st, launches);
         if (pe != cudaSuccess) return pe;
     }
     if (use_team(mode, n)) {
-        launch_xsph_team(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c, st);
+        launch_xsph_team(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs_in, g, c, st);
         if (launches) (*launches)++;
         return cudaGetLastError();
     }
+    HaloSync hs = hs_in;
+    halo_sync_blocks(hs, n, GATHER_THREADS);
     if (mode.rebin && mode.moved)
-        PBF_LAUNCH((xsph_kernel<true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+        PBF_LAUNCH((xsph_kernel<true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
     else
-        PBF_LAUNCH((xsph_kernel<false>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+        PBF_LAUNCH((xsph_kernel<false>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

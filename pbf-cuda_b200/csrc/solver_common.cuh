@@ -116,6 +116,62 @@ __device__ __forceinline__ float4 delta_p_finish(const float4 p, float ax, float
     return make_float4(qx, qy, qz, 0.f);
 }
 
+// ---- HaloSync (pbf_internal.h): the in-kernel handshake of the fused halo -------------------------------------
+// logical block of this CTA: the edges first (see HaloSync)
+__device__ __forceinline__ uint32_t halo_block(const HaloSync& hs) {
+    const uint32_t b = blockIdx.x;
+    if (hs.nb == 0 || b < hs.nb_left) return b;
+    if (b < hs.nb_left + hs.nb_right) return hs.nb - hs.nb_right + (b - hs.nb_left);
+    return b - hs.nb_right;
+}
+__device__ __forceinline__ bool halo_is_left(const HaloSync& hs, uint32_t lb) { return lb < hs.nb_left; }
+__device__ __forceinline__ bool halo_is_right(const HaloSync& hs, uint32_t lb) { return hs.nb_right && lb >= hs.nb - hs.nb_right; }
+__device__ __forceinline__ void halo_spin(const uint32_t* w, uint32_t seq, uint64_t timeout_ns, uint32_t* flags) {
+    uint64_t t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+        if ((int32_t)(v - seq) >= 0) return;   // (int32 difference: the sequence number may wrap)
+        uint64_t t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {            // a dead neighbour must not hang the device
+            if (flags) atomicOr(flags, (uint32_t)PBF_SLAB_FLAG_TIMEOUT);
+            return;
+        }
+        __nanosleep(64);
+    }
+}
+// consumer side: called by ALL threads of the block before anything reads a ghost slot
+__device__ __forceinline__ void halo_enter(const HaloSync& hs, uint32_t lb) {
+    const bool wl = hs.wait_left && halo_is_left(hs, lb), wr = hs.wait_right && halo_is_right(hs, lb);
+    if (!(wl || wr)) return;   // (uniform in the block)
+    if (threadIdx.x == 0) {
+        if (wl) halo_spin(hs.wait_left, hs.wait_seq, hs.timeout_ns, hs.flags);
+        if (wr) halo_spin(hs.wait_right, hs.wait_seq, hs.timeout_ns, hs.flags);
+    }
+    __syncthreads();
+}
+// producer side: called by every thread of the block that is still alive, behind its last push (thread 0 always is)
+__device__ __forceinline__ void halo_exit(const HaloSync& hs, uint32_t lb) {
+    const bool sl = hs.peer_left && halo_is_left(hs, lb), sr = hs.peer_right && halo_is_right(hs, lb);
+    if (!(sl || sr)) return;   // (uniform in the block)
+    __threadfence_system();    // my pushes are performed before ...
+    __syncthreads();           // ... thread 0 counts the block as done
+    if (threadIdx.x == 0) {
+        if (sl && atomicAdd(hs.done + 0, 1u) == hs.nb_left - 1) {
+            hs.done[0] = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hs.peer_left), "r"(hs.signal_seq) : "memory");
+        }
+        if (sr && atomicAdd(hs.done + 1, 1u) == hs.nb_right - 1) {
+            hs.done[1] = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hs.peer_right), "r"(hs.signal_seq) : "memory");
+        }
+    }
+}
+
 // VelTail (pbf_internal.h): the velocity update of particle t (slot i) right behind its final position `q`
 __device__ __forceinline__ void velocity_tail(const VelTail& vt, int64_t t, int64_t i, const float4 q) {
     const float3 p0 = load_f3(vt.npos_io, t);
@@ -180,13 +236,13 @@ __device__ __noinline__ float4 delta_p_one(const float4* __restrict__ xl, uint32
 constexpr int64_t TEAM_MAX_PARTICLES = 48 * 1024;
 cudaError_t preload_solver_team();
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp,
+                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp, HaloSync hs,
                         const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut co, int64_t first, int64_t n, const uint2* pair_js,
-                                const uint32_t* pair_cnt, const uint2* cell_range, const HaloPush& hp, const VelTail& vt,
-                                const GridConsts& g, const SolverConsts& c, int pow_mode, cudaStream_t st);
+                                const uint32_t* pair_cnt, const uint2* cell_range, const HaloPush& hp, HaloSync hs,
+                                const VelTail& vt, const GridConsts& g, const SolverConsts& c, int pow_mode, cudaStream_t st);
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
-                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, const GridConsts& g,
-                      const SolverConsts& c, cudaStream_t st);
+                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, HaloSync hs,
+                      const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 
 }  // namespace pbf

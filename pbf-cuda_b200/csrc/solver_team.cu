@@ -137,12 +137,13 @@ __global__ void __launch_bounds__(TEAM_THREADS, 8)
 lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
                    const uint2* __restrict__ cell_range, int64_t first, int64_t n,
                    uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
-                   const __grid_constant__ HaloPush hp, const __grid_constant__ GridConsts g,
-                   const __grid_constant__ SolverConsts c) {
+                   const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
+                   const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
     extern __shared__ uint32_t s_list[];
     const Team tm = team_of();
-    const int64_t t = (int64_t)blockIdx.x * TEAM_PARTICLES + (threadIdx.x >> 2);
+    const uint32_t lb = halo_block(hs);   // (slab mode: the edge blocks first, see HaloSync)
+    const int64_t t = (int64_t)lb * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;   // whole teams leave together
     const int64_t i = first + t;
     const float4 p = x[i];
@@ -193,6 +194,7 @@ lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __re
     if (SAVE_PAIRS) {
         pair_cnt[t] = pair_word(n_pairs, (uint32_t)(t % GATHER_THREADS));
     }
+    halo_exit(hs, lb);
 }
 
 // ---- delta-p replay ----------------------------------------------------------------------------------------
@@ -202,56 +204,54 @@ __global__ void __launch_bounds__(TEAM_THREADS, 16)
 delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                            const uint2* __restrict__ pair_js, const uint32_t* __restrict__ pair_cnt,
                            const uint2* __restrict__ cell_range, const __grid_constant__ HaloPush hp,
-                           const __grid_constant__ VelTail vt, const __grid_constant__ GridConsts g,
-                           const __grid_constant__ SolverConsts c) {
+                           const __grid_constant__ HaloSync hs, const __grid_constant__ VelTail vt,
+                           const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     pdl_wait();
     const Team tm = team_of();
-    const int64_t t = (int64_t)blockIdx.x * TEAM_PARTICLES + (threadIdx.x >> 2);
+    const uint32_t lb = halo_block(hs);
+    halo_enter(hs, lb);   // (edge blocks: the neighbours' lambdas of this iteration are in the ghost slots of xl)
+    const int64_t t = (int64_t)lb * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;
     const uint32_t cw = pair_cnt[t];   // (the team kernels do not re-bin: column t % GATHER_THREADS is particle t)
     const int64_t i = first + t;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cw & PAIR_OVERFLOW) {          // more neighbours than the list holds: the plain pass, on the team's first lane
-        if (tm.lane == 0) {
-            const float4 out = delta_p_one<POW>(xl, (uint32_t)i, cell_range, g, c);
-            x_out[i] = out;
-            co.store(i, out);
-            halo_push(hp, t, out);
-            if (vt.v4) velocity_tail(vt, t, i, out);
-        }
-        return;
-    }
-    const uint32_t cnt = pair_count(cw);
-    const float4 p = xl[i];
-    const size_t pair0 = (size_t)(t / GATHER_THREADS) * PAIR_CAP * GATHER_THREADS + (size_t)(t % GATHER_THREADS);
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    for (uint32_t k0 = 0; k0 < cnt; k0 += TEAM) {
-        const uint32_t k = k0 + tm.lane;
-        float sc = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;   // a padding lane adds fma(0, 0, a) == a
-        if (k < cnt) {
-            const uint2 js = __ldg(&pair_js[pair0 + (size_t)k * GATHER_THREADS]);
-            const float4 q = __ldg(&xl[js.x]);
-            const float sj = __uint_as_float(js.y);
-            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-            const float pw = pow_ncorr<POW>(poly6(sumsq(dx, dy, dz), c), c);
-            sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-            tx = __fmul_rn(dx, sj); ty = __fmul_rn(dy, sj); tz = __fmul_rn(dz, sj);
-        }
+        if (tm.lane == 0) out = delta_p_one<POW>(xl, (uint32_t)i, cell_range, g, c);
+    } else {
+        const uint32_t cnt = pair_count(cw);
+        const float4 p = xl[i];
+        const size_t pair0 = (size_t)(t / GATHER_THREADS) * PAIR_CAP * GATHER_THREADS + (size_t)(t % GATHER_THREADS);
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        for (uint32_t k0 = 0; k0 < cnt; k0 += TEAM) {
+            const uint32_t k = k0 + tm.lane;
+            float sc = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;   // a padding lane adds fma(0, 0, a) == a
+            if (k < cnt) {
+                const uint2 js = __ldg(&pair_js[pair0 + (size_t)k * GATHER_THREADS]);
+                const float4 q = __ldg(&xl[js.x]);
+                const float sj = __uint_as_float(js.y);
+                const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+                const float pw = pow_ncorr<POW>(poly6(sumsq(dx, dy, dz), c), c);
+                sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+                tx = __fmul_rn(dx, sj); ty = __fmul_rn(dy, sj); tz = __fmul_rn(dz, sj);
+            }
 #pragma unroll
-        for (int m = 0; m < TEAM; m++) {
-            if (k0 + m < cnt) {   // (uniform in the team; a skipped fma(sc, t, a) is not the same as fma(0, 0, a) when a == -0)
-                const float scm = team_bcast(tm, sc, m);
-                ax = __fmaf_rn(scm, team_bcast(tm, tx, m), ax);
-                ay = __fmaf_rn(scm, team_bcast(tm, ty, m), ay);
-                az = __fmaf_rn(scm, team_bcast(tm, tz, m), az);
+            for (int m = 0; m < TEAM; m++) {
+                if (k0 + m < cnt) {   // (uniform in the team; a skipped fma(sc, t, a) is not the same as fma(0, 0, a) when a == -0)
+                    const float scm = team_bcast(tm, sc, m);
+                    ax = __fmaf_rn(scm, team_bcast(tm, tx, m), ax);
+                    ay = __fmaf_rn(scm, team_bcast(tm, ty, m), ay);
+                    az = __fmaf_rn(scm, team_bcast(tm, tz, m), az);
+                }
             }
         }
+        out = delta_p_finish(p, ax, ay, az, c);
     }
     if (tm.lane != 0) return;
-    const float4 out = delta_p_finish(p, ax, ay, az, c);
     x_out[i] = out;
     co.store(i, out);
     halo_push(hp, t, out);
     if (vt.v4) velocity_tail(vt, t, i, out);
+    halo_exit(hs, lb);
 }
 
 // ---- XSPH ----------------------------------------------------------------------------------------------------
@@ -260,11 +260,14 @@ __global__ void __launch_bounds__(TEAM_THREADS, 8)
 xsph_team_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
                  const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
                  const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
-                 const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+                 const __grid_constant__ HaloSync hs, const __grid_constant__ GridConsts g,
+                 const __grid_constant__ SolverConsts c) {
     pdl_wait();
     extern __shared__ uint32_t s_list[];
     const Team tm = team_of();
-    const int64_t t = (int64_t)blockIdx.x * TEAM_PARTICLES + (threadIdx.x >> 2);
+    const uint32_t lb = halo_block(hs);
+    halo_enter(hs, lb);   // (edge blocks: the neighbours' velocities are in the ghost slots of v4)
+    const int64_t t = (int64_t)lb * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;
     const int64_t i = first + t;
     const float4 p = x[i];
@@ -315,33 +318,36 @@ cudaError_t preload_solver_team() {
 }
 
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,
-                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp,
+                        int64_t n, uint2* pair_js, uint32_t* pair_cnt, const HaloPush& hp, HaloSync hs,
                         const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
     const unsigned nb = team_blocks(n);
+    halo_sync_blocks(hs, n, TEAM_PARTICLES);
     if (!pair_js && !c.fast_spiky)
-        PBF_LAUNCH((lambda_team_kernel<false, false>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<false, false>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, hs, g, c);
     else if (!pair_js)
-        PBF_LAUNCH((lambda_team_kernel<false, true>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<false, true>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, nullptr, nullptr, hp, hs, g, c);
     else if (!c.fast_spiky)
-        PBF_LAUNCH((lambda_team_kernel<true, false>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<true, false>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, hs, g, c);
     else
-        PBF_LAUNCH((lambda_team_kernel<true, true>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, g, c);
+        PBF_LAUNCH((lambda_team_kernel<true, true>), nb, TEAM_THREADS, TEAM_SMEM, st, x, soa, xl, rho, cell_range, first, n, pair_js, pair_cnt, hp, hs, g, c);
 }
 
 void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut co, int64_t first, int64_t n, const uint2* pair_js,
-                                const uint32_t* pair_cnt, const uint2* cell_range, const HaloPush& hp, const VelTail& vt,
-                                const GridConsts& g, const SolverConsts& c, int pow_mode, cudaStream_t st) {
+                                const uint32_t* pair_cnt, const uint2* cell_range, const HaloPush& hp, HaloSync hs,
+                                const VelTail& vt, const GridConsts& g, const SolverConsts& c, int pow_mode, cudaStream_t st) {
     const unsigned nb = team_blocks(n);
-    if (pow_mode == 3) PBF_LAUNCH((delta_p_replay_team_kernel<3>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
-    else if (pow_mode == 2) PBF_LAUNCH((delta_p_replay_team_kernel<2>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
-    else if (pow_mode == 1) PBF_LAUNCH((delta_p_replay_team_kernel<1>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
-    else PBF_LAUNCH((delta_p_replay_team_kernel<0>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, vt, g, c);
+    halo_sync_blocks(hs, n, TEAM_PARTICLES);
+    if (pow_mode == 3) PBF_LAUNCH((delta_p_replay_team_kernel<3>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, hs, vt, g, c);
+    else if (pow_mode == 2) PBF_LAUNCH((delta_p_replay_team_kernel<2>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, hs, vt, g, c);
+    else if (pow_mode == 1) PBF_LAUNCH((delta_p_replay_team_kernel<1>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, hs, vt, g, c);
+    else PBF_LAUNCH((delta_p_replay_team_kernel<0>), nb, TEAM_THREADS, 0, st, xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, hs, vt, g, c);
 }
 
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
-                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, const GridConsts& g,
-                      const SolverConsts& c, cudaStream_t st) {
-    PBF_LAUNCH((xsph_team_kernel), team_blocks(n), TEAM_THREADS, TEAM_SMEM, st, x, soa, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, g, c);
+                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, HaloSync hs,
+                      const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
+    halo_sync_blocks(hs, n, TEAM_PARTICLES);
+    PBF_LAUNCH((xsph_team_kernel), team_blocks(n), TEAM_THREADS, TEAM_SMEM, st, x, soa, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
 }
 
 }  // namespace pbf
