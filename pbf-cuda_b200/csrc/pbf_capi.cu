@@ -12,6 +12,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <mutex>
 #include <new>
 
 #include "launch.cuh"
@@ -170,6 +171,15 @@ struct pbf_sim {
     bool wait_valid = false;
     uint64_t halo_timeout_ns = 10ull * 1000 * 1000 * 1000;
 
+    // the exhaustive verifications below run on a stream of their own with result words allocated once (a
+    // parameter change costs no device-wide synchronisation), and what they found is remembered per value:
+    // toggling a GUI slider back is free (the reference reloads its parameters every frame, Simulator.cpp:101-115)
+    cudaStream_t verify_stream = nullptr;
+    void* verify_scratch = nullptr;
+    struct DivEntry { float d, lo, hi; } div_cache[4] = {};
+    struct SpikyEntry { float h; int ok; unsigned long long bad; } spiky_cache[4] = {};
+    struct PowEntry { float top; int ok; unsigned long long bad; } pow_cache[4] = {};
+    int div_n = 0, spiky_n = 0, pow_n = 0;   // entries filled (round robin beyond 4)
     // verified constant division (refresh_consts)
     bool div_verified = false;
     float div_d = 0.f, div_rcp = 0.f, div_lo = 1.f, div_hi = 0.f;
@@ -296,12 +306,19 @@ int refresh_consts(pbf_sim* s) {
         const char* off = getenv("PBF_NO_CONST_DIV");
         if (!(off && off[0] == '1') && p.pho0 > 0.f && p.pho0 < 3.0e38f && cudaSetDevice(s->device) == cudaSuccess) {
             float lo = 1.f, hi = 0.f;
-            if (verify_const_div(p.pho0, s->div_rcp, &lo, &hi, nullptr) == cudaSuccess) {
-                // use it only if the verified interval is comfortably wide around the values that occur
-                if (lo <= 1e-30f && hi >= 1e30f) { s->div_lo = lo; s->div_hi = hi; }
-            } else {
-                cudaGetLastError();
+            bool known = false;
+            for (int k = 0; k < (s->div_n < 4 ? s->div_n : 4); k++)
+                if (s->div_cache[k].d == p.pho0) { lo = s->div_cache[k].lo; hi = s->div_cache[k].hi; known = true; }
+            if (!known) {
+                if (verify_const_div(p.pho0, s->div_rcp, &lo, &hi, s->verify_scratch, s->verify_stream) == cudaSuccess) {
+                    s->div_cache[s->div_n++ % 4] = {p.pho0, lo, hi};
+                } else {
+                    cudaGetLastError();
+                    lo = 1.f; hi = 0.f;
+                }
             }
+            // use it only if the verified interval is comfortably wide around the values that occur
+            if (lo <= 1e-30f && hi >= 1e30f) { s->div_lo = lo; s->div_hi = hi; }
         }
         s->div_d = p.pho0;
         s->div_verified = true;
@@ -317,7 +334,11 @@ int refresh_consts(pbf_sim* s) {
         const char* off = getenv("PBF_NO_FAST_SPIKY");
         if (!(off && off[0] == '1') && cudaSetDevice(s->device) == cudaSuccess) {
             unsigned long long bad = ~0ull;
-            if (verify_spiky(c, c.h2_cull, &bad, nullptr) == cudaSuccess) {
+            bool known = false;
+            for (int k = 0; k < (s->spiky_n < 4 ? s->spiky_n : 4); k++)
+                if (s->spiky_cache[k].h == p.h) { bad = s->spiky_cache[k].bad; known = true; }
+            if (known || verify_spiky(c, c.h2_cull, &bad, s->verify_scratch, s->verify_stream) == cudaSuccess) {
+                if (!known) s->spiky_cache[s->spiky_n++ % 4] = {p.h, bad == 0 ? 1 : 0, bad};
                 s->spiky_mismatches = bad;
                 s->spiky_ok = bad == 0 ? 1 : 0;
             } else {
@@ -337,7 +358,11 @@ int refresh_consts(pbf_sim* s) {
             const char* off = getenv("PBF_NO_TRIM_POW");
             if (!(off && off[0] == '1') && w_top >= 0.f && w_top < 3.0e38f && cudaSetDevice(s->device) == cudaSuccess) {
                 unsigned long long bad = ~0ull;
-                if (verify_pow4(w_top, &bad, nullptr) == cudaSuccess) {
+                bool known = false;
+                for (int k = 0; k < (s->pow_n < 4 ? s->pow_n : 4); k++)
+                    if (s->pow_cache[k].top == w_top) { bad = s->pow_cache[k].bad; known = true; }
+                if (known || verify_pow4(w_top, &bad, s->verify_scratch, s->verify_stream) == cudaSuccess) {
+                    if (!known) s->pow_cache[s->pow_n++ % 4] = {w_top, bad == 0 ? 1 : 0, bad};
                     s->pow4_mismatches = bad;
                     s->pow4_ok = bad == 0 ? 1 : 0;
                 } else {
@@ -374,6 +399,8 @@ void free_all(pbf_sim* s) {
             if (b) cudaIpcCloseMemHandle(b);
     cudaFree(s->sync_words);
     cudaFree(s->halo_done);
+    cudaFree(s->verify_scratch);
+    if (s->verify_stream) cudaStreamDestroy(s->verify_stream);
     if (s->ev_valid) {
         for (auto& e : s->ev) cudaEventDestroy(e);
         for (auto& e : s->kev) cudaEventDestroy(e);
@@ -477,15 +504,31 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (prop.major != 10) return fail(PBF_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CUDA_TRY(cudaSetDevice(device));
 
-    {   // once per device: load all kernels now, not at their first launch (preload_solver, solver.cu)
-        static bool loaded[64] = {};
-        if (device < 64 && !loaded[device]) {
+    {   // load all kernels now, not at their first launch (preload_solver, solver.cu): once per device, and safe
+        // when several host threads create their handles at the same time (one thread per rank); a device beyond
+        // the table is preloaded on every create (the query is cheap once the module is resident)
+        auto preload = []() -> cudaError_t {
             cudaFuncAttributes fa;
-            CUDA_TRY(cudaFuncGetAttributes(&fa, extract_words_kernel));
-            CUDA_TRY(preload_advect_key()); CUDA_TRY(preload_sort()); CUDA_TRY(preload_reorder()); CUDA_TRY(preload_scene());
-            CUDA_TRY(preload_slab()); CUDA_TRY(preload_solver()); CUDA_TRY(preload_stats());
-            loaded[device] = true;
+            cudaError_t e = cudaFuncGetAttributes(&fa, extract_words_kernel);
+            if (e == cudaSuccess) e = preload_advect_key();
+            if (e == cudaSuccess) e = preload_sort();
+            if (e == cudaSuccess) e = preload_reorder();
+            if (e == cudaSuccess) e = preload_scene();
+            if (e == cudaSuccess) e = preload_slab();
+            if (e == cudaSuccess) e = preload_solver();
+            if (e == cudaSuccess) e = preload_stats();
+            return e;
+        };
+        static std::once_flag once[64];
+        static cudaError_t result[64];
+        cudaError_t pe;
+        if (device < 64) {
+            std::call_once(once[device], [&]() { result[device] = preload(); });
+            pe = result[device];
+        } else {
+            pe = preload();
         }
+        if (pe != cudaSuccess) return fail(PBF_ERR_CUDA, "kernel preload failed: %s", cudaGetErrorString(pe));
     }
     pbf_sim* s = new (std::nothrow) pbf_sim;
     if (!s) return fail(PBF_ERR_INVALID, "out of host memory");
@@ -551,6 +594,8 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (e == cudaSuccess) { *s->flags_host = 0; e = cudaHostGetDevicePointer((void**)&s->flags_dev, s->flags_host, 0); }
     A((void**)&s->sync_words, 8 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(s->sync_words, 0, 8 * sizeof(uint32_t));
+    A((void**)&s->verify_scratch, 16);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->verify_stream, cudaStreamNonBlocking);
     A((void**)&s->halo_done, 2 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(s->halo_done, 0, 2 * sizeof(uint32_t));
     // (the memset runs on the legacy stream; a neighbour's first flag store comes from a non-blocking
@@ -996,6 +1041,15 @@ int pbf_stage_end(pbf_sim* s) {
         int rc = peers_signal(s);
         if (rc) return rc;
         s->state_seq = s->halo_seq;
+    }
+    // A handshake that timed out, or a neighbour search that left the stored planes, lets the kernels run on with
+    // stale / missing ghost values: a caller of the bare C ABI that never polls pbf_slab_flags must not get
+    // that silently. The word is mapped host memory: no synchronisation, so what is seen here is what the device
+    // has raised SO FAR (typically the previous step's) — the sticky flags stay up until pbf_slab_flags clears them.
+    if (s->slab_on && s->flags_host) {
+        const uint32_t f = *(volatile uint32_t*)s->flags_host;
+        if (f & PBF_SLAB_FLAG_TIMEOUT) return fail(PBF_ERR_STATE, "slab step: a neighbour's halo completion word did not arrive in time (PBF_SLAB_FLAG_TIMEOUT); results are not valid");
+        if (f & PBF_SLAB_FLAG_GHOST) return fail(PBF_ERR_STATE, "slab step: a neighbour search left the stored ghost planes (PBF_SLAB_FLAG_GHOST); results are not exact — raise `ghost`");
     }
     return PBF_OK;
 }
@@ -1495,6 +1549,7 @@ int pbf_read(pbf_sim* s, int what, void* dst, int64_t count) {
 int pbf_get_stats(pbf_sim* s, const float* npos, const float* nvel, int64_t n, pbf_stats* out) {
     if (!s || !npos || !nvel || !out) return fail(PBF_ERR_INVALID, "null argument");
     if (n <= 0 || n > s->max_particles) return fail(PBF_ERR_INVALID, "bad n");
+    if (n > s->own_count) return fail(PBF_ERR_INVALID, "n = %lld exceeds the %lld particles of the last step", (long long)n, (long long)s->own_count);
     CUDA_TRY(cudaSetDevice(s->device));
     int nb = (int)((n + 255) / 256);
     if (nb > 1024) nb = 1024;
@@ -1741,21 +1796,27 @@ int pbf_checkpoint_load(pbf_sim* s, const char* path, float* pos, float* vel, ui
     if (!h_pos.p || !h_vel.p || !h_iid.p) return fail(PBF_ERR_INVALID, "out of host memory (%lld particles)", (long long)info.n);
     rc = pbf_state_read(path, &info, (float*)h_pos.p, (float*)h_vel.p, (uint32_t*)h_iid.p, info.n);
     if (rc) return rc;
-    // parameters and box first: a file that does not fit this handle must not leave it half-configured
+    // parameters, box and pow option TOGETHER, validated once (a file whose (h, box) pair fits the handle must not
+    // be rejected because of an intermediate (new h, old box) state); a file that does not fit leaves the handle
+    // as it was
     const pbf_params old_p = s->p;
     float old_u[3], old_l[3];
     memcpy(old_u, s->ulim, sizeof(old_u));
     memcpy(old_l, s->llim, sizeof(old_l));
     const int old_exact = s->exact_pow;
+    s->p = info.params;
+    memcpy(s->ulim, info.ulim, sizeof(s->ulim));
+    memcpy(s->llim, info.llim, sizeof(s->llim));
     s->exact_pow = info.exact_pow ? 1 : 0;
-    rc = pbf_set_params(s, &info.params);
-    if (rc == PBF_OK) rc = pbf_set_lim(s, info.ulim, info.llim);
+    rc = refresh_consts(s);
     if (rc != PBF_OK) {
         char msg[sizeof(g_err)];
         snprintf(msg, sizeof(msg), "%s", g_err);
+        s->p = old_p;
+        memcpy(s->ulim, old_u, sizeof(old_u));
+        memcpy(s->llim, old_l, sizeof(old_l));
         s->exact_pow = old_exact;
-        pbf_set_params(s, &old_p);
-        pbf_set_lim(s, old_u, old_l);
+        refresh_consts(s);
         return fail(rc, "%s does not fit this handle: %s", path, msg);
     }
     CUDA_TRY(cudaSetDevice(s->device));

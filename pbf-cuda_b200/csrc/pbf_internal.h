@@ -276,10 +276,10 @@ cudaError_t launch_neighbor_count(const float4* x, CullScratch& cs, const uint2*
 
 // stats.cu: exhaustive check of the reciprocal division sequence for divisor d over all 2^32 bit
 // patterns of the dividend; returns the verified interval of |a| around 1 (lo > hi: none)
-cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStream_t st);
+cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, void* scratch8, cudaStream_t st);
 // stats.cu: exhaustive comparison of spiky_scale_fast with spiky_scale over every float r2 in [0, top]
-cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* mismatches, cudaStream_t st);
-cudaError_t verify_pow4(float top, unsigned long long* mismatches, cudaStream_t st);
+cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* mismatches, void* scratch8, cudaStream_t st);
+cudaError_t verify_pow4(float top, unsigned long long* mismatches, void* scratch8, cudaStream_t st);
 
 // force-load every kernel of a translation unit (see the comment at preload_solver in solver.cu)
 cudaError_t preload_advect_key();

@@ -78,10 +78,11 @@ __global__ void __launch_bounds__(256) const_div_check_kernel(float d, float y, 
     if (hi != 0xffffffffu) atomicMin(fail_above, hi);
 }
 
-cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStream_t st) {
-    uint32_t* dev = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dev, 8);
-    if (e != cudaSuccess) return e;
+// (`scratch`: 8 bytes of device memory owned by the caller — no allocation, hence no device-wide synchronisation,
+//  on this path; the kernels run on `st` and only `st` is waited for)
+cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, void* scratch, cudaStream_t st) {
+    uint32_t* dev = (uint32_t*)scratch;
+    cudaError_t e = cudaSuccess;
     const uint32_t init[2] = {0u, 0xffffffffu};
     uint32_t out[2] = {0, 0};
     e = cudaMemcpyAsync(dev, init, 8, cudaMemcpyHostToDevice, st);
@@ -91,7 +92,6 @@ cudaError_t verify_const_div(float d, float rcp, float* lo, float* hi, cudaStrea
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dev, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(dev);
     if (e != cudaSuccess) return e;
     // strictly inside the failures; +0 (pattern 0) "fails below" only if 0/d mismatched, which it does not,
     // but zero is excluded anyway: lo is at least the smallest normal number
@@ -116,10 +116,9 @@ __global__ void __launch_bounds__(256) spiky_check_kernel(uint32_t top_bits, Sol
     if (bad) atomicAdd(mismatches, bad);
 }
 
-cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* mismatches, cudaStream_t st) {
-    unsigned long long* dev = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dev, 8);
-    if (e != cudaSuccess) return e;
+cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* mismatches, void* scratch, cudaStream_t st) {
+    unsigned long long* dev = (unsigned long long*)scratch;
+    cudaError_t e = cudaSuccess;
     uint32_t top_bits;
     memcpy(&top_bits, &top, 4);
     e = cudaMemsetAsync(dev, 0, 8, st);
@@ -129,7 +128,6 @@ cudaError_t verify_spiky(const SolverConsts& c, float top, unsigned long long* m
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches, dev, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(dev);
     return e;
 }
 
@@ -143,10 +141,9 @@ __global__ void __launch_bounds__(256) pow4_check_kernel(uint32_t top_bits, unsi
     if (bad) atomicAdd(mismatches, bad);
 }
 
-cudaError_t verify_pow4(float top, unsigned long long* mismatches, cudaStream_t st) {
-    unsigned long long* dev = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dev, 8);
-    if (e != cudaSuccess) return e;
+cudaError_t verify_pow4(float top, unsigned long long* mismatches, void* scratch, cudaStream_t st) {
+    unsigned long long* dev = (unsigned long long*)scratch;
+    cudaError_t e = cudaSuccess;
     uint32_t top_bits;
     memcpy(&top_bits, &top, 4);
     e = cudaMemsetAsync(dev, 0, 8, st);
@@ -156,7 +153,6 @@ cudaError_t verify_pow4(float top, unsigned long long* mismatches, cudaStream_t 
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches, dev, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(dev);
     return e;
 }
 

@@ -334,7 +334,10 @@ class GpuEngine:
         return out
 
     def end(self):
-        self.sim.end()
+        try:
+            self.sim.end()
+        except self.pbf.PbfError as ex:   # pbf_stage_end reports a raised TIMEOUT / GHOST flag as an error
+            raise SlabError(str(ex)) from ex
         self._swap()
         self.n_own = int(self.layout.own_count)
         return self.n_own
