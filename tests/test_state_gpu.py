@@ -303,3 +303,44 @@ def test_graph_and_pdl_steps_give_the_same_bits(pbf, torch, moving):
     # the legacy default stream cannot be captured: the step is launched directly, same bits
     got, _ = run(1, 1, side_stream=False)
     assert got == plain
+
+
+def test_checkpoint_load_validates_parameters_and_box_together(pbf, torch, tmp_path):
+    """A file whose (h, box) PAIR fits the handle loads, even though (file h, handle box) alone would not: handle created
+    at h = 0.1 on a 4x4x4 box (64 000 cells, capacity 256 000), file at h = 0.05 on a 2x2x2 box (64 000 cells) — the
+    intermediate state 'h = 0.05 on the 4x4x4 box' has 512 000 cells. And a file that does not fit leaves the handle
+    exactly as it was."""
+    dev = torch.device("cuda:0")
+    n = 64
+    rng = np.random.RandomState(1)
+    pos = (rng.rand(n, 3).astype(np.float32) * 1.5 + 0.2).astype(np.float32)
+    vel = np.zeros((n, 3), np.float32)
+    iid = np.arange(n, dtype=np.uint32)
+    p_file = pbf.default_params()
+    p_file.h = 0.05
+    path = str(tmp_path / "pair.pbf")
+    pbf.state_write(path, pos, vel, iid, p_file, (2.0, 2.0, 2.0), (0.0, 0.0, 0.0), frame=7)
+    sim = pbf.Simulator(pbf.default_params(), (4.0, 4.0, 4.0), (0.0, 0.0, 0.0), 1024)
+    d_pos, d_vel = torch.zeros((1024, 3), device=dev), torch.zeros((1024, 3), device=dev)
+    d_iid = torch.zeros(1024, dtype=torch.int32, device=dev)
+    got_n, frame = sim.checkpoint_load(path, d_pos, d_vel, d_iid, 1024)
+    assert (got_n, frame) == (n, 7)
+    assert sim.grid_dim() == (40, 40, 40) and abs(sim.saveParams().h - 0.05) < 1e-9
+    # a file that cannot fit (h = 0.02 on the 4x4x4 box: 8e6 cells): rejected, handle untouched
+    p_big = pbf.default_params()
+    p_big.h = 0.02
+    big = str(tmp_path / "big.pbf")
+    pbf.state_write(big, pos, vel, iid, p_big, (4.0, 4.0, 4.0), (0.0, 0.0, 0.0))
+    with pytest.raises(pbf.PbfError) as ei:
+        sim.checkpoint_load(big, d_pos, d_vel, d_iid, 1024)
+    assert ei.value.code == pbf.ERR_CAPACITY
+    assert sim.grid_dim() == (40, 40, 40) and abs(sim.saveParams().h - 0.05) < 1e-9
+    u, l = sim.getLim()
+    assert np.allclose(u, (2, 2, 2)) and np.allclose(l, (0, 0, 0))
+    # stats on more particles than the last step held is an error, not a read past the owned range
+    d = [d_pos[:n].contiguous(), torch.zeros((n, 3), device=dev), d_vel[:n].contiguous(), torch.zeros((n, 3), device=dev)]
+    sim.step(d[0], d[1], d[2], d[3], d_iid[:n].contiguous(), n)
+    torch.cuda.synchronize()
+    with pytest.raises(pbf.PbfError):
+        sim.stats(d_pos, d_vel, n + 1)
+    sim.close()

@@ -17,7 +17,7 @@ def main(path):
             v *= 1e6
         tot[name] += v
         cnt[name] += 1
-    SETUP = ("scene", "stats", "const_div_check", "spiky_check")   # one-off kernels outside the step
+    SETUP = ("scene", "stats", "const_div_check", "spiky_check", "pow4_check", "digest")   # one-off kernels outside the step
     own = sum(v for k, v in tot.items() if "pbf::" in k and not any(s in k for s in SETUP))
     print("%-66s %5s %12s %7s %10s" % ("kernel", "n", "total_ns", "share", "avg_ns"))
     for k, v in tot.most_common():
