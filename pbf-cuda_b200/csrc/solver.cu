@@ -317,8 +317,22 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
 #define PBF_REPLAY_UNROLL3 4
 #endif
 constexpr int REPLAY_UNROLL3 = PBF_REPLAY_UNROLL3;
+// POW = 3: two list entries per trip through the two-lane fp32 instructions (pow4_trim2, pbf_math.cuh)
+#ifndef PBF_REPLAY_PACKED
+#define PBF_REPLAY_PACKED 1
+#endif
+#ifndef PBF_REPLAY_MINBLOCKS_PACKED
+#define PBF_REPLAY_MINBLOCKS_PACKED 10
+#endif
+#ifndef PBF_REPLAY_UNROLL2
+#define PBF_REPLAY_UNROLL2 1
+#endif
+constexpr bool REPLAY_PACKED = PBF_REPLAY_PACKED != 0;
+constexpr int REPLAY_UNROLL2 = PBF_REPLAY_UNROLL2;
+// (the packed POW = 3 loop keeps two pairs in flight: 48 registers, 10 CTAs per SM — measured against 16 (spills),
+//  12 (spills) and 8: 0.1360 ms per launch vs 0.1626 / 0.1422 / 0.1704, scalar loop at 16 CTAs 0.1483; dam_1m, early state)
 template <int POW>
-__global__ void __launch_bounds__(GATHER_THREADS, PBF_REPLAY_MINBLOCKS)
+__global__ void __launch_bounds__(GATHER_THREADS, (POW == 3 && REPLAY_PACKED) ? PBF_REPLAY_MINBLOCKS_PACKED : PBF_REPLAY_MINBLOCKS)
 delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                       const uint2* __restrict__ pair_js,
                       const uint32_t* __restrict__ pair_cnt, const uint2* __restrict__ cell_range,
@@ -342,18 +356,66 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
         const float4 p = xl[i];
         float ax = 0.f, ay = 0.f, az = 0.f;
         const size_t pair0 = (size_t)lb * PAIR_CAP * GATHER_THREADS + threadIdx.x;
+        if (POW == 3 && REPLAY_PACKED) {
+            // two list entries per trip, their arithmetic in the two lanes of the packed fp32 instructions (each lane
+            // the scalar IEEE operation, pow4_trim2); the sums are still accumulated one pair after the other, in
+            // list order. An odd list ends with its last entry in both lanes, the second one not accumulated.
+            const f32x2 px = splat2(p.x), py = splat2(p.y), pz = splat2(p.z), pw_ = splat2(p.w);
+            const f32x2 h2 = splat2(c.h2), coef = splat2(c.poly6_coef), corr = splat2(c.coef_corr);
+            // (the records of the NEXT trip are requested before this trip's gathers: record -> gather -> arithmetic
+            //  is a chain of two long-latency loads otherwise)
+            uint2 nx0 = make_uint2(0u, 0u), nx1 = nx0;
+            if (cnt > 0) {
+                nx0 = __ldg(&pair_js[pair0]);
+                nx1 = __ldg(&pair_js[pair0 + (size_t)(cnt > 1 ? 1 : 0) * GATHER_THREADS]);
+            }
+#pragma unroll REPLAY_UNROLL2
+            for (uint32_t k = 0; k < cnt; k += 2) {
+                const bool two = k + 1 < cnt;
+                const uint2 js0 = nx0, js1 = nx1;
+                if (k + 2 < cnt) {
+                    nx0 = __ldg(&pair_js[pair0 + (size_t)(k + 2) * GATHER_THREADS]);
+                    nx1 = __ldg(&pair_js[pair0 + (size_t)(k + 3 < cnt ? k + 3 : k + 2) * GATHER_THREADS]);
+                }
+                const float4 q0 = __ldg(&xl[js0.x]), q1 = __ldg(&xl[js1.x]);
+                const f32x2 dx = sub2(px, pack2(q0.x, q1.x)), dy = sub2(py, pack2(q0.y, q1.y)), dz = sub2(pz, pack2(q0.z, q1.z));
+                const f32x2 r2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                const f32x2 t = sub2(h2, r2);
+                float w0, w1, r20, r21;
+                unpack2(mul2(mul2(mul2(coef, t), t), t), w0, w1);      // poly6_in ...
+                unpack2(r2, r20, r21);
+                w0 = r20 >= c.h2 ? 0.f : w0;                           // ... and poly6's range test
+                w1 = r21 >= c.h2 ? 0.f : w1;
+                const f32x2 sc = fma2(corr, pow4_trim2(pack2(w0, w1)), add2(pw_, pack2(q0.w, q1.w)));
+                const f32x2 sj = pack2(__uint_as_float(js0.y), __uint_as_float(js1.y));
+                float sc0, sc1, tx0, tx1, ty0, ty1, tz0, tz1;
+                unpack2(sc, sc0, sc1);
+                unpack2(mul2(dx, sj), tx0, tx1);
+                unpack2(mul2(dy, sj), ty0, ty1);
+                unpack2(mul2(dz, sj), tz0, tz1);
+                ax = __fmaf_rn(sc0, tx0, ax);
+                ay = __fmaf_rn(sc0, ty0, ay);
+                az = __fmaf_rn(sc0, tz0, az);
+                if (two) {
+                    ax = __fmaf_rn(sc1, tx1, ax);
+                    ay = __fmaf_rn(sc1, ty1, ay);
+                    az = __fmaf_rn(sc1, tz1, az);
+                }
+            }
+        } else {
 #pragma unroll (POW == 3 ? REPLAY_UNROLL3 : 4)
-        for (uint32_t k = 0; k < cnt; k++) {
-            const size_t e = pair0 + (size_t)k * GATHER_THREADS;
-            const uint2 js = __ldg(&pair_js[e]);
-            const float4 q = __ldg(&xl[js.x]);
-            const float sj = __uint_as_float(js.y);  // spiky scale of the pair, saved by the lambda pass
-            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-            const float pw = pow_ncorr<POW>(poly6(sumsq(dx, dy, dz), c), c);
-            const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
-            ax = __fmaf_rn(sc, __fmul_rn(dx, sj), ax);
-            ay = __fmaf_rn(sc, __fmul_rn(dy, sj), ay);
-            az = __fmaf_rn(sc, __fmul_rn(dz, sj), az);
+            for (uint32_t k = 0; k < cnt; k++) {
+                const size_t e = pair0 + (size_t)k * GATHER_THREADS;
+                const uint2 js = __ldg(&pair_js[e]);
+                const float4 q = __ldg(&xl[js.x]);
+                const float sj = __uint_as_float(js.y);  // spiky scale of the pair, saved by the lambda pass
+                const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+                const float pw = pow_ncorr<POW>(poly6(sumsq(dx, dy, dz), c), c);
+                const float sc = __fmaf_rn(c.coef_corr, pw, __fadd_rn(p.w, q.w));
+                ax = __fmaf_rn(sc, __fmul_rn(dx, sj), ax);
+                ay = __fmaf_rn(sc, __fmul_rn(dy, sj), ay);
+                az = __fmaf_rn(sc, __fmul_rn(dz, sj), az);
+            }
         }
         out = delta_p_finish(p, ax, ay, az, c);
     }

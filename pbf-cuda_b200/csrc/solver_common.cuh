@@ -53,29 +53,6 @@ struct CullOut {
     __device__ __forceinline__ void store(int64_t i, const float4 q) const { xs[i] = q.x; ys[i] = q.y; zs[i] = q.z; }
 };
 
-// Two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2, sm_100): each lane is the same IEEE
-// round-to-nearest operation as the scalar instruction, so r2 below has the bits of sumsq().
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
 // two candidates: RN(r2 - limit) of each, sign bits pushed into `hits` (first candidate first)
 __device__ __forceinline__ uint32_t push_hits2(uint32_t hits, f32x2 px, f32x2 py, f32x2 pz, f32x2 lim,
                                                float x0, float x1, float y0, float y1, float z0, float z1) {

@@ -136,7 +136,14 @@ __global__ void __launch_bounds__(256) pow4_check_kernel(uint32_t top_bits, unsi
     unsigned long long bad = 0;
     for (uint64_t b = (uint64_t)blockIdx.x * 256 + threadIdx.x; b <= top_bits; b += (uint64_t)gridDim.x * 256) {
         const float w = __uint_as_float((uint32_t)b);
-        if (__float_as_uint(pow4_trim(w)) != __float_as_uint(powf(w, 4.0f))) bad++;
+        const uint32_t want = __float_as_uint(powf(w, 4.0f));
+        if (__float_as_uint(pow4_trim(w)) != want) bad++;
+        // the two-lane form (pow4_trim2): this w in lane 0 next to a different argument, and in lane 1
+        const float other = __uint_as_float(top_bits - (uint32_t)b);
+        float a0, a1, b0, b1;
+        unpack2(pow4_trim2(pack2(w, other)), a0, a1);
+        unpack2(pow4_trim2(pack2(other, w)), b0, b1);
+        if (__float_as_uint(a0) != want || __float_as_uint(b1) != want) bad++;
     }
     if (bad) atomicAdd(mismatches, bad);
 }
