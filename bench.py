@@ -413,6 +413,37 @@ def run_product(args, rank, world, dist):
             except Exception as ex:   # noqa: BLE001 - an entry that failed says so, the headline stays
                 sizes.append({"scene": name, "error": repr(ex)})
         out["sizes"] = sizes
+    # ---- opt-in tolerance mode (north_star: lambda / delta-p / positions within 1e-5 relative; the headline above
+    # is the bit-exact default): s_corr's w^4 as (w*w)^2 instead of the exact powf. Same scene, same window; the
+    # error is measured the way the tolerance is defined — ONE step from an identical state, against the exact path.
+    if world == 1 and not args.no_sizes:
+        try:
+            q = ProductRun(pbf, torch, local, args.scene)
+            q.sim.set_exact_pow(False)
+            ms, _ = timed_window(torch, q.step, args.steps, args.warmup, flush)
+            state = [t.clone() for t in (q.bufs[0], q.bufs[2], q.iid)]
+            q.step()                                     # one step, tolerance mode ...
+            fast = (q.bufs[0].clone(), q.bufs[2].clone(), q.iid.clone())
+            q.bufs[0].copy_(state[0]); q.bufs[2].copy_(state[1]); q.iid.copy_(state[2])
+            q.frame -= 1
+            q.sim.set_exact_pow(True)
+            q.step()                                     # ... and the same step, bit-exact mode
+            torch.cuda.synchronize()
+            same_order = bool(torch.equal(fast[2], q.iid))
+            dpos = float((fast[0] - q.bufs[0]).abs().max() / q.bufs[0].abs().max()) if same_order else None
+            dvel = float((fast[1] - q.bufs[2]).abs().max() / q.bufs[2].abs().max()) if same_order else None
+            out["tolerance_mode"] = {"option": "pbf_set_option_exact_pow(sim, 0): (w*w)^2 for n_corr = 4; everything else as in the default",
+                                     "value": round(n * args.steps / (ms * 1e-3), 1), "unit": "particle-steps/s",
+                                     "ms_per_step": round(ms / args.steps, 5), "steps": args.steps, "warmup": args.warmup,
+                                     "one_step_max_rel_err_positions": dpos, "one_step_max_rel_err_velocities": dvel,
+                                     "same_sorted_order_as_exact": same_order,
+                                     "note": "NOT the headline: results differ from the reference's bits (within the stated 1e-5 on "
+                                             "positions after one step; trajectories then diverge chaotically like any two fp32 runs)"}
+            q.close()
+            del q, state, fast
+            torch.cuda.empty_cache()
+        except Exception as ex:   # noqa: BLE001
+            out["tolerance_mode"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, pbf.SCENES[args.scene], n)
     return out

@@ -332,7 +332,7 @@ constexpr int REPLAY_UNROLL2 = PBF_REPLAY_UNROLL2;
 // (the packed POW = 3 loop keeps two pairs in flight: 48 registers, 10 CTAs per SM — measured against 16 (spills),
 //  12 (spills) and 8: 0.1360 ms per launch vs 0.1626 / 0.1422 / 0.1704, scalar loop at 16 CTAs 0.1483; dam_1m, early state)
 template <int POW>
-__global__ void __launch_bounds__(GATHER_THREADS, (POW == 3 && REPLAY_PACKED) ? PBF_REPLAY_MINBLOCKS_PACKED : PBF_REPLAY_MINBLOCKS)
+__global__ void __launch_bounds__(GATHER_THREADS, ((POW == 3 || POW == 0) && REPLAY_PACKED) ? PBF_REPLAY_MINBLOCKS_PACKED : PBF_REPLAY_MINBLOCKS)
 delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                       const uint2* __restrict__ pair_js,
                       const uint32_t* __restrict__ pair_cnt, const uint2* __restrict__ cell_range,
@@ -356,7 +356,7 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
         const float4 p = xl[i];
         float ax = 0.f, ay = 0.f, az = 0.f;
         const size_t pair0 = (size_t)lb * PAIR_CAP * GATHER_THREADS + threadIdx.x;
-        if (POW == 3 && REPLAY_PACKED) {
+        if ((POW == 3 || POW == 0) && REPLAY_PACKED) {
             // two list entries per trip, their arithmetic in the two lanes of the packed fp32 instructions (each lane
             // the scalar IEEE operation, pow4_trim2); the sums are still accumulated one pair after the other, in
             // list order. An odd list ends with its last entry in both lanes, the second one not accumulated.
@@ -386,7 +386,8 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                 unpack2(r2, r20, r21);
                 w0 = r20 >= c.h2 ? 0.f : w0;                           // ... and poly6's range test
                 w1 = r21 >= c.h2 ? 0.f : w1;
-                const f32x2 sc = fma2(corr, pow4_trim2(pack2(w0, w1)), add2(pw_, pack2(q0.w, q1.w)));
+                const f32x2 w2 = pack2(w0, w1), ww = mul2(w2, w2);
+                const f32x2 sc = fma2(corr, POW == 3 ? pow4_trim2(w2) : mul2(ww, ww), add2(pw_, pack2(q0.w, q1.w)));
                 const f32x2 sj = pack2(__uint_as_float(js0.y), __uint_as_float(js1.y));
                 float sc0, sc1, tx0, tx1, ty0, ty1, tz0, tz1;
                 unpack2(sc, sc0, sc1);
