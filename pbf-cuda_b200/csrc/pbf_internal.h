@@ -217,6 +217,8 @@ struct SweepMode {
     int team = -1;   // -1: by particle count (solver_common.cuh TEAM_MAX_PARTICLES); 0 / 1: thread / four-lane kernels
     int rebin = 0;   // thread kernels: re-deal a block's particles by CURRENT home cell once the iterate has moved
                      // (measured: no gain, DESIGN.md 3.7 — off by default, kept selectable for the A/B)
+    int staged = 0;  // first-iteration lambda pass with its candidates staged in shared memory by TMA bulk copies
+                     // (the A/B of DESIGN.md 3.3: measured, not faster — off)
     int pdl = 1;     // programmatic dependent launch between the step's kernels (launch.cuh)
     int halo_inkernel = 1;   // fused halo: handshakes inside the pass kernels (HaloSync) instead of two one-thread kernels per refresh
     int graph = -1;  // pbf_step replayed from a CUDA graph: -1 below 256 K particles, 0 never, 1 always (pbf_capi.cu)

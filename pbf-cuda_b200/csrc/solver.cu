@@ -19,9 +19,6 @@
 #include "launch.cuh"
 #include "solver_common.cuh"
 
-#ifndef PBF_CULL_IDX
-#define PBF_CULL_IDX 0
-#endif
 #ifndef PBF_CULL_UNROLL
 #define PBF_CULL_UNROLL 1
 #endif
@@ -54,11 +51,21 @@ constexpr int CULL_UNROLL = PBF_CULL_UNROLL;
 //  next neighbour ahead of the heavy arithmetic — no change in either case. The sweeps are bound by the L1
 //  wavefront rate (70-80 % of peak, ncu): lanes of a warp sit in ~3 cells, and after the first Jacobi
 //  iteration their home cells drift apart, so one warp load touches 3-9 different lines.)
-template <bool SKIP_SELF, typename Heavy>
+// STAGED (the TMA A/B of DESIGN.md 3.3, lambda_staged_kernel below): the block has copied, per (dx, dy) run, the
+// union of its threads' runs into shared memory with cp.async.bulk; the cull then reads from there —
+// `st_base` = shared address of the staged coordinates [run][x|y|z][STAGE_CAP], `st_ubase[run]` = first staged slot.
+constexpr int STAGE_CAP = 192;   // slots staged per run (9 runs x 3 arrays x 192 x 4 B = 20.25 KB per CTA)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <bool SKIP_SELF, bool STAGED = false, typename Heavy>
 __device__ __forceinline__ void gather(const float4 p, const uint32_t self, const float limit,
                                        const float4* __restrict__ x, const CullSoA soa,
                                        const uint2* __restrict__ cell_range, const GridConsts& g,
-                                       uint2* __restrict__ my_words, Heavy&& heavy) {
+                                       uint2* __restrict__ my_words, Heavy&& heavy, uint32_t st_base = 0,
+                                       const uint32_t* st_ubase = nullptr) {
     const int3 cc = cell_of(p.x, p.y, p.z, g);
     const bool has_below = cc.z > 0, has_above = cc.z + 1 < g.dim[2];
     uint2* const words_end = my_words + WORD_CAP * GATHER_THREADS;
@@ -116,30 +123,26 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
                 const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
                 const uint32_t groups = (cnt + 3) >> 2;
                 uint32_t hits = 0;
-#if PBF_CULL_IDX
-                // one 32-bit group index against the three (uniform) array bases instead of three 64-bit pointers
-                // that are each advanced per trip: 6 integer instructions fewer per four candidates
-                const float4* const xs4 = reinterpret_cast<const float4*>(soa.xs);
-                const float4* const ys4 = reinterpret_cast<const float4*>(soa.ys);
-                const float4* const zs4 = reinterpret_cast<const float4*>(soa.zs);
-                const uint32_t q_end = (b >> 2) + groups;
+                if (STAGED) {
+                    const int run = (dx + 1) * 3 + (dy + 1);
+                    uint32_t a = st_base + ((uint32_t)run * 3u * STAGE_CAP + (b - st_ubase[run])) * 4u;
 #pragma unroll 1
-                for (uint32_t q = b >> 2; q < q_end; q++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
-                    const float4 X = __ldg(xs4 + q), Y = __ldg(ys4 + q), Z = __ldg(zs4 + q);
-                    hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
-                    hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
-                }
-#else
-                const float4* xp = reinterpret_cast<const float4*>(soa.xs + b);
-                const float4* yp = reinterpret_cast<const float4*>(soa.ys + b);
-                const float4* zp = reinterpret_cast<const float4*>(soa.zs + b);
+                    for (uint32_t gi = 0; gi < groups; gi++, a += 16u) {  // the same four candidates out of shared memory
+                        const float4 X = lds128(a), Y = lds128(a + STAGE_CAP * 4u), Z = lds128(a + 2u * STAGE_CAP * 4u);
+                        hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
+                        hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
+                    }
+                } else {
+                    const float4* xp = reinterpret_cast<const float4*>(soa.xs + b);
+                    const float4* yp = reinterpret_cast<const float4*>(soa.ys + b);
+                    const float4* zp = reinterpret_cast<const float4*>(soa.zs + b);
 #pragma unroll CULL_UNROLL
-                for (uint32_t gi = 0; gi < groups; gi++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
-                    const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
-                    hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
-                    hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
+                    for (uint32_t gi = 0; gi < groups; gi++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
+                        const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
+                        hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
+                        hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
+                    }
                 }
-#endif
                 // first slot to the top bit; drop the slots before the run and what was read past its end
                 hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt)) & (0xffffffffu >> (b < start ? start - b : 0));
                 *tail = make_uint2(b, hits);
@@ -229,6 +232,86 @@ __device__ __forceinline__ uint32_t rebin_block(const float4* __restrict__ x, in
     return s_re[tid];
 }
 
+// ---- the TMA A/B: the block's candidate coordinates staged in shared memory ---------------------
+// North-star item 2 asks for the 27-cell neighbourhood staged in shared memory by TMA bulk copies of contiguous
+// sorted cell ranges. In the FIRST Jacobi iteration a block's 128 particles sit in consecutive cells, so for each of
+// the nine (dx, dy) runs the union of its threads' runs is one short contiguous slot range: thread 0 issues 27
+// cp.async.bulk copies (9 runs x {xs, ys, zs}) that complete on one mbarrier, and the cull reads shared memory
+// instead of global memory / L1 (gather<.., STAGED>). Returns false (all threads) when a union does not fit
+// STAGE_CAP slots: the block then takes the plain path. s_u: 20 words (9 union starts, 9 union ends, ok, bytes).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool stage_runs(const float4* __restrict__ x, const CullSoA soa, const uint2* __restrict__ cell_range,
+                                           const GridConsts& g, int64_t first, int64_t n, uint32_t block, float* s_xyz,
+                                           uint32_t* s_u, unsigned long long* s_mbar) {
+    const uint32_t tid = threadIdx.x;
+    const int64_t t = (int64_t)block * GATHER_THREADS + tid;
+    const bool valid = t < n;
+    if (tid < 9) { s_u[tid] = 0xffffffffu; s_u[9 + tid] = 0u; }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(s_mbar)));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the async proxy (TMA) sees the initialised barrier
+    }
+    __syncthreads();
+    int3 cc = make_int3(0, 0, 0);
+    if (valid) {
+        const float4 p = x[first + t];
+        cc = cell_of(p.x, p.y, p.z, g);
+    }
+    const bool has_below = cc.z > 0, has_above = cc.z + 1 < g.dim[2];
+#pragma unroll
+    for (int run = 0; run < 9; run++) {
+        const int cx = cc.x + run / 3 - 1, cy = cc.y + run % 3 - 1, lx = cx - g.xoff;
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        if (valid && cx >= 0 && cx < g.dim[0] && lx >= 0 && lx < g.nxl && cy >= 0 && cy < g.dim[1]) {
+            const int cbase = lx * g.dyz + cy * g.dim[2];
+            const uint2 zero = make_uint2(0u, 0u);
+            const uint2 r0 = has_below ? __ldg(&cell_range[cbase + cc.z - 1]) : zero;
+            const uint2 r1 = __ldg(&cell_range[cbase + cc.z]);
+            const uint2 r2 = has_above ? __ldg(&cell_range[cbase + cc.z + 1]) : zero;
+            const bool e0 = r0.y > r0.x, e1 = r1.y > r1.x, e2 = r2.y > r2.x;
+            const uint32_t start = e0 ? r0.x : e1 ? r1.x : r2.x, end = e2 ? r2.y : e1 ? r1.y : r0.y;
+            if (end > start) { lo = start; hi = end; }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((tid & 31u) == 0 && hi > lo) { atomicMin(&s_u[run], lo); atomicMax(&s_u[9 + run], hi); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = 0, ok = 1;
+        for (int run = 0; run < 9; run++) {
+            if (s_u[9 + run] <= s_u[run]) continue;
+            const uint32_t b = s_u[run] & ~3u, len = (s_u[9 + run] - b + 3u) & ~3u;   // whole groups of four slots
+            if (len > (uint32_t)STAGE_CAP) ok = 0;
+            bytes += 3u * len * 4u;
+        }
+        if (ok && bytes) {
+            const uint32_t mb = smem_addr(s_mbar);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            for (int run = 0; run < 9; run++) {
+                if (s_u[9 + run] <= s_u[run]) continue;
+                const uint32_t b = s_u[run] & ~3u, nbytes = ((s_u[9 + run] - b + 3u) & ~3u) * 4u;
+                const float* src[3] = {soa.xs + b, soa.ys + b, soa.zs + b};
+                for (int a = 0; a < 3; a++)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_addr(s_xyz + ((size_t)run * 3 + a) * STAGE_CAP)), "l"(src[a]), "r"(nbytes), "r"(mb) : "memory");
+                s_u[run] = b;   // what the cull subtracts
+            }
+        }
+        s_u[18] = ok;
+        s_u[19] = bytes;
+    }
+    __syncthreads();
+    const bool ok = s_u[18] != 0;
+    if (ok && s_u[19]) {
+        const uint32_t mb = smem_addr(s_mbar);
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+    }
+    return ok;
+}
+
 // ---- neighbour-list reuse between the two passes of one Jacobi iteration ------------------------
 // The lambda and delta-p passes of an iteration read the SAME positions (the reference runs
 // computeLambda and computetpos on the same dc_npos, Simulator.cu:222-245), so their in-range
@@ -243,8 +326,8 @@ __device__ __forceinline__ uint32_t rebin_block(const float4* __restrict__ x, in
 // entries are contiguous 8-byte (slot, s) records. A particle with more than PAIR_CAP neighbours
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
 
-template <bool SAVE_PAIRS, bool FAST_SPIKY, bool REBIN>
-__global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
+template <bool SAVE_PAIRS, bool FAST_SPIKY, bool REBIN, bool STAGED = false>
+__global__ void __launch_bounds__(GATHER_THREADS, STAGED ? 6 : PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
               uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
@@ -255,6 +338,11 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     __shared__ __align__(16) uint32_t s_re[REBIN ? GATHER_THREADS + 4 : 4];
     const uint32_t lb = halo_block(hs);   // (slab mode: the edge blocks first; blockIdx.x otherwise)
     const uint32_t local = REBIN ? rebin_block(x, first, n, lb, g, s_re) : threadIdx.x;   // which particle of the block
+    // STAGED (first iteration only): the block's candidates by TMA bulk copies into shared memory, see stage_runs
+    __shared__ __align__(16) float s_xyz[STAGED ? 9 * 3 * STAGE_CAP : 4];
+    __shared__ uint32_t s_u[STAGED ? 20 : 1];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const bool staged = STAGED && stage_runs(x, soa, cell_range, g, first, n, lb, s_xyz, s_u, &s_mbar);
     const int64_t t = (int64_t)lb * GATHER_THREADS + local;
     if (t >= n) return;
     const int64_t i = first + t;
@@ -266,7 +354,7 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     const float w_self = poly6_in(0.f, c);
     const size_t pair0 = (size_t)lb * PAIR_CAP * GATHER_THREADS + threadIdx.x;
     int n_pairs = 0;
-    gather<false>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
+    auto heavy = [&](uint32_t j, float4 q, int) {
         if (j == (uint32_t)i) {
             rho = __fadd_rn(rho, w_self);
         } else {
@@ -289,7 +377,11 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
                 n_pairs++;
             }
         }
-    });
+    };
+    if (STAGED && staged)
+        gather<false, true>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, heavy, smem_addr(s_xyz), s_u);
+    else
+        gather<false, false>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, heavy);
     if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
     const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
     const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
@@ -555,6 +647,10 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, false, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, false, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true, false, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<0>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<1>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_kernel<2>);
@@ -633,7 +729,10 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
     halo_sync_blocks(hs, n, GATHER_THREADS);
 #define PBF_LAMBDA_LAUNCH(SAVE, FAST)                                                                                          \
     do {                                                                                                                       \
-        if (mode.rebin && mode.moved)                                                                                          \
+        if (mode.staged && !mode.moved)                                                                                        \
+            PBF_LAUNCH((lambda_kernel<SAVE, FAST, false, true>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n, \
+                       pl.js, pl.cnt, hp, hs, g, c);                                                                         \
+        else if (mode.rebin && mode.moved)                                                                                     \
             PBF_LAUNCH((lambda_kernel<SAVE, FAST, true>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n,       \
                                                                                  pl.js, pl.cnt, hp, hs, g, c);               \
         else                                                                                                                   \

@@ -229,7 +229,7 @@ def test_rebinned_sweeps_give_the_same_bits(pbf, torch):
     n = n3[0] * n3[1] * n3[2]
     ulim, llim = (4.0, 3.0, 4.0), (0.0, 0.0, 0.0)
 
-    def run(rebin, steps=6):
+    def run(rebin, steps=6, staged=0):
         pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
         vel = torch.empty_like(pos)
         iid = torch.empty(n, dtype=torch.int32, device=dev)
@@ -238,7 +238,8 @@ def test_rebinned_sweeps_give_the_same_bits(pbf, torch):
         sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
         sim.set_option(pbf.OPT_TEAM, 0)
         sim.set_option(pbf.OPT_REBIN, rebin)
-        assert sim.get_option(pbf.OPT_REBIN) == rebin
+        sim.set_option(pbf.OPT_STAGED, staged)
+        assert sim.get_option(pbf.OPT_REBIN) == rebin and sim.get_option(pbf.OPT_STAGED) == staged
         for _ in range(steps):
             sim.step(d[0], d[1], d[2], d[3], iid, n)
             d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
@@ -249,9 +250,11 @@ def test_rebinned_sweeps_give_the_same_bits(pbf, torch):
 
     plain = run(0)
     assert run(1) == plain
+    # PBF_OPT_STAGED: the first iteration's candidates staged in shared memory by TMA bulk copies — the same bits
+    assert run(0, staged=1) == plain and run(1, staged=1) == plain
     os.environ["PBF_NO_PAIR_REUSE"] = "1"               # (read at create): the full-gather delta-p kernels
     try:
-        assert run(1) == plain and run(0) == plain
+        assert run(1) == plain and run(0) == plain and run(0, staged=1) == plain
     finally:
         del os.environ["PBF_NO_PAIR_REUSE"]
 
