@@ -118,6 +118,7 @@ struct pbf_sim {
     cudaStream_t host_main = nullptr, host_copy = nullptr;
     cudaEvent_t host_ev = nullptr, host_iid_ev = nullptr;
     cudaEvent_t reorder_wait = nullptr;   // step_host: the iid upload, still in flight while the keys are sorted
+    cudaEvent_t layout_ev[2] = {nullptr, nullptr};   // slab mode: plane table ready / downloaded (side stream)
 
     // bound state of the step in flight
     Stage stage = ST_IDLE;
@@ -390,6 +391,7 @@ void free_all(pbf_sim* s) {
     if (s->host_copy) cudaStreamDestroy(s->host_copy);
     if (s->host_ev) cudaEventDestroy(s->host_ev);
     if (s->host_iid_ev) cudaEventDestroy(s->host_iid_ev);
+    for (auto& e : s->layout_ev) if (e) cudaEventDestroy(e);
     if (s->stats_host) cudaFreeHost(s->stats_host);
     cudaFree(s->plane_dev);
     if (s->plane_host) cudaFreeHost(s->plane_host);
@@ -761,11 +763,21 @@ static int kernel_event(pbf_sim* s, int slot, int after) {
 // Slab mode, after the sort: where every stored plane starts in the sorted order. One small
 // kernel + a 8*(nxl+1)-byte download + the step's only host synchronisation; from the table
 // follow the owned range, the ghost counts and the sizes of every halo message.
-static int slab_learn_layout(pbf_sim* s) {
+// ... in two halves, so that the reorder pass (which reads the table on the device) can run while the host waits for
+// the download: begin = plane table, download on the handle's side stream, publish; end = handshake wait on the
+// compute stream, host waits for the DOWNLOAD only (an event on the side stream), layout.
+static int slab_layout_begin(pbf_sim* s) {
     const GridConsts& g = s->g;
     if (g.nxl + 1 > s->plane_capacity) return fail(PBF_ERR_CAPACITY, "slab stores %d planes, handle holds %lld", g.nxl, (long long)s->plane_capacity - 1);
+    if (!s->layout_ev[0]) {
+        CUDA_TRY(cudaEventCreateWithFlags(&s->layout_ev[0], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->layout_ev[1], cudaEventDisableTiming));
+    }
     CUDA_TRY(launch_plane_table(s->pairs[s->sorted_buf], s->n, s->plane_dev, g, s->stream, &s->launches));
-    CUDA_TRY(cudaMemcpyAsync(s->plane_host, s->plane_dev, (size_t)(g.nxl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaEventRecord(s->layout_ev[0], s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->verify_stream, s->layout_ev[0], 0));
+    CUDA_TRY(cudaMemcpyAsync(s->plane_host, s->plane_dev, (size_t)(g.nxl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s->verify_stream));
+    CUDA_TRY(cudaEventRecord(s->layout_ev[1], s->verify_stream));
     const pbf_slab_step& sl = s->slab;
     if (s->peer[0].on || s->peer[1].on) {
         // fused halo: device to device, tell the right neighbour where my right-ghost slots begin (the
@@ -777,10 +789,16 @@ static int slab_learn_layout(pbf_sim* s) {
                                      s->peer[1].on ? (int64_t*)(s->peer[1].sync + 2) : nullptr,
                                      s->peer[0].on ? s->peer[0].sync + 1 : nullptr, s->peer[1].on ? s->peer[1].sync + 0 : nullptr,
                                      s->halo_seq, s->stream, &s->launches));
+    }
+    return PBF_OK;
+}
+static int slab_layout_end(pbf_sim* s) {
+    const GridConsts& g = s->g;
+    const pbf_slab_step& sl = s->slab;
+    if (s->peer[0].on || s->peer[1].on)
         CUDA_TRY(launch_halo_wait(s->peer[0].on ? s->sync_words + 0 : nullptr, s->peer[1].on ? s->sync_words + 1 : nullptr,
                                   s->halo_seq, s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
-    }
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaEventSynchronize(s->layout_ev[1]));   // the step's one host wait: for 8 * (planes + 1) bytes
     const int64_t* ps = s->plane_host;
     const int gl = s->ghost_left, nx = sl.x_end - sl.x_begin;
     const int gw_l = sl.has_left ? (sl.ghost < nx ? sl.ghost : nx) : 0;   // owned planes a neighbour mirrors
@@ -808,6 +826,10 @@ static int slab_learn_layout(pbf_sim* s) {
     s->own_count = L.own_count;
     s->layout_valid = true;
     return PBF_OK;
+}
+static int slab_learn_layout(pbf_sim* s) {
+    int rc = slab_layout_begin(s);
+    return rc ? rc : slab_layout_end(s);
 }
 
 // Where the boundary values of the pass writing array `a` (x[0], x[1] or xl of this handle) go on
@@ -934,15 +956,25 @@ int pbf_stage_build_grid(pbf_sim* s) {
     sc.tile_desc_words = 0;
     KTIMED(PBF_KERNEL_SORT, launch_sort(s->keys, sc, s->n, s->npass, s->si, &s->sorted_buf, s->stream, &s->launches));
     if (s->slab_on) {
-        int rc = slab_learn_layout(s);
+        int rc = slab_layout_begin(s);
         if (rc) return rc;
     }
     if (s->reorder_wait) {   // reorder is the first kernel that reads iid
         CUDA_TRY(cudaStreamWaitEvent(s->stream, s->reorder_wait, 0));
         s->reorder_wait = nullptr;
     }
+    // slab mode: launched over every sorted entry with the layout read from the device table, so that it runs while
+    // the host is still waiting for that table (slab_layout_end below)
+    const pbf_slab_step& sl = s->slab;
     KTIMED(PBF_KERNEL_REORDER, launch_reorder(s->pairs[s->sorted_buf], s->pos, s->vel, s->iid, s->x[0], s->cull, s->npos, s->iid_sorted,
-                                              s->cell_range, s->sort_zero, sort_scratch_zero_bytes(s->n, s->npass), s->n_local, s->own_first, s->own_count, s->g, s->c, s->stream, &s->launches));
+                                              s->cell_range, s->sort_zero, sort_scratch_zero_bytes(s->n, s->npass),
+                                              s->slab_on ? s->n : s->n_local, s->own_first, s->own_count,
+                                              s->slab_on ? s->plane_dev : nullptr, s->ghost_left, sl.x_end - sl.x_begin,
+                                              s->g, s->c, s->stream, &s->launches));
+    if (s->slab_on) {
+        int rc = slab_layout_end(s);
+        if (rc) return rc;
+    }
     s->sort_dirty = false;   // (the reorder kernel left the sort's scratch zeroed)
     s->cur = 0;
     s->pos0_in_npos = true;

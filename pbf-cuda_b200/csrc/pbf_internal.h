@@ -192,10 +192,13 @@ struct CullScratch {
 
 // gather the payload into sorted SoA + cell ranges (reorder.cu)
 // `n` slots are gathered (slab mode: ghosts included); pos0_out is written for the owned slots
-// [own_first, own_first + own_count) only, at slot - own_first.
+// [own_first, own_first + own_count) only, at slot - own_first. plane_start != null (slab mode): n is only an upper
+// bound (the grid), the three numbers are read on the device from the plane table: n = plane_start[g.nxl],
+// own_first = plane_start[gl], own_count = plane_start[gl + nx] - own_first.
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                            float4* x0, CullScratch& cs, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
-                           uint32_t* sort_zero, size_t sort_zero_bytes, int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
+                           uint32_t* sort_zero, size_t sort_zero_bytes, int64_t n, int64_t own_first, int64_t own_count,
+                           const int64_t* plane_start, int gl, int nx, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches);
 
 // The velocity update (h_updateVelocity, Simulator.cu:127-137, 267-274) as the tail of the LAST delta-p pass of a

@@ -32,13 +32,20 @@ reorder_kernel(const KeyIdx* __restrict__ sorted, const float* __restrict__ pos,
                float4* __restrict__ x0, float* __restrict__ xs, float* __restrict__ ys, float* __restrict__ zs,
                float* __restrict__ pos0_out, uint32_t* __restrict__ iid_sorted,
                uint2* __restrict__ cell_range, uint4* __restrict__ sort_zero, int64_t sort_zero_quads,
-               int64_t n, int64_t own_first, int64_t own_count,
+               int64_t n, int64_t own_first, int64_t own_count, const int64_t* __restrict__ plane_start, int gl, int nx,
                const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
     pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
     const int64_t s = (int64_t)blockIdx.x * RO_THREADS + threadIdx.x;
     // the sort is done: leave its histograms, tickets and look-back descriptors zeroed for the next one
     // (the invariant of pbf_sim::sort_zero), instead of a memset in front of every step
     for (int64_t k = s; k < sort_zero_quads; k += (int64_t)gridDim.x * RO_THREADS) sort_zero[k] = make_uint4(0u, 0u, 0u, 0u);
+    // slab mode: how many of the sorted entries this rank keeps and which of them it owns is read from the plane
+    // table on the DEVICE (slab.cu plane_table_kernel) — the host is still downloading that table while this runs
+    if (plane_start) {
+        n = plane_start[g.nxl];
+        own_first = plane_start[gl];
+        own_count = plane_start[gl + nx] - own_first;
+    }
     if (s >= n) return;
     const KeyIdx e = sorted[s];
     const uint32_t prev = s == 0 ? 0xffffffffu : sorted[s - 1].key;
@@ -68,12 +75,13 @@ cudaError_t preload_reorder() {
 
 cudaError_t launch_reorder(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                            float4* x0, CullScratch& cs, float* pos0_out, uint32_t* iid_sorted, uint2* cell_range,
-                           uint32_t* sort_zero, size_t sort_zero_bytes, int64_t n, int64_t own_first, int64_t own_count, const GridConsts& g,
+                           uint32_t* sort_zero, size_t sort_zero_bytes, int64_t n, int64_t own_first, int64_t own_count,
+                           const int64_t* plane_start, int gl, int nx, const GridConsts& g,
                            const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     cs.holds = nullptr;
     if (n <= 0) return cudaSuccess;   // (nothing was sorted and nothing will be read)
     unsigned blocks = (unsigned)((n + RO_THREADS - 1) / RO_THREADS);
-    PBF_LAUNCH((reorder_kernel), blocks, RO_THREADS, 0, st, sorted, pos, vel, iid, x0, cs.xs[0], cs.ys[0], cs.zs[0], pos0_out, iid_sorted, cell_range, reinterpret_cast<uint4*>(sort_zero), (int64_t)((sort_zero_bytes + 15) / 16), n, own_first, own_count, g, c);
+    PBF_LAUNCH((reorder_kernel), blocks, RO_THREADS, 0, st, sorted, pos, vel, iid, x0, cs.xs[0], cs.ys[0], cs.zs[0], pos0_out, iid_sorted, cell_range, reinterpret_cast<uint4*>(sort_zero), (int64_t)((sort_zero_bytes + 15) / 16), n, own_first, own_count, plane_start, gl, nx, g, c);
     if (launches) (*launches)++;
     cs.cur = 0;
     cs.holds = x0;   // every stored slot

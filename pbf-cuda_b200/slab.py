@@ -164,6 +164,50 @@ class TorchComm:
         return host.numpy().reshape(self.world, -1)
 
     _side = None
+    _pin = [None, None]
+
+    def allgather_counts_start(self, counts):
+        """The same all-gather without waiting for it: returns a handle whose wait() gives the table. On GPUs the
+        collective and the download into pinned memory run on the transport's own stream; nothing on the compute
+        stream and nothing on the host waits until wait() is called — one step later (SlabSimulator.step)."""
+        if self.device is None:
+            return _Done(self.allgather_counts(counts))
+        import torch
+        mine = torch.from_numpy(np.ascontiguousarray(counts, np.int64))
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._pin = [None, None]
+        with torch.cuda.stream(self._side):
+            dev = mine.to(self.device, non_blocking=True)
+            out = torch.empty(self.world * mine.numel(), dtype=torch.int64, device=self.device)
+            self.dist.all_gather_into_tensor(out, dev, group=self.group)
+            # (two pinned buffers in rotation: pinning memory every step would cost more than the exchange)
+            k = self._pin_next = (getattr(self, "_pin_next", 0) + 1) % 2
+            if self._pin[k] is None or self._pin[k].numel() != out.numel():
+                self._pin[k] = torch.empty(out.shape, dtype=torch.int64).pin_memory()
+            host = self._pin[k]
+            host.copy_(out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        return _Pending(ev, host, self.world, (mine, dev, out))
+
+
+class _Done:
+    def __init__(self, table):
+        self.table = table
+
+    def wait(self):
+        return self.table
+
+
+class _Pending:
+    def __init__(self, ev, host, world, keep):
+        self.ev, self.host, self.world, self.keep = ev, host, world, keep
+
+    def wait(self):
+        self.ev.synchronize()
+        self.keep = None
+        return self.host.numpy().reshape(self.world, -1).copy()
 
 
 class SingleComm:
@@ -178,6 +222,9 @@ class SingleComm:
 
     def allgather_counts(self, counts):
         return np.asarray(counts, np.int64)[None, :]
+
+    def allgather_counts_start(self, counts):
+        return _Done(self.allgather_counts(counts))
 
 
 class ThreadComm:
@@ -241,6 +288,9 @@ class ThreadComm:
         out = np.stack(self.hub.gather)
         self.hub.barrier.wait(timeout=120)
         return out
+
+    def allgather_counts_start(self, counts):
+        return _Done(self.allgather_counts(counts))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -457,8 +507,20 @@ class SlabSimulator:
 
     def _gather_counts(self):
         """Replicates every rank's per-plane particle counts (sizes of the next step's raw exchange, input of
-        the planner)."""
-        self.counts = self.c.allgather_counts(np.asarray(self.e.plane_counts(), np.int64))
+        the planner). The exchange is only STARTED here; the table is needed at the beginning of the next step
+        (`_counts()`), a whole step of device work later, so neither the host nor the compute stream waits for the
+        slowest rank in the middle of a step."""
+        start = getattr(self.c, "allgather_counts_start", None)
+        mine = np.asarray(self.e.plane_counts(), np.int64)
+        self._pending_counts = start(mine) if start else _Done(self.c.allgather_counts(mine))
+
+    _pending_counts = None
+
+    def _counts(self):
+        if self._pending_counts is not None:
+            self.counts = self._pending_counts.wait()
+            self._pending_counts = None
+        return self.counts
 
     # -- one step
     def _xchg(self, left_send, left_recv, right_send, right_recv):
@@ -504,8 +566,8 @@ class SlabSimulator:
         old = self.bounds
         new = old
         if self.replan_every and self.steps and self.steps % self.replan_every == 0 and w > 1:
-            new = plan_boundaries(self.counts.sum(axis=0), w, self.min_width, old=old, reach=self.reach)
-        xp = exchange_plan(self.counts, old, new, r, self.reach)
+            new = plan_boundaries(self._counts().sum(axis=0), w, self.min_width, old=old, reach=self.reach)
+        xp = exchange_plan(self._counts(), old, new, r, self.reach)
         n_own = e.n_own
         assert n_own == int(self.counts[r].sum())
         m_l, m_r = xp["m_left"], xp["m_right"]
@@ -581,7 +643,7 @@ class SlabSimulator:
                             "results are not exact — raise `ghost`" % (self.rank, self.ghost))
 
     def total_particles(self):
-        return int(self.counts.sum())
+        return int(self._counts().sum())
 
 
 def plane_of(x, llim_x, h, planes):
