@@ -562,7 +562,7 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (const char* gr = getenv("PBF_GRAPH")) s->mode.graph = gr[0] == '1' ? 1 : gr[0] == '0' ? 0 : -1;
 
     const size_t n = (size_t)max_particles;
-    s->sort_zero_capacity = sort_scratch_zero_bytes(max_particles, MAX_PASSES);
+    s->sort_zero_capacity = sort_scratch_capacity_bytes(max_particles);
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&s->keys, n * 4);

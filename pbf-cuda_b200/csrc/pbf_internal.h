@@ -92,6 +92,8 @@ constexpr int MAX_PASSES = 4;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int SORT_ITEMS_SMALL = 4;              // tiles of 1024 keys ...
+constexpr int64_t SORT_SMALL_N = 128 * 1024;     // ... for inputs below this many keys
 
 // Fused halo push (slab mode with attached peers): the pass that produces a float4 per owned
 // particle also stores it — for the particles of the first / last ghost-width planes — straight
@@ -173,6 +175,7 @@ struct SortScratch {
 cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, const SlabInput& si,
                         int* result_buf, cudaStream_t st, int64_t* launches);
 size_t sort_scratch_zero_bytes(int64_t n, int npass);
+size_t sort_scratch_capacity_bytes(int64_t max_n);
 
 // Coordinate arrays the cull of the neighbour sweeps reads (solver.cu CullSoA): max_particles + 8 floats
 // each, 16-byte aligned.

@@ -8,7 +8,7 @@
 // Algorithm (Adinets & Merrill "Onesweep", restated from the paper, not from CUB's sources):
 //   - digit histograms of ALL passes are produced up front by advect_key.cu (raw counts; every tile scans the
 //     256 counts of its pass itself);
-//   - one kernel per 8-bit digit: each CTA takes a tile through an atomic ticket (so that every
+//   - one kernel per 8-bit digit: each CTA takes a tile (4096 keys; 1024 below 128 K keys) through an atomic ticket (so that every
 //     tile it may wait on is already resident), ranks its keys with warp-level match_any
 //     (stable: items are visited in memory order), publishes its per-digit counts, resolves its
 //     per-digit exclusive prefix by decoupled look-back over the preceding tiles, reorders the
@@ -39,14 +39,17 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <bool FIRST>
+// ITEMS keys per thread: 16 (tiles of 4096 keys) for large inputs, 4 (tiles of 1024) below SORT_SMALL_N keys, where
+// the eight-tile look-back chain of a 32 K-particle scene was most of the pass (20 us for two passes).
+template <bool FIRST, int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__ pairs_in,
                 KeyIdx* __restrict__ out, const uint32_t* __restrict__ hist,
                 uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ tile_desc, int64_t n,
                 int shift, const __grid_constant__ SlabInput si) {
     pdl_wait();
-    __shared__ KeyIdx s_pairs[SORT_TILE];
+    constexpr int TILE = SORT_THREADS * ITEMS;
+    __shared__ KeyIdx s_pairs[TILE];
     __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];
     __shared__ uint32_t s_digit_start[RADIX];
     __shared__ uint32_t s_global_base[RADIX];
@@ -61,14 +64,14 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
     for (int w = 0; w < SORT_WARPS; w++) s_warp_hist[w][tid] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const int64_t tile_base = (int64_t)tile * SORT_TILE;
-    const int tile_n = (int)min((int64_t)SORT_TILE, n - tile_base);
+    const int64_t tile_base = (int64_t)tile * TILE;
+    const int tile_n = (int)min((int64_t)TILE, n - tile_base);
 
     // ---- load, warp-striped so that (item k, lane l) is memory order within the warp's chunk
-    KeyIdx item[SORT_ITEMS];
-    const int warp_base = warp * 32 * SORT_ITEMS;
+    KeyIdx item[ITEMS];
+    const int warp_base = warp * 32 * ITEMS;
 #pragma unroll
-    for (int k = 0; k < SORT_ITEMS; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const int local = warp_base + k * 32 + lane;
         if (local < tile_n) {
             if (FIRST) {
@@ -85,10 +88,10 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
     }
 
     // ---- rank within the warp (stable)
-    uint32_t rank[SORT_ITEMS];
+    uint32_t rank[ITEMS];
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int k = 0; k < SORT_ITEMS; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const bool valid = (warp_base + k * 32 + lane) < tile_n;
         const uint32_t d = valid ? ((item[k].key >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -160,7 +163,7 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
 
     // ---- reorder the tile through shared memory
 #pragma unroll
-    for (int k = 0; k < SORT_ITEMS; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         if ((warp_base + k * 32 + lane) < tile_n) {
             const uint32_t d = (item[k].key >> shift) & (RADIX - 1);
             s_pairs[s_digit_start[d] + s_warp_hist[warp][d] + rank[k]] = item[k];
@@ -184,27 +187,41 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const KeyIdx* __restrict__
 cudaError_t preload_sort() {
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<true, SORT_ITEMS>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<false, SORT_ITEMS>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<true, SORT_ITEMS_SMALL>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, onesweep_kernel<false, SORT_ITEMS_SMALL>);
     return e;
 }
 
+static inline int sort_tile(int64_t n) { return SORT_THREADS * (n < SORT_SMALL_N ? SORT_ITEMS_SMALL : SORT_ITEMS); }
 size_t sort_scratch_zero_bytes(int64_t n, int npass) {
-    int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const int64_t tiles = (n + sort_tile(n) - 1) / sort_tile(n);
     return sizeof(uint32_t) * ((size_t)MAX_PASSES * RADIX + MAX_PASSES + (size_t)npass * tiles * RADIX);
+}
+size_t sort_scratch_capacity_bytes(int64_t max_n) {   // the largest of the above over every n <= max_n
+    const size_t big = sort_scratch_zero_bytes(max_n, MAX_PASSES);
+    const int64_t small_n = max_n < SORT_SMALL_N ? max_n : SORT_SMALL_N - 1;
+    const size_t small = sort_scratch_zero_bytes(small_n, MAX_PASSES);
+    return big > small ? big : small;
 }
 
 cudaError_t launch_sort(const uint32_t* keys, SortScratch& s, int64_t n, int npass, const SlabInput& si,
                         int* result_buf, cudaStream_t st, int64_t* launches) {
     if (n <= 0) { *result_buf = 0; return cudaSuccess; }
-    const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const bool small = n < SORT_SMALL_N;
+    const int64_t tiles = (n + sort_tile(n) - 1) / sort_tile(n);
     for (int p = 0; p < npass; p++) {
         uint32_t* desc = s.tile_desc + (size_t)p * tiles * RADIX;
         const uint32_t* h = s.hist + p * RADIX;
-        if (p == 0)
-            PBF_LAUNCH((onesweep_kernel<true>), (unsigned)tiles, SORT_THREADS, 0, st, keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
+        if (p == 0 && small)
+            PBF_LAUNCH((onesweep_kernel<true, SORT_ITEMS_SMALL>), (unsigned)tiles, SORT_THREADS, 0, st, keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
+        else if (p == 0)
+            PBF_LAUNCH((onesweep_kernel<true, SORT_ITEMS>), (unsigned)tiles, SORT_THREADS, 0, st, keys, nullptr, s.bufs[0], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
+        else if (small)
+            PBF_LAUNCH((onesweep_kernel<false, SORT_ITEMS_SMALL>), (unsigned)tiles, SORT_THREADS, 0, st, nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
         else
-            PBF_LAUNCH((onesweep_kernel<false>), (unsigned)tiles, SORT_THREADS, 0, st, nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
+            PBF_LAUNCH((onesweep_kernel<false, SORT_ITEMS>), (unsigned)tiles, SORT_THREADS, 0, st, nullptr, s.bufs[(p - 1) & 1], s.bufs[p & 1], h, s.tile_counter + p, desc, n, p * RADIX_BITS, si);
         if (launches) (*launches)++;
     }
     *result_buf = (npass - 1) & 1;
