@@ -1308,24 +1308,20 @@ int pbf_slab_begin(pbf_sim* s, const pbf_slab_step* st, float* pos, float* npos,
         if (which < 0 || vel != s->state[2 + which] || iid != s->state_iid)
             return fail(PBF_ERR_INVALID, "fused slab step: pos / vel / iid are not the registered state arrays");
         if (getenv("PBF_HALO_TRACE")) fprintf(stderr, "[halo %p] pull wait %u (m_left %lld m_right %lld)\n", (void*)s, s->state_seq, (long long)st->m_left, (long long)st->m_right);
+        CUDA_TRY(launch_halo_wait(s->peer[0].on && st->m_left > 0 ? s->sync_words + 0 : nullptr,
+                                  s->peer[1].on && st->m_right > 0 ? s->sync_words + 1 : nullptr, s->state_seq,
+                                  s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
         struct { int side; int64_t src, dst, cnt; } pull[2] = {{0, st->pull_left_first, st->n_own, st->m_left},
                                                                 {1, 0, st->n_own + st->m_left, st->m_right}};
-        const void* src[6] = {};
-        void* dst[6] = {};
-        int64_t words[6] = {};
-        int k = 0;
         for (auto& q : pull) {
-            if (q.cnt <= 0) { k += 3; continue; }
+            if (q.cnt <= 0) continue;
             const pbf_sim::Peer& pr = s->peer[q.side];
             if (!pr.on || !pr.iid) return fail(PBF_ERR_STATE, "fused slab step: neighbour %d has no registered state attached", q.side);
-            src[k] = pr.state[which] + 3 * q.src;     dst[k] = pos + 3 * q.dst; words[k++] = 3 * q.cnt;
-            src[k] = pr.state[2 + which] + 3 * q.src; dst[k] = vel + 3 * q.dst; words[k++] = 3 * q.cnt;
-            src[k] = pr.iid + q.src;                  dst[k] = iid + q.dst;     words[k++] = q.cnt;
+            CUDA_TRY(cudaMemcpyAsync(pos + 3 * q.dst, pr.state[which] + 3 * q.src, (size_t)q.cnt * 12, cudaMemcpyDefault, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(vel + 3 * q.dst, pr.state[2 + which] + 3 * q.src, (size_t)q.cnt * 12, cudaMemcpyDefault, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(iid + q.dst, pr.iid + q.src, (size_t)q.cnt * 4, cudaMemcpyDefault, s->stream));
+            s->launches += 3;
         }
-        // one kernel: waits for the neighbours' "state complete" words, then copies the six ranges over NVLink
-        CUDA_TRY(launch_pull_raw(src, dst, words, s->peer[0].on && st->m_left > 0 ? s->sync_words + 0 : nullptr,
-                                 s->peer[1].on && st->m_right > 0 ? s->sync_words + 1 : nullptr, s->state_seq,
-                                 s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
     }
     return PBF_OK;
 }

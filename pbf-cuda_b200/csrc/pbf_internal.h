@@ -276,11 +276,6 @@ cudaError_t launch_pack_ghosts(const float4* x, CullScratch& cs, int64_t n_slots
 cudaError_t launch_plane_table(const KeyIdx* sorted, int64_t n, int64_t* plane_start, const GridConsts& g,
                                cudaStream_t st, int64_t* launches);
 // slab.cu: npos/nvel/iid_out[s] = pos/vel/iid[sorted[s].idx] (state sort without a step)
-// slab.cu: fused mode, the raw-state pull of a step as ONE kernel: six flat word ranges copied out of the neighbours'
-// state arrays (peer memory) behind their "state complete" words
-cudaError_t launch_pull_raw(const void* const src[6], void* const dst[6], const int64_t words[6], const uint32_t* wait_left,
-                            const uint32_t* wait_right, uint32_t seq, uint64_t timeout_ns, uint32_t* flags, cudaStream_t st,
-                            int64_t* launches);
 cudaError_t launch_gather_state(const KeyIdx* sorted, const float* pos, const float* vel, const uint32_t* iid,
                                 float* npos, float* nvel, uint32_t* iid_out, int64_t n, cudaStream_t st,
                                 int64_t* launches);

@@ -92,81 +92,7 @@ __global__ void halo_wait_kernel(const uint32_t* word_left, const uint32_t* word
     }
 }
 
-// Fused mode, start of a step: the raw state (pos, vel, iid) of the planes a neighbour hands over is PULLED out of
-// its state arrays over NVLink by one kernel — up to six ranges (three arrays x two sides) as flat 4-byte words —
-// behind the neighbours' "state complete" words (every block's first thread waits; the words were raised at the
-// end of the neighbours' previous step, normally long ago). Round 1 issued a one-thread wait kernel and six
-// cudaMemcpyAsync calls: ~55 us of serialised launch latency for ~5 MB.
-struct PullRange {
-    const uint32_t* src;
-    uint32_t* dst;
-    int64_t words;
-};
-struct PullPlan {
-    PullRange r[6];
-    const uint32_t* wait_left;
-    const uint32_t* wait_right;
-    uint32_t seq;
-    uint64_t timeout_ns;
-    uint32_t* flags;
-};
-__global__ void __launch_bounds__(256) pull_raw_kernel(const __grid_constant__ PullPlan p) {
-    pdl_wait();
-    if (threadIdx.x == 0) {
-        const uint64_t t0 = global_ns();
-        for (int side = 0; side < 2; side++) {
-            const uint32_t* w = side == 0 ? p.wait_left : p.wait_right;
-            if (!w) continue;
-            while ((int32_t)(ld_acquire_sys(w) - p.seq) < 0) {
-                if (global_ns() - t0 > p.timeout_ns) {
-                    if (p.flags) atomicOr(p.flags, (uint32_t)PBF_SLAB_FLAG_TIMEOUT);
-                    break;
-                }
-                __nanosleep(64);
-            }
-        }
-    }
-    __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * 256;
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const uint32_t* __restrict__ src = p.r[k].src;
-        uint32_t* __restrict__ dst = p.r[k].dst;
-        // (remote READS are latency bound: eight words in flight per thread)
-        int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-        for (; i + 7 * stride < p.r[k].words; i += 8 * stride) {
-            uint32_t v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = src[i + u * stride];
-#pragma unroll
-            for (int u = 0; u < 8; u++) dst[i + u * stride] = v[u];
-        }
-        for (; i < p.r[k].words; i += stride) dst[i] = src[i];
-    }
-}
-
 }  // namespace
-
-cudaError_t launch_pull_raw(const void* const src[6], void* const dst[6], const int64_t words[6], const uint32_t* wait_left,
-                            const uint32_t* wait_right, uint32_t seq, uint64_t timeout_ns, uint32_t* flags, cudaStream_t st,
-                            int64_t* launches) {
-    PullPlan p;
-    int64_t total = 0;
-    for (int k = 0; k < 6; k++) {
-        p.r[k].src = (const uint32_t*)src[k];
-        p.r[k].dst = (uint32_t*)dst[k];
-        p.r[k].words = words[k];
-        total += words[k];
-    }
-    if (total <= 0) return cudaSuccess;
-    p.wait_left = wait_left; p.wait_right = wait_right; p.seq = seq; p.timeout_ns = timeout_ns; p.flags = flags;
-    int64_t nb = (total + 256 * 8 - 1) / (256 * 8);
-    if (nb > 148 * 2) nb = 148 * 2;
-    if (nb < 1) nb = 1;
-    PBF_LAUNCH((pull_raw_kernel), (unsigned)nb, 256, 0, st, p);
-    if (launches) (*launches)++;
-    return cudaGetLastError();
-}
 
 // Lazy module loading (the CUDA default) loads a kernel at its first launch, and that load can wait for
 // running kernels to finish: if the running kernel is a neighbour rank's flag wait (several ranks in one
@@ -178,7 +104,6 @@ cudaError_t preload_slab() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, gather_state_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, halo_signal_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, halo_wait_kernel);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pull_raw_kernel);
     return e;
 }
 
