@@ -184,6 +184,8 @@ struct pbf_sim {
     // verified constant division (refresh_consts)
     bool div_verified = false;
     float div_d = 0.f, div_rcp = 0.f, div_lo = 1.f, div_hi = 0.f;
+    bool hdiv_verified = false;      // the same for the division by h of the cell coordinate
+    float hdiv_d = 0.f, hdiv_rcp = 0.f, hdiv_lo = 1.f, hdiv_hi = 0.f;
     // branch-free spiky scale (pbf_math.cuh spiky_scale_fast): verified exhaustively for this h, or off
     bool spiky_checked = false;
     float spiky_h = 0.f;
@@ -224,6 +226,29 @@ void compute_dim(const float ulim[3], const float llim[3], float h, int32_t dim[
         float diff = ulim[a] - llim[a];
         dim[a] = (int32_t)ceilf(diff / h);
     }
+}
+
+// The interval of |a| in which a / d as the reciprocal sequence q = a*y, q' = fma(fma(-q, d, a), y, q) equals div.rn
+// for EVERY float a on this device (stats.cu verify_const_div, remembered per divisor), or the empty interval
+// (lo > hi: always the plain division) when it is switched off, cannot be checked, or is not comfortably wide.
+void verified_div_interval(pbf_sim* s, float d, float rcp, float* out_lo, float* out_hi) {
+    *out_lo = 1.f; *out_hi = 0.f;
+    const char* off = getenv("PBF_NO_CONST_DIV");
+    if ((off && off[0] == '1') || !(d > 0.f) || !(d < 3.0e38f) || cudaSetDevice(s->device) != cudaSuccess) return;
+    float lo = 1.f, hi = 0.f;
+    bool known = false;
+    for (int k = 0; k < (s->div_n < 4 ? s->div_n : 4); k++)
+        if (s->div_cache[k].d == d) { lo = s->div_cache[k].lo; hi = s->div_cache[k].hi; known = true; }
+    if (!known) {
+        if (verify_const_div(d, rcp, &lo, &hi, s->verify_scratch, s->verify_stream) == cudaSuccess) {
+            s->div_cache[s->div_n++ % 4] = {d, lo, hi};
+        } else {
+            cudaGetLastError();
+            lo = 1.f; hi = 0.f;
+        }
+    }
+    // use it only if the verified interval is comfortably wide around the values that occur
+    if (lo <= 1e-30f && hi >= 1e30f) { *out_lo = lo; *out_hi = hi; }
 }
 
 int refresh_consts(pbf_sim* s) {
@@ -301,29 +326,21 @@ int refresh_consts(pbf_sim* s) {
     // division by pho0 as a verified reciprocal sequence (pbf_math.cuh div_pho0); re-verified on the
     // device whenever pho0 changes, plain division if anything is off
     if (!(s->div_verified && s->div_d == p.pho0)) {
-        s->div_verified = false;
-        s->div_lo = 1.f; s->div_hi = 0.f;   // empty interval: always the plain division
         s->div_rcp = (float)(1.0 / (double)p.pho0);
-        const char* off = getenv("PBF_NO_CONST_DIV");
-        if (!(off && off[0] == '1') && p.pho0 > 0.f && p.pho0 < 3.0e38f && cudaSetDevice(s->device) == cudaSuccess) {
-            float lo = 1.f, hi = 0.f;
-            bool known = false;
-            for (int k = 0; k < (s->div_n < 4 ? s->div_n : 4); k++)
-                if (s->div_cache[k].d == p.pho0) { lo = s->div_cache[k].lo; hi = s->div_cache[k].hi; known = true; }
-            if (!known) {
-                if (verify_const_div(p.pho0, s->div_rcp, &lo, &hi, s->verify_scratch, s->verify_stream) == cudaSuccess) {
-                    s->div_cache[s->div_n++ % 4] = {p.pho0, lo, hi};
-                } else {
-                    cudaGetLastError();
-                    lo = 1.f; hi = 0.f;
-                }
-            }
-            // use it only if the verified interval is comfortably wide around the values that occur
-            if (lo <= 1e-30f && hi >= 1e30f) { s->div_lo = lo; s->div_hi = hi; }
-        }
+        verified_div_interval(s, p.pho0, s->div_rcp, &s->div_lo, &s->div_hi);
         s->div_d = p.pho0;
         s->div_verified = true;
     }
+    // ... and the division by h of the cell coordinate (pbf_math.cuh cell_coord), whenever h changes
+    if (!(s->hdiv_verified && s->hdiv_d == p.h)) {
+        s->hdiv_rcp = (float)(1.0 / (double)p.h);
+        verified_div_interval(s, p.h, s->hdiv_rcp, &s->hdiv_lo, &s->hdiv_hi);
+        s->hdiv_d = p.h;
+        s->hdiv_verified = true;
+    }
+    g.h_rcp = s->hdiv_rcp;
+    g.hdiv_lo = s->hdiv_lo;
+    g.hdiv_hi = s->hdiv_hi;
     c.pho0_rcp = s->div_rcp;
     c.div_lo = s->div_lo;
     c.div_hi = s->div_hi;

@@ -23,6 +23,11 @@ struct GridConsts {
     int32_t xoff;
     int32_t nxl;
     uint32_t* flags;  // sticky PBF_SLAB_FLAG_* word (mapped host memory) in slab mode, else null
+    // (p - llim) / h of the cell coordinate (Simulator.cu:30-35) as a reciprocal sequence VERIFIED exhaustively
+    // against div.rn for |a| in [hdiv_lo, hdiv_hi] (pbf_math.cuh cell_coord, stats.cu verify_const_div); an empty
+    // interval (lo > hi) keeps the plain division
+    float h_rcp;      // RN(1 / h)
+    float hdiv_lo, hdiv_hi;
 };
 
 // How the caller's particle arrays map to the sort's input order in slab mode (slab.cu).
