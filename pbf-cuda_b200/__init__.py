@@ -46,7 +46,7 @@ EXPORTS = (
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
-OPT_TEAM, OPT_REBIN, OPT_PDL, OPT_GRAPH, OPT_HALO_INKERNEL, OPT_STAGED = 0, 1, 2, 3, 4, 5
+OPT_TEAM, OPT_REBIN, OPT_PDL, OPT_GRAPH, OPT_HALO_INKERNEL, OPT_STAGED, OPT_PAIRED = 0, 1, 2, 3, 4, 5, 6
 SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST, SLAB_FLAG_TIMEOUT = 1, 2, 4
 
 

@@ -574,6 +574,7 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (const char* tm = getenv("PBF_TEAM")) s->mode.team = tm[0] == '1' ? 1 : tm[0] == '0' ? 0 : -1;
     if (const char* rb = getenv("PBF_REBIN")) s->mode.rebin = rb[0] == '1' ? 1 : 0;
     if (const char* sg = getenv("PBF_STAGED")) s->mode.staged = sg[0] == '1' ? 1 : 0;
+    if (const char* pr = getenv("PBF_PAIRED")) s->mode.paired = pr[0] == '1' ? 1 : 0;
     if (const char* pd = getenv("PBF_PDL")) s->mode.pdl = pd[0] == '0' ? 0 : 1;
     if (const char* hk = getenv("PBF_HALO_INKERNEL")) s->mode.halo_inkernel = hk[0] == '0' ? 0 : 1;
     if (const char* gr = getenv("PBF_GRAPH")) s->mode.graph = gr[0] == '1' ? 1 : gr[0] == '0' ? 0 : -1;
@@ -687,6 +688,9 @@ int pbf_set_option(pbf_sim* s, int option, int value) {
         case PBF_OPT_STAGED:
             s->mode.staged = value ? 1 : 0;
             return PBF_OK;
+        case PBF_OPT_PAIRED:
+            s->mode.paired = value ? 1 : 0;
+            return PBF_OK;
         case PBF_OPT_HALO_INKERNEL:
             s->mode.halo_inkernel = value ? 1 : 0;
             return PBF_OK;
@@ -705,6 +709,7 @@ int pbf_get_option(const pbf_sim* s, int option, int* value) {
         case PBF_OPT_REBIN: *value = s->mode.rebin; return PBF_OK;
         case PBF_OPT_PDL: *value = s->mode.pdl; return PBF_OK;
         case PBF_OPT_STAGED: *value = s->mode.staged; return PBF_OK;
+        case PBF_OPT_PAIRED: *value = s->mode.paired; return PBF_OK;
         case PBF_OPT_GRAPH: *value = s->mode.graph; return PBF_OK;
         case PBF_OPT_HALO_INKERNEL: *value = s->mode.halo_inkernel; return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
@@ -1141,7 +1146,7 @@ static int step_graph(pbf_sim* s, float* pos, float* npos, float* vel, float* nv
     StepGraph* lru = nullptr;   // where a new graph goes: a free slot, else the least recently used one
     for (auto& gq : s->graphs) {
         if (gq.exec && gq.n == n && gq.stream == (cudaStream_t)stream && gq.consts_hash == hc &&
-            gq.niter == s->p.niter && gq.team == s->mode.team && gq.rebin == s->mode.rebin + 2 * s->mode.staged && gq.pdl == s->mode.pdl &&
+            gq.niter == s->p.niter && gq.team == s->mode.team && gq.rebin == s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired && gq.pdl == s->mode.pdl &&
             memcmp(gq.ptr, ptr, sizeof(ptr)) == 0) {
             hit = &gq;
             break;
@@ -1186,7 +1191,7 @@ static int step_graph(pbf_sim* s, float* pos, float* npos, float* vel, float* nv
         }
         memcpy(lru->ptr, ptr, sizeof(ptr));
         lru->n = n; lru->stream = (cudaStream_t)stream; lru->consts_hash = hc;
-        lru->niter = s->p.niter; lru->team = s->mode.team; lru->rebin = s->mode.rebin + 2 * s->mode.staged; lru->pdl = s->mode.pdl;
+        lru->niter = s->p.niter; lru->team = s->mode.team; lru->rebin = s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired; lru->pdl = s->mode.pdl;
         lru->launches = s->launches - l0;
         lru->sorted_buf = s->sorted_buf; lru->cur = s->cur; lru->iters_done = s->iters_done;
         lru->cull_cur = s->cull.cur; lru->cull_holds = s->cull.holds; lru->v4 = s->v4;

@@ -230,6 +230,8 @@ struct SweepMode {
                      // (measured: no gain, DESIGN.md 3.7 — off by default, kept selectable for the A/B)
     int staged = 0;  // first-iteration lambda pass with its candidates staged in shared memory by TMA bulk copies
                      // (the A/B of DESIGN.md 3.3: measured, not faster — off)
+    int paired = 0;  // thread kernels: two consecutive slots per thread, one walk over the union of their candidate runs
+                     // (solver.cu gather2): half the cull's loads per test
     int pdl = 1;     // programmatic dependent launch between the step's kernels (launch.cuh)
     int halo_inkernel = 1;   // fused halo: handshakes inside the pass kernels (HaloSync) instead of two one-thread kernels per refresh
     int graph = -1;  // pbf_step replayed from a CUDA graph: -1 below 256 K particles, 0 never, 1 always (pbf_capi.cu)

@@ -344,7 +344,10 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     __shared__ __align__(8) unsigned long long s_mbar;
     const bool staged = STAGED && stage_runs(x, soa, cell_range, g, first, n, lb, s_xyz, s_u, &s_mbar);
     const int64_t t = (int64_t)lb * GATHER_THREADS + local;
-    if (t >= n) return;
+    if (t >= n) {   // a column of the last block without a particle: its word names a particle >= n, the replay skips it
+        if (SAVE_PAIRS) pair_cnt[(int64_t)lb * GATHER_THREADS + threadIdx.x] = pair_word(0, local);
+        return;
+    }
     const int64_t i = first + t;
     const float4 p = x[i];
     float rho = 0.f, gradj_l2 = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
@@ -435,10 +438,9 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
     const uint32_t lb = halo_block(hs);
     halo_enter(hs, lb);   // (edge blocks: the neighbours' lambdas of this iteration are in the ghost slots of xl)
     const int64_t col = (int64_t)lb * GATHER_THREADS + threadIdx.x;   // list column; its word names the particle
-    if (col >= n) return;
-    const uint32_t cw = pair_cnt[col];
+    const uint32_t cw = pair_cnt[col];   // (the lambda pass writes the word of EVERY column of its blocks)
     const int64_t t = (int64_t)lb * GATHER_THREADS + pair_local(cw);
-    if (t >= n) return;   // (cannot happen: a column below n names a particle below n)
+    if (t >= n) return;   // a column of the last block that holds no particle (the paired sweeps' columns are not 0..m-1)
     const int64_t i = first + t;
     float4 out;
     if (cw & PAIR_OVERFLOW) {   // more neighbours than the list holds: the plain pass for this one particle
@@ -620,6 +622,301 @@ xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __res
     iid_out[t] = iid_sorted[i];
 }
 
+// ---- two particles per thread: the paired sweeps (PBF_OPT_PAIRED) ---------------------------------------------------
+// The cull is where the sweeps sit on the L1 data pipe: every thread streams its particle's ~216-390 candidates
+// through three 16-byte loads per four slots, and two particles in neighbouring slots stream almost the same
+// candidates. A thread of the paired kernels therefore takes TWO consecutive slots A and B and walks the UNION of
+// their candidate runs once: one set of loads feeds both particles' tests (half the L1 wavefronts, a quarter fewer
+// instructions per test). Each particle keeps its own hit words, masked to ITS run ([start, end) of the three cells
+// around ITS current home cell in that column), so each still sees exactly its candidates in ascending slot order,
+// and each is accumulated by this one thread in that order: no bit changes. Columns are visited over the bounding
+// box of the two 3 x 3 column neighbourhoods in ascending (x, y) = ascending slot order; a column only one of the
+// two searches is culled for that one alone. A pair whose home cells are far apart (a slot pair that straddles the
+// end of a z column) is simply done one after the other.
+constexpr int PAIR_THREADS = GATHER_THREADS / 2;   // 64 threads = 128 particles per block, like the other sweeps:
+                                                   // the neighbour list's layout and the halo's edge blocks stay
+#ifndef PBF_PAIRED_MINBLOCKS
+#define PBF_PAIRED_MINBLOCKS 10
+#endif
+
+struct SlotRun { uint32_t start, end; };
+// the run of a column for a particle whose home cell has z index cz: first slot of the first non-empty cell of
+// (cz - 1, cz, cz + 1) to the end of the last non-empty one; {0, 0} if all are empty (see gather())
+__device__ __forceinline__ SlotRun column_run(const uint2* __restrict__ cell_range, int cbase, int cz, int dimz) {
+    const uint2 zero = make_uint2(0u, 0u);
+    const uint2 r0 = cz > 0 ? __ldg(&cell_range[cbase + cz - 1]) : zero;
+    const uint2 r1 = __ldg(&cell_range[cbase + cz]);
+    const uint2 r2 = cz + 1 < dimz ? __ldg(&cell_range[cbase + cz + 1]) : zero;
+    const bool e0 = r0.y > r0.x, e1 = r1.y > r1.x, e2 = r2.y > r2.x;
+    SlotRun r;
+    r.start = e0 ? r0.x : e1 ? r1.x : r2.x;
+    r.end = e2 ? r2.y : e1 ? r1.y : r0.y;
+    return r;
+}
+// bits of the 32-slot word that starts at slot b (first slot in the top bit) whose slots lie in [s, e)
+__device__ __forceinline__ uint32_t word_mask(uint32_t b, uint32_t s, uint32_t e) {
+    if (e <= b || s >= b + 32u || e <= s) return 0u;
+    const uint32_t lo = s > b ? s - b : 0u;          // 0..31
+    const uint32_t hi = min(e - b, 32u);             // 1..32
+    return (0xffffffffu >> lo) & (0xffffffffu << (32u - hi));
+}
+__device__ __forceinline__ uint32_t push_hits2p(uint32_t hits, f32x2 px, f32x2 py, f32x2 pz, f32x2 lim, f32x2 cx, f32x2 cy, f32x2 cz) {
+    const f32x2 dx = sub2(px, cx), dy = sub2(py, cy), dz = sub2(pz, cz);
+    const f32x2 t = sub2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lim);
+    uint32_t t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+    hits = __funnelshift_l(t0, hits, 1);
+    return __funnelshift_l(t1, hits, 1);
+}
+// phase 2 of one particle: the exact arithmetic over the set bits of its list, in slot order (see gather())
+template <bool SKIP_SELF, typename Heavy>
+__device__ __forceinline__ void drain_words(const uint2* col, const uint2* tail, uint32_t self, const float4* __restrict__ x, Heavy& heavy) {
+    const uint2* e = col;
+    uint32_t first = 0, hits = 0;
+    for (;;) {
+        if (hits == 0) {
+            if (e == tail) break;
+            const uint2 w = *e;
+            e += GATHER_THREADS;
+            first = w.x;
+            hits = w.y;
+        }
+        const int lead = __clz((int)hits);
+        hits &= ~(0x80000000u >> lead);
+        const uint32_t j = first + (uint32_t)lead;
+        if (SKIP_SELF && j == self) continue;
+        heavy(j, __ldg(&x[j]));
+    }
+}
+
+// wordsA / wordsB: the two particles' columns of the block's shared-memory list (entry k at [k * GATHER_THREADS])
+template <bool SKIP_SELF, typename HeavyA, typename HeavyB>
+__device__ __forceinline__ void gather2(const float4 pA, const float4 pB, const bool validB, const uint32_t selfA, const uint32_t selfB,
+                                        const float limit, const float4* __restrict__ x, const CullSoA soa,
+                                        const uint2* __restrict__ cell_range, const GridConsts& g,
+                                        uint2* __restrict__ wordsA, uint2* __restrict__ wordsB, HeavyA& heavyA, HeavyB& heavyB) {
+    const int3 ca = cell_of(pA.x, pA.y, pA.z, g);
+    const int3 cb = validB ? cell_of(pB.x, pB.y, pB.z, g) : ca;
+    // one walk over the union of the two neighbourhoods when they are close (runs of three cells up to three cells
+    // apart in z still form one gap-free slot range), else A's walk, then B's
+    const bool joint = validB && abs(ca.x - cb.x) <= 2 && abs(ca.y - cb.y) <= 2 && abs(ca.z - cb.z) <= 3;
+    uint2* tailA = wordsA;
+    uint2* tailB = wordsB;
+    uint2* const endA = wordsA + WORD_CAP * GATHER_THREADS;
+    uint2* const endB = wordsB + WORD_CAP * GATHER_THREADS;
+    const f32x2 pxA = pack2(pA.x, pA.x), pyA = pack2(pA.y, pA.y), pzA = pack2(pA.z, pA.z);
+    const f32x2 pxB = pack2(pB.x, pB.x), pyB = pack2(pB.y, pB.y), pzB = pack2(pB.z, pB.z);
+    const f32x2 lim = pack2(limit, limit);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const bool actA = joint || pass == 0, actB = validB && (joint || pass == 1);
+        if (pass == 1 && (joint || !validB)) break;
+        const int xlo = actA && actB ? min(ca.x, cb.x) : actA ? ca.x : cb.x, xhi = actA && actB ? max(ca.x, cb.x) : actA ? ca.x : cb.x;
+        const int ylo = actA && actB ? min(ca.y, cb.y) : actA ? ca.y : cb.y, yhi = actA && actB ? max(ca.y, cb.y) : actA ? ca.y : cb.y;
+#pragma unroll 1
+        for (int cx = xlo - 1; cx <= xhi + 1; cx++) {
+            const int lx = cx - g.xoff;
+            if (cx < 0 || cx >= g.dim[0]) continue;
+            const bool ax = actA && abs(cx - ca.x) <= 1, bx = actB && abs(cx - cb.x) <= 1;
+            if (!(ax || bx)) continue;
+            if (lx < 0 || lx >= g.nxl) {   // the search leaves the stored planes (slab mode): say so, see gather()
+                if (g.flags) atomicOr(g.flags, (uint32_t)PBF_SLAB_FLAG_GHOST);
+                continue;
+            }
+#pragma unroll 1
+            for (int cy = ylo - 1; cy <= yhi + 1; cy++) {
+                if (cy < 0 || cy >= g.dim[1]) continue;
+                const bool a = ax && abs(cy - ca.y) <= 1, b = bx && abs(cy - cb.y) <= 1;
+                if (!(a || b)) continue;
+                const int cbase = lx * g.dyz + cy * g.dim[2];
+                SlotRun ra = {0u, 0u}, rb = {0u, 0u};
+                if (a) ra = column_run(cell_range, cbase, ca.z, g.dim[2]);
+                if (b) rb = (a && cb.z == ca.z) ? ra : column_run(cell_range, cbase, cb.z, g.dim[2]);
+                const bool ea = ra.end > ra.start, eb = rb.end > rb.start;
+                if (!(ea || eb)) continue;
+                const uint32_t start = ea && eb ? min(ra.start, rb.start) : ea ? ra.start : rb.start;
+                const uint32_t end = ea && eb ? max(ra.end, rb.end) : ea ? ra.end : rb.end;
+#pragma unroll 1
+                for (uint32_t w0 = start & ~3u; w0 < end; w0 += 32) {   // words start at multiples of four slots
+                    const uint32_t cnt = min(end - w0, 32u);
+                    const uint32_t groups = (cnt + 3) >> 2;
+                    const float4* xp = reinterpret_cast<const float4*>(soa.xs + w0);
+                    const float4* yp = reinterpret_cast<const float4*>(soa.ys + w0);
+                    const float4* zp = reinterpret_cast<const float4*>(soa.zs + w0);
+                    uint32_t hA = 0, hB = 0;
+                    if (ea && eb) {
+#pragma unroll 1
+                        for (uint32_t gi = 0; gi < groups; gi++) {   // four candidates, both particles: 3 loads, 28 packed flops, 8 shifts
+                            const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
+                            const f32x2 x01 = pack2(X.x, X.y), y01 = pack2(Y.x, Y.y), z01 = pack2(Z.x, Z.y);
+                            const f32x2 x23 = pack2(X.z, X.w), y23 = pack2(Y.z, Y.w), z23 = pack2(Z.z, Z.w);
+                            hA = push_hits2p(hA, pxA, pyA, pzA, lim, x01, y01, z01);
+                            hB = push_hits2p(hB, pxB, pyB, pzB, lim, x01, y01, z01);
+                            hA = push_hits2p(hA, pxA, pyA, pzA, lim, x23, y23, z23);
+                            hB = push_hits2p(hB, pxB, pyB, pzB, lim, x23, y23, z23);
+                        }
+                    } else {
+                        const f32x2 px = ea ? pxA : pxB, py = ea ? pyA : pyB, pz = ea ? pzA : pzB;
+                        uint32_t h = 0;
+#pragma unroll 1
+                        for (uint32_t gi = 0; gi < groups; gi++) {
+                            const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
+                            h = push_hits2p(h, px, py, pz, lim, pack2(X.x, X.y), pack2(Y.x, Y.y), pack2(Z.x, Z.y));
+                            h = push_hits2p(h, px, py, pz, lim, pack2(X.z, X.w), pack2(Y.z, Y.w), pack2(Z.z, Z.w));
+                        }
+                        hA = ea ? h : 0u;
+                        hB = ea ? 0u : h;
+                    }
+                    // first slot to the top bit; keep each particle's own run only
+                    const uint32_t sh = 32 - 4 * groups;
+                    hA = (hA << sh) & word_mask(w0, ra.start, ra.end);
+                    hB = (hB << sh) & word_mask(w0, rb.start, rb.end);
+                    *tailA = make_uint2(w0, hA);
+                    tailA += hA ? GATHER_THREADS : 0;
+                    *tailB = make_uint2(w0, hB);
+                    tailB += hB ? GATHER_THREADS : 0;
+                    if (tailA == endA) { drain_words<SKIP_SELF>(wordsA, tailA, selfA, x, heavyA); tailA = wordsA; }
+                    if (tailB == endB) { drain_words<SKIP_SELF>(wordsB, tailB, selfB, x, heavyB); tailB = wordsB; }
+                }
+            }
+        }
+    }
+    drain_words<SKIP_SELF>(wordsA, tailA, selfA, x, heavyA);
+    if (validB) drain_words<SKIP_SELF>(wordsB, tailB, selfB, x, heavyB);
+}
+
+// one particle's sums of the lambda pass (computeLambda, Simulator_kernel.cuh:52-129), see lambda_kernel
+template <bool SAVE_PAIRS, bool FAST_SPIKY>
+struct LambdaAcc {
+    float4 p;
+    uint32_t self;
+    float rho = 0.f, gradj_l2 = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
+    int n_pairs = 0;
+    float w_self;
+    uint2* pair_col;   // this particle's column of the neighbour list (entry k at [k * GATHER_THREADS])
+    const SolverConsts& c;
+    __device__ __forceinline__ LambdaAcc(const float4 p_, uint32_t self_, uint2* col, const SolverConsts& c_)
+        : p(p_), self(self_), w_self(poly6_in(0.f, c_)), pair_col(col), c(c_) {}
+    __device__ __forceinline__ void operator()(uint32_t j, const float4 q) {
+        if (j == self) {
+            rho = __fadd_rn(rho, w_self);
+        } else {
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            const float r2 = sumsq(dx, dy, dz);
+            rho = __fadd_rn(rho, poly6(r2, c));
+            const float s = FAST_SPIKY ? spiky_scale_fast(r2, c) : spiky_scale(r2, c);
+            float gx = __fmul_rn(dx, s), gy = __fmul_rn(dy, s), gz = __fmul_rn(dz, s);
+            div3_pho0(gx, gy, gz, c);
+            gix = __fadd_rn(gix, gx);
+            giy = __fadd_rn(giy, gy);
+            giz = __fadd_rn(giz, gz);
+            gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
+            if (SAVE_PAIRS) {
+                if (n_pairs < PAIR_CAP) pair_col[(size_t)n_pairs * GATHER_THREADS] = make_uint2(j, __float_as_uint(s));
+                n_pairs++;
+            }
+        }
+    }
+    __device__ __forceinline__ float4 finish(float& rho_out, const GridConsts& g) {
+        if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
+        const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
+        const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
+        rho_out = rho;
+        return make_float4(p.x, p.y, p.z, lambda);
+    }
+};
+
+// Thread u of block lb takes the block's particles 2u (A) and 2u + 1 (B); their list columns are u and 64 + u (the
+// k-th records of a warp's particles stay contiguous), and the count word of a column names its particle, which is
+// all the delta-p replay needs to know (pair_word).
+template <bool SAVE_PAIRS, bool FAST_SPIKY>
+__global__ void __launch_bounds__(PAIR_THREADS, PBF_PAIRED_MINBLOCKS)
+lambda2_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
+               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
+               uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
+               const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
+               const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();
+    extern __shared__ uint2 s_words[];
+    const uint32_t lb = halo_block(hs);
+    const uint32_t colA = threadIdx.x, colB = PAIR_THREADS + threadIdx.x;
+    const int64_t tA = (int64_t)lb * GATHER_THREADS + 2 * threadIdx.x, tB = tA + 1;
+    if (tA >= n) {   // columns without a particle: their words name particles >= n, the replay skips them
+        if (SAVE_PAIRS) {
+            pair_cnt[(int64_t)lb * GATHER_THREADS + colA] = pair_word(0, 2 * threadIdx.x);
+            pair_cnt[(int64_t)lb * GATHER_THREADS + colB] = pair_word(0, 2 * threadIdx.x + 1);
+        }
+        return;
+    }
+    const bool validB = tB < n;
+    const int64_t iA = first + tA, iB = iA + 1;
+    const float4 pA = x[iA], pB = validB ? x[iB] : pA;
+    uint2* const list0 = SAVE_PAIRS ? pair_js + (size_t)lb * PAIR_CAP * GATHER_THREADS : nullptr;
+    LambdaAcc<SAVE_PAIRS, FAST_SPIKY> accA(pA, (uint32_t)iA, list0 + colA, c), accB(pB, (uint32_t)iB, list0 + colB, c);
+    gather2<false>(pA, pB, validB, (uint32_t)iA, (uint32_t)iB, c.h2_cull, x, soa, cell_range, g, s_words + colA, s_words + colB, accA, accB);
+    float rho;
+    const float4 outA = accA.finish(rho, g);
+    xl[iA] = outA;
+    halo_push(hp, tA, outA);
+    rho_out[iA] = rho;
+    if (validB) {
+        const float4 outB = accB.finish(rho, g);
+        xl[iB] = outB;
+        halo_push(hp, tB, outB);
+        rho_out[iB] = rho;
+    }
+    if (SAVE_PAIRS) {
+        const int64_t c0 = (int64_t)lb * GATHER_THREADS;
+        pair_cnt[c0 + colA] = pair_word(accA.n_pairs, 2 * threadIdx.x);
+        pair_cnt[c0 + colB] = pair_word(validB ? accB.n_pairs : 0, 2 * threadIdx.x + 1);
+    }
+    halo_exit(hs, lb);
+}
+
+struct XsphAcc {
+    float4 p, vi;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    const float4* __restrict__ v4;
+    const SolverConsts& c;
+    __device__ __forceinline__ XsphAcc(const float4 p_, const float4 vi_, const float4* v4_, const SolverConsts& c_) : p(p_), vi(vi_), v4(v4_), c(c_) {}
+    __device__ __forceinline__ void operator()(uint32_t j, const float4 q) {
+        const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
+        const float4 vj = __ldg(&v4[j]);
+        const float w = poly6_in(r2, c);
+        const float den = __fadd_rn(vi.w, vj.w);
+        const float tx = __fsub_rn(vj.x, vi.x), ty = __fsub_rn(vj.y, vi.y), tz = __fsub_rn(vj.z, vi.z);
+        ax = __fadd_rn(ax, __fdiv_rn(__fmul_rn(__fadd_rn(tx, tx), w), den));
+        ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
+        az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
+    }
+};
+
+__global__ void __launch_bounds__(PAIR_THREADS, PBF_PAIRED_MINBLOCKS)
+xsph2_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
+             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
+             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
+             const __grid_constant__ HaloSync hs, const __grid_constant__ GridConsts g,
+             const __grid_constant__ SolverConsts c) {
+    pdl_wait();
+    extern __shared__ uint2 s_words[];
+    const uint32_t lb = halo_block(hs);
+    halo_enter(hs, lb);   // (edge blocks: the neighbours' velocities are in the ghost slots of v4)
+    const int64_t tA = (int64_t)lb * GATHER_THREADS + 2 * threadIdx.x, tB = tA + 1;
+    if (tA >= n) return;
+    const bool validB = tB < n;
+    const int64_t iA = first + tA, iB = iA + 1;
+    const float4 pA = x[iA], pB = validB ? x[iB] : pA;
+    XsphAcc accA(pA, v4[iA], v4, c), accB(pB, validB ? v4[iB] : v4[iA], v4, c);
+    gather2<true>(pA, pB, validB, (uint32_t)iA, (uint32_t)iB, c.h2, x, soa, cell_range, g, s_words + threadIdx.x,
+                  s_words + PAIR_THREADS + threadIdx.x, accA, accB);
+    store_f3(nvel_out, tA, __fmaf_rn(c.c_xsph, accA.ax, accA.vi.x), __fmaf_rn(c.c_xsph, accA.ay, accA.vi.y), __fmaf_rn(c.c_xsph, accA.az, accA.vi.z));
+    iid_out[tA] = iid_sorted[iA];
+    if (validB) {
+        store_f3(nvel_out, tB, __fmaf_rn(c.c_xsph, accB.ax, accB.vi.x), __fmaf_rn(c.c_xsph, accB.ay, accB.vi.y), __fmaf_rn(c.c_xsph, accB.az, accB.vi.z));
+        iid_out[tB] = iid_sorted[iB];
+    }
+}
+
 __global__ void __launch_bounds__(GATHER_THREADS)
 neighbor_count_kernel(const float4* __restrict__ x, const CullSoA soa, const uint2* __restrict__ cell_range,
                       uint32_t* __restrict__ count, int64_t n, const __grid_constant__ GridConsts g,
@@ -667,6 +964,11 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, neighbor_count_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda2_kernel<false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda2_kernel<true, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda2_kernel<false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda2_kernel<true, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph2_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_ghosts_kernel);
     if (e == cudaSuccess) e = preload_solver_team();
@@ -729,7 +1031,10 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
     halo_sync_blocks(hs, n, GATHER_THREADS);
 #define PBF_LAMBDA_LAUNCH(SAVE, FAST)                                                                                          \
     do {                                                                                                                       \
-        if (mode.staged && !mode.moved)                                                                                        \
+        if (mode.paired)                                                                                                       \
+            PBF_LAUNCH((lambda2_kernel<SAVE, FAST>), nb, PAIR_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n,   \
+                       pl.js, pl.cnt, hp, hs, g, c);                                                                         \
+        else if (mode.staged && !mode.moved)                                                                                        \
             PBF_LAUNCH((lambda_kernel<SAVE, FAST, false, true>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n, \
                        pl.js, pl.cnt, hp, hs, g, c);                                                                         \
         else if (mode.rebin && mode.moved)                                                                                     \
@@ -818,7 +1123,9 @@ cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const
     }
     HaloSync hs = hs_in;
     halo_sync_blocks(hs, n, GATHER_THREADS);
-    if (mode.rebin && mode.moved)
+    if (mode.paired)
+        PBF_LAUNCH((xsph2_kernel), nblocks(n, GATHER_THREADS), PAIR_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
+    else if (mode.rebin && mode.moved)
         PBF_LAUNCH((xsph_kernel<true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
     else
         PBF_LAUNCH((xsph_kernel<false>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);

@@ -259,6 +259,43 @@ def test_rebinned_sweeps_give_the_same_bits(pbf, torch):
         del os.environ["PBF_NO_PAIR_REUSE"]
 
 
+def test_paired_sweeps_give_the_same_bits(pbf, torch):
+    """PBF_OPT_PAIRED: two consecutive slots per thread, one walk over the union of their candidate runs (solver.cu
+    gather2). Each particle is still accumulated by one thread over exactly its candidates in ascending slot order,
+    so no bit may change — odd particle count (a thread with one particle, a ragged last block whose list columns are
+    not 0..m-1), enough steps for home cells to drift apart, through the neighbour list and without it."""
+    dev = torch.device("cuda:0")
+    n3 = (47, 41, 37)                                   # 71 299 particles: odd, 557 blocks of 128, the last one ragged
+    n = n3[0] * n3[1] * n3[2]
+    ulim, llim = (4.0, 3.0, 4.0), (0.0, 0.0, 0.0)
+
+    def run(paired, steps=10):
+        pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        vel = torch.empty_like(pos)
+        iid = torch.empty(n, dtype=torch.int32, device=dev)
+        pbf.scene_block_device((0.2, 0.2, 0.2), n3, pos, vel, iid)
+        d = [pos, torch.zeros_like(pos), vel, torch.zeros_like(vel)]
+        sim = pbf.Simulator(pbf.default_params(), ulim, llim, n)
+        sim.set_option(pbf.OPT_TEAM, 0)
+        sim.set_option(pbf.OPT_PAIRED, paired)
+        assert sim.get_option(pbf.OPT_PAIRED) == paired
+        for _ in range(steps):
+            sim.step(d[0], d[1], d[2], d[3], iid, n)
+            d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+        torch.cuda.synchronize()
+        out = pbf.state_digest(d[0], d[2], iid, n)
+        sim.close()
+        return out
+
+    plain = run(0)
+    assert run(1) == plain
+    os.environ["PBF_NO_PAIR_REUSE"] = "1"               # (read at create): the full-gather delta-p kernels
+    try:
+        assert run(1) == plain
+    finally:
+        del os.environ["PBF_NO_PAIR_REUSE"]
+
+
 @pytest.mark.parametrize("moving", [0, 1])
 def test_graph_and_pdl_steps_give_the_same_bits(pbf, torch, moving):
     """PBF_OPT_GRAPH / PBF_OPT_PDL (include/pbf.h): a step replayed from a CUDA graph, with or without programmatic
