@@ -39,13 +39,14 @@ EXPORTS = (
     "pbf_slab_begin", "pbf_slab_get_layout", "pbf_slab_plane_counts", "pbf_stage_lambda", "pbf_stage_delta_p",
     "pbf_slab_halo", "pbf_slab_flags", "pbf_slab_sort_state", "pbf_scene_block_slice_device",
     "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
-    "pbf_slab_halo_sync", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
+    "pbf_slab_halo_sync", "pbf_slab_push_state", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
     "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count", "pbf_get_const_div_interval",
     "pbf_get_fast_spiky", "pbf_get_trim_pow", "pbf_set_option", "pbf_get_option", "pbf_state_digest_device",
     "pbf_state_digest_host", "pbf_state_write", "pbf_state_read_info", "pbf_state_read", "pbf_checkpoint_save", "pbf_checkpoint_load",
 )
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
+SLAB_STATE_PUSHED = -1   # pbf_slab_step.pull_left_first: the neighbours stored the raw state themselves (pbf_slab_push_state)
 OPT_TEAM, OPT_REBIN, OPT_PDL, OPT_GRAPH, OPT_HALO_INKERNEL, OPT_STAGED, OPT_PAIRED = 0, 1, 2, 3, 4, 5, 6
 SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST, SLAB_FLAG_TIMEOUT = 1, 2, 4
 
@@ -86,7 +87,7 @@ class SlabLayout(C.Structure):
 class SlabPeerInfo(C.Structure):
     """pbf_slab_peer_info (include/pbf.h): a rank's solver arrays as CUDA IPC handles / raw pointers."""
     _fields_ = [("ipc", (C.c_ubyte * 64) * 9), ("ptr", C.c_uint64 * 9), ("pid", C.c_int64), ("device", C.c_int32),
-                ("has_state", C.c_int32)]
+                ("has_state", C.c_int32), ("state_capacity", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -170,6 +171,7 @@ _lib.pbf_slab_register_state.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
 _lib.pbf_slab_peer_export.argtypes = [_vp, C.POINTER(SlabPeerInfo)]
 _lib.pbf_slab_peer_attach.argtypes = [_vp, C.c_int, C.POINTER(SlabPeerInfo)]
 _lib.pbf_slab_halo_sync.argtypes = [_vp]
+_lib.pbf_slab_push_state.argtypes = [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
 _lib.pbf_last_error.restype = C.c_char_p
 _lib.pbf_version.restype = C.c_char_p
 
@@ -465,6 +467,9 @@ class Simulator:
 
     def slab_halo_sync(self):
         _check(_lib.pbf_slab_halo_sync(self._h))
+
+    def slab_push_state(self, left_count, left_dst, right_first, right_dst):
+        _check(_lib.pbf_slab_push_state(self._h, int(left_count), int(left_dst), int(right_first), int(right_dst)))
 
     def slab_flags(self):
         f = C.c_uint32()

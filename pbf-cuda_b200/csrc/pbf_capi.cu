@@ -157,8 +157,10 @@ struct pbf_sim {
         uint32_t* sync = nullptr;
         float* state[4] = {nullptr, nullptr, nullptr, nullptr};    // pos A, pos B, vel A, vel B (if registered)
         uint32_t* iid = nullptr;
+        int64_t state_capacity = 0;                                // particles its state arrays hold
         void* ipc_base[9] = {};                                    // opened IPC mappings to close
     } peer[2];
+    StatePush state_push;            // armed by pbf_slab_push_state for this step's velocity / XSPH kernels
     float* state[4] = {nullptr, nullptr, nullptr, nullptr};        // my registered pos A, pos B, vel A, vel B
     uint32_t* state_iid = nullptr;
     uint32_t state_seq = 0;          // handshake number of my neighbours' "state complete" signal to wait for
@@ -944,6 +946,7 @@ int pbf_stage_begin(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel
     s->n_local = n; s->own_first = 0; s->own_count = n;
     s->layout_valid = false;
     s->wait_valid = false;
+    s->state_push = StatePush();
     s->cur = 0;
     s->iters_done = 0;
     s->pos0_in_npos = false;
@@ -1070,7 +1073,7 @@ int pbf_stage_update_velocity(pbf_sim* s) {
     //  their ghost slots, so its edge blocks wait for that pass's completion word first)
     HaloSync hs;
     make_sync(s, true, true, &hs);
-    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, hp, hs, s->c, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_UPDATE_VELOCITY, launch_update_velocity(s->x[s->cur], s->rho, s->pos, s->npos, s->vel, s->xl, s->own_first, s->own_count, hp, hs, s->state_push, s->c, s->stream, &s->launches));
     if ((prc = signal_empty_edges(s, hs))) return prc;
     s->v4 = s->xl;
     s->pos0_in_npos = false;
@@ -1086,7 +1089,7 @@ int pbf_stage_correct_velocity(pbf_sim* s) {
     if (prc) return prc;
     HaloSync hs;
     make_sync(s, true, false, &hs);
-    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->v4, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, hs, s->g, s->c, s->mode, s->stream, &s->launches));
+    KTIMED(PBF_KERNEL_XSPH, launch_xsph(s->x[s->cur], s->cull, s->n_local, s->v4, s->cell_range, s->nvel, s->iid_sorted, s->iid, s->own_first, s->own_count, hs, s->state_push, s->g, s->c, s->mode, s->stream, &s->launches));
     s->stage = ST_XSPH;
     return stage_event(s, 5);
 }
@@ -1284,7 +1287,7 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     for (int64_t k = 0; k < slices && n > 0; k++) {
         const int64_t a = n * k / slices, b = n * (k + 1) / slices;
         CUDA_TRY(launch_xsph(s->x[s->cur], s->cull, k == 0 ? s->n_local : 0, s->v4, s->cell_range, s->nvel + 3 * a,
-                             s->iid_sorted, s->iid + a, a, b - a, HaloSync(), s->g, s->c, s->mode, st, &s->launches));
+                             s->iid_sorted, s->iid + a, a, b - a, HaloSync(), StatePush(), s->g, s->c, s->mode, st, &s->launches));
         CUDA_TRY(cudaEventRecord(s->host_ev, st));
         CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
         CUDA_TRY(cudaMemcpyAsync(nvel + 3 * a, s->h_nvel + 3 * a, (size_t)(b - a) * 12, cudaMemcpyDeviceToHost, s->host_copy));
@@ -1337,6 +1340,9 @@ int pbf_slab_begin(pbf_sim* s, const pbf_slab_step* st, float* pos, float* npos,
                                                                 {1, 0, st->n_own + st->m_left, st->m_right}};
         for (auto& q : pull) {
             if (q.cnt <= 0) continue;
+            // the neighbours' velocity / XSPH kernels of the last step stored the particles here themselves
+            // (pbf_slab_push_state): nothing to copy, the wait above was for their end-of-step signal
+            if (st->pull_left_first == PBF_SLAB_STATE_PUSHED) continue;
             const pbf_sim::Peer& pr = s->peer[q.side];
             if (!pr.on || !pr.iid) return fail(PBF_ERR_STATE, "fused slab step: neighbour %d has no registered state attached", q.side);
             CUDA_TRY(cudaMemcpyAsync(pos + 3 * q.dst, pr.state[which] + 3 * q.src, (size_t)q.cnt * 12, cudaMemcpyDefault, s->stream));
@@ -1413,6 +1419,7 @@ int pbf_slab_peer_export(pbf_sim* s, pbf_slab_peer_info* out) {
     }
     out->pid = (int64_t)getpid();
     out->device = s->device;
+    out->state_capacity = s->max_particles;
     return PBF_OK;
 }
 
@@ -1449,6 +1456,7 @@ int pbf_slab_peer_attach(pbf_sim* s, int side, const pbf_slab_peer_info* peer) {
     pr.x[0] = (float4*)arr[0]; pr.x[1] = (float4*)arr[1]; pr.xl = (float4*)arr[2]; pr.sync = (uint32_t*)arr[3];
     for (int k = 0; k < 4; k++) pr.state[k] = (float*)arr[4 + k];
     pr.iid = (uint32_t*)arr[8];
+    pr.state_capacity = peer->has_state ? peer->state_capacity : 0;
     pr.on = true;
     return PBF_OK;
 }
@@ -1471,6 +1479,36 @@ int pbf_slab_halo_sync(pbf_sim* s) {
     if (rc) return rc;
     CUDA_TRY(launch_halo_wait(s->peer[0].on ? s->sync_words + 0 : nullptr, s->peer[1].on ? s->sync_words + 1 : nullptr,
                               s->halo_seq, s->halo_timeout_ns, s->flags_dev, s->stream, &s->launches));
+    return PBF_OK;
+}
+
+int pbf_slab_push_state(pbf_sim* s, int64_t left_count, int64_t left_dst, int64_t right_first, int64_t right_dst) {
+    if (!s) return fail(PBF_ERR_INVALID, "null handle");
+    if (!s->slab_on || !s->layout_valid) return fail(PBF_ERR_STATE, "push_state: no slab layout (pbf_slab_begin .. pbf_stage_build_grid first)");
+    if (s->stage == ST_VELOCITY || s->stage == ST_XSPH) return fail(PBF_ERR_STATE, "push_state: arm it before pbf_stage_update_velocity");
+    if (!s->state_iid) return fail(PBF_ERR_STATE, "push_state: no registered state arrays");
+    const int which = s->pos == s->state[0] ? 0 : s->pos == s->state[1] ? 1 : -1;
+    if (which < 0 || s->npos != s->state[which ^ 1] || s->nvel != s->state[2 + (which ^ 1)] || s->iid != s->state_iid)
+        return fail(PBF_ERR_INVALID, "push_state: the step does not run on the registered state arrays");
+    const int64_t n = s->own_count;
+    if (left_count < 0 || left_count > n || right_first < 0 || right_first > n || left_dst < 0 || right_dst < 0)
+        return fail(PBF_ERR_INVALID, "push_state: ranges outside the %lld owned particles", (long long)n);
+    StatePush sp;
+    // every rank uses buffers A and B in the same rhythm (pbf_slab_register_state): my npos / nvel of this step and
+    // the neighbours' are the same letter, and they are the next step's pos / vel
+    const pbf_sim::Peer& L = s->peer[0];
+    const pbf_sim::Peer& R = s->peer[1];
+    if (L.on && L.iid && left_count > 0) {
+        if (left_dst + left_count > L.state_capacity) return fail(PBF_ERR_CAPACITY, "push_state: the left neighbour's arrays hold %lld particles, %lld needed", (long long)L.state_capacity, (long long)(left_dst + left_count));
+        sp.pos_l = L.state[which ^ 1]; sp.vel_l = L.state[2 + (which ^ 1)]; sp.iid_l = L.iid;
+        sp.left_count = left_count; sp.left_dst = left_dst; sp.cap_l = L.state_capacity;
+    }
+    if (R.on && R.iid && right_first < n) {
+        if (right_dst + (n - right_first) > R.state_capacity) return fail(PBF_ERR_CAPACITY, "push_state: the right neighbour's arrays hold %lld particles, %lld needed", (long long)R.state_capacity, (long long)(right_dst + n - right_first));
+        sp.pos_r = R.state[which ^ 1]; sp.vel_r = R.state[2 + (which ^ 1)]; sp.iid_r = R.iid;
+        sp.right_first = right_first; sp.right_dst = right_dst; sp.cap_r = R.state_capacity;
+    }
+    s->state_push = sp;
     return PBF_OK;
 }
 

@@ -118,6 +118,19 @@ __device__ __forceinline__ void halo_push(const HaloPush& hp, int64_t t, const f
     if (hp.right && t >= hp.right_first) hp.right[t - hp.right_first] = v;
 }
 
+// Fused raw-state hand-over (slab mode with attached neighbours and registered state arrays): the kernels that write
+// a particle's FINAL position (update_velocity), velocity and iid (the XSPH sweep) also store them — for the owned
+// particles of the planes a neighbour will need for its next step — straight into that neighbour's input arrays of
+// the next step, behind its own particles, where pbf_slab_begin would otherwise copy them to with six peer-memory
+// copies at the start of the next step (pbf_slab_push_state). `t` = index among the owned slots.
+struct StatePush {
+    float* pos_l = nullptr;  float* vel_l = nullptr;  uint32_t* iid_l = nullptr;   // the left neighbour's next input arrays
+    float* pos_r = nullptr;  float* vel_r = nullptr;  uint32_t* iid_r = nullptr;   // the right neighbour's
+    int64_t left_count = 0, left_dst = 0;     // owned t in [0, left_count)  -> the left neighbour's slot left_dst + t
+    int64_t right_first = 0, right_dst = 0;   // owned t in [right_first, n) -> the right neighbour's slot right_dst + t - right_first
+    int64_t cap_l = 0, cap_r = 0;             // slots the neighbours' arrays hold (a store beyond is dropped)
+};
+
 // In-kernel handshake of the fused halo (slab mode with attached peers; everything zero / null otherwise).
 // Only the particles of a slab's first and last `ghost` planes — its two EDGES — exchange anything with a
 // neighbour: they are the ones whose results are pushed into the neighbour's ghost slots, and the only ones whose
@@ -257,7 +270,7 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
                            const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
-                                   const HaloSync& hs, const SolverConsts& c, cudaStream_t st, int64_t* launches);
+                                   const HaloSync& hs, const StatePush& sp, const SolverConsts& c, cudaStream_t st, int64_t* launches);
 // slab.cu: flag handshake of a fused halo refresh. signal: store `seq` (release, system scope) to
 // a word in a peer's memory; wait: spin until the local word reaches `seq`, give up after
 // `timeout_ns` and raise PBF_SLAB_FLAG_TIMEOUT instead of hanging the device.
@@ -271,7 +284,7 @@ cudaError_t launch_halo_wait(const uint32_t* word_left, const uint32_t* word_rig
                              uint64_t timeout_ns, uint32_t* flags, cudaStream_t st, int64_t* launches);
 cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
-                        int64_t first, int64_t n, const HaloSync& hs, const GridConsts& g, const SolverConsts& c,
+                        int64_t first, int64_t n, const HaloSync& hs, const StatePush& sp, const GridConsts& g, const SolverConsts& c,
                         const SweepMode& mode, cudaStream_t st, int64_t* launches);
 // slab mode with in-kernel halo handshakes: the cull's coordinates of the GHOST slots [0, own_first) and
 // [own_first + own_count, n_slots) of `x` (the owned slots were written by the pass that produced x); its blocks

@@ -565,7 +565,7 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
                        float* __restrict__ pos_out, float* __restrict__ npos_io,
                        float* __restrict__ vel_out, float4* __restrict__ v4, int64_t first, int64_t n,
                        const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
-                       const __grid_constant__ SolverConsts c) {
+                       const __grid_constant__ StatePush sp, const __grid_constant__ SolverConsts c) {
     pdl_wait();
     const uint32_t lb = halo_block(hs);
     halo_enter(hs, lb);   // (edge blocks: the neighbours are done with what this kernel's pushes overwrite)
@@ -583,6 +583,7 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
     store_f3(vel_out, t, vx, vy, vz);
     store_f3(pos_out, t, p0.x, p0.y, p0.z);
     store_f3(npos_io, t, q.x, q.y, q.z);
+    push_state_pos(sp, t, q.x, q.y, q.z);
     halo_exit(hs, lb);
 }
 
@@ -591,7 +592,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
             const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
-            const __grid_constant__ HaloSync hs, const __grid_constant__ GridConsts g,
+            const __grid_constant__ HaloSync hs, const __grid_constant__ StatePush sp, const __grid_constant__ GridConsts g,
             const __grid_constant__ SolverConsts c) {
     pdl_wait();
     extern __shared__ uint2 s_words[];
@@ -618,8 +619,11 @@ xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __res
         ay = __fadd_rn(ay, __fdiv_rn(__fmul_rn(__fadd_rn(ty, ty), w), den));
         az = __fadd_rn(az, __fdiv_rn(__fmul_rn(__fadd_rn(tz, tz), w), den));
     });
-    store_f3(nvel_out, t, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
-    iid_out[t] = iid_sorted[i];
+    const float ox = __fmaf_rn(c.c_xsph, ax, vi.x), oy = __fmaf_rn(c.c_xsph, ay, vi.y), oz = __fmaf_rn(c.c_xsph, az, vi.z);
+    const uint32_t id = iid_sorted[i];
+    store_f3(nvel_out, t, ox, oy, oz);
+    iid_out[t] = id;
+    push_state_vel(sp, t, ox, oy, oz, id);
 }
 
 // ---- two particles per thread: the paired sweeps (PBF_OPT_PAIRED) ---------------------------------------------------
@@ -895,7 +899,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, PBF_PAIRED_MINBLOCKS)
 xsph2_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
              const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
              const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
-             const __grid_constant__ HaloSync hs, const __grid_constant__ GridConsts g,
+             const __grid_constant__ HaloSync hs, const __grid_constant__ StatePush sp, const __grid_constant__ GridConsts g,
              const __grid_constant__ SolverConsts c) {
     pdl_wait();
     extern __shared__ uint2 s_words[];
@@ -909,11 +913,19 @@ xsph2_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __re
     XsphAcc accA(pA, v4[iA], v4, c), accB(pB, validB ? v4[iB] : v4[iA], v4, c);
     gather2<true>(pA, pB, validB, (uint32_t)iA, (uint32_t)iB, c.h2, x, soa, cell_range, g, s_words + threadIdx.x,
                   s_words + PAIR_THREADS + threadIdx.x, accA, accB);
-    store_f3(nvel_out, tA, __fmaf_rn(c.c_xsph, accA.ax, accA.vi.x), __fmaf_rn(c.c_xsph, accA.ay, accA.vi.y), __fmaf_rn(c.c_xsph, accA.az, accA.vi.z));
-    iid_out[tA] = iid_sorted[iA];
+    {
+        const float ox = __fmaf_rn(c.c_xsph, accA.ax, accA.vi.x), oy = __fmaf_rn(c.c_xsph, accA.ay, accA.vi.y), oz = __fmaf_rn(c.c_xsph, accA.az, accA.vi.z);
+        const uint32_t id = iid_sorted[iA];
+        store_f3(nvel_out, tA, ox, oy, oz);
+        iid_out[tA] = id;
+        push_state_vel(sp, tA, ox, oy, oz, id);
+    }
     if (validB) {
-        store_f3(nvel_out, tB, __fmaf_rn(c.c_xsph, accB.ax, accB.vi.x), __fmaf_rn(c.c_xsph, accB.ay, accB.vi.y), __fmaf_rn(c.c_xsph, accB.az, accB.vi.z));
-        iid_out[tB] = iid_sorted[iB];
+        const float ox = __fmaf_rn(c.c_xsph, accB.ax, accB.vi.x), oy = __fmaf_rn(c.c_xsph, accB.ay, accB.vi.y), oz = __fmaf_rn(c.c_xsph, accB.az, accB.vi.z);
+        const uint32_t id = iid_sorted[iB];
+        store_f3(nvel_out, tB, ox, oy, oz);
+        iid_out[tB] = id;
+        push_state_vel(sp, tB, ox, oy, oz, id);
     }
 }
 
@@ -1097,11 +1109,11 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
 
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
-                                   const HaloSync& hs_in, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+                                   const HaloSync& hs_in, const StatePush& sp, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     HaloSync hs = hs_in;
     halo_sync_blocks(hs, n, 256);
-    PBF_LAUNCH((update_velocity_kernel), nblocks(n, 256), 256, 0, st, x, rho, pos_out, npos_io, vel_out, v4, first, n, hp, hs, c);
+    PBF_LAUNCH((update_velocity_kernel), nblocks(n, 256), 256, 0, st, x, rho, pos_out, npos_io, vel_out, v4, first, n, hp, hs, sp, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -1109,7 +1121,7 @@ cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos
 // n_slots > 0: refresh the cull's coordinate arrays first; 0: they are current (a further chunk of the same sweep)
 cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const float4* v4,
                         const uint2* cell_range, float* nvel_out, const uint32_t* iid_sorted, uint32_t* iid_out,
-                        int64_t first, int64_t n, const HaloSync& hs_in, const GridConsts& g, const SolverConsts& c,
+                        int64_t first, int64_t n, const HaloSync& hs_in, const StatePush& sp, const GridConsts& g, const SolverConsts& c,
                         const SweepMode& mode, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return cudaSuccess;
     if (n_slots > 0) {
@@ -1117,18 +1129,18 @@ cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const
         if (pe != cudaSuccess) return pe;
     }
     if (use_team(mode, n)) {
-        launch_xsph_team(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs_in, g, c, st);
+        launch_xsph_team(x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs_in, sp, g, c, st);
         if (launches) (*launches)++;
         return cudaGetLastError();
     }
     HaloSync hs = hs_in;
     halo_sync_blocks(hs, n, GATHER_THREADS);
     if (mode.paired)
-        PBF_LAUNCH((xsph2_kernel), nblocks(n, GATHER_THREADS), PAIR_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
+        PBF_LAUNCH((xsph2_kernel), nblocks(n, GATHER_THREADS), PAIR_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c);
     else if (mode.rebin && mode.moved)
-        PBF_LAUNCH((xsph_kernel<true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
+        PBF_LAUNCH((xsph_kernel<true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c);
     else
-        PBF_LAUNCH((xsph_kernel<false>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
+        PBF_LAUNCH((xsph_kernel<false>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

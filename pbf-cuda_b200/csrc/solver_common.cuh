@@ -149,6 +149,22 @@ __device__ __forceinline__ void halo_exit(const HaloSync& hs, uint32_t lb) {
     }
 }
 
+// StatePush (pbf_internal.h): a boundary particle's final position / velocity + iid into the neighbours' next input
+__device__ __forceinline__ void push_state_pos(const StatePush& sp, int64_t t, float x, float y, float z) {
+    if (sp.pos_l && t < sp.left_count && sp.left_dst + t < sp.cap_l) store_f3(sp.pos_l, sp.left_dst + t, x, y, z);
+    if (sp.pos_r && t >= sp.right_first && sp.right_dst + (t - sp.right_first) < sp.cap_r) store_f3(sp.pos_r, sp.right_dst + (t - sp.right_first), x, y, z);
+}
+__device__ __forceinline__ void push_state_vel(const StatePush& sp, int64_t t, float x, float y, float z, uint32_t id) {
+    if (sp.vel_l && t < sp.left_count && sp.left_dst + t < sp.cap_l) {
+        store_f3(sp.vel_l, sp.left_dst + t, x, y, z);
+        sp.iid_l[sp.left_dst + t] = id;
+    }
+    if (sp.vel_r && t >= sp.right_first && sp.right_dst + (t - sp.right_first) < sp.cap_r) {
+        store_f3(sp.vel_r, sp.right_dst + (t - sp.right_first), x, y, z);
+        sp.iid_r[sp.right_dst + (t - sp.right_first)] = id;
+    }
+}
+
 // VelTail (pbf_internal.h): the velocity update of particle t (slot i) right behind its final position `q`
 __device__ __forceinline__ void velocity_tail(const VelTail& vt, int64_t t, int64_t i, const float4 q) {
     const float3 p0 = load_f3(vt.npos_io, t);
@@ -219,7 +235,7 @@ void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut c
                                 const uint32_t* pair_cnt, const uint2* cell_range, const HaloPush& hp, HaloSync hs,
                                 const VelTail& vt, const GridConsts& g, const SolverConsts& c, int pow_mode, cudaStream_t st);
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
-                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, HaloSync hs,
+                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, HaloSync hs, const StatePush& sp,
                       const GridConsts& g, const SolverConsts& c, cudaStream_t st);
 
 }  // namespace pbf

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, 8)
 xsph_team_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
                  const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
                  const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
-                 const __grid_constant__ HaloSync hs, const __grid_constant__ GridConsts g,
+                 const __grid_constant__ HaloSync hs, const __grid_constant__ StatePush sp, const __grid_constant__ GridConsts g,
                  const __grid_constant__ SolverConsts c) {
     pdl_wait();
     extern __shared__ uint32_t s_list[];
@@ -294,8 +294,11 @@ xsph_team_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* 
             az = __fadd_rn(az, team_bcast(tm, ez, m));
         });
     if (tm.lane != 0) return;
-    store_f3(nvel_out, t, __fmaf_rn(c.c_xsph, ax, vi.x), __fmaf_rn(c.c_xsph, ay, vi.y), __fmaf_rn(c.c_xsph, az, vi.z));
-    iid_out[t] = iid_sorted[i];
+    const float ox = __fmaf_rn(c.c_xsph, ax, vi.x), oy = __fmaf_rn(c.c_xsph, ay, vi.y), oz = __fmaf_rn(c.c_xsph, az, vi.z);
+    const uint32_t id = iid_sorted[i];
+    store_f3(nvel_out, t, ox, oy, oz);
+    iid_out[t] = id;
+    push_state_vel(sp, t, ox, oy, oz, id);
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------------
@@ -344,10 +347,10 @@ void launch_delta_p_replay_team(const float4* xl, float4* x_out, const CullOut c
 }
 
 void launch_xsph_team(const float4* x, const CullSoA soa, const float4* v4, const uint2* cell_range, float* nvel_out,
-                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, HaloSync hs,
+                      const uint32_t* iid_sorted, uint32_t* iid_out, int64_t first, int64_t n, HaloSync hs, const StatePush& sp,
                       const GridConsts& g, const SolverConsts& c, cudaStream_t st) {
     halo_sync_blocks(hs, n, TEAM_PARTICLES);
-    PBF_LAUNCH((xsph_team_kernel), team_blocks(n), TEAM_THREADS, TEAM_SMEM, st, x, soa, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, g, c);
+    PBF_LAUNCH((xsph_team_kernel), team_blocks(n), TEAM_THREADS, TEAM_SMEM, st, x, soa, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c);
 }
 
 }  // namespace pbf

@@ -24,7 +24,7 @@ restricted to the particles it sees; ghosts are exact copies refreshed from thei
 import numpy as np
 
 from . import (HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY, SLAB_FLAG_GHOST, SLAB_FLAG_MIGRATION, SLAB_FLAG_TIMEOUT,
-               SlabPeerInfo, SlabStep)
+               SLAB_STATE_PUSHED, SlabPeerInfo, SlabStep)
 import ctypes as _C
 
 
@@ -408,6 +408,10 @@ class GpuEngine:
     def halo_sync(self):
         self.sim.slab_halo_sync()
 
+    def push_state(self, left_count, left_dst, right_first, right_dst):
+        """Arms the fused raw-state hand-over of this step (include/pbf.h pbf_slab_push_state)."""
+        self.sim.slab_push_state(left_count, left_dst, right_first, right_dst)
+
     def flags(self):
         return self.sim.slab_flags()
 
@@ -564,10 +568,17 @@ class SlabSimulator:
         caller that wants them on the host can start the download under the XSPH sweep (bench.py's e2e leg)."""
         e, r, w = self.e, self.rank, self.world
         old = self.bounds
-        new = old
-        if self.replan_every and self.steps and self.steps % self.replan_every == 0 and w > 1:
-            new = plan_boundaries(self._counts().sum(axis=0), w, self.min_width, old=old, reach=self.reach)
-        xp = exchange_plan(self._counts(), old, new, r, self.reach)
+        pushed = False
+        if self._planned is not None:    # planned during the last step; the neighbours' kernels delivered the raw state
+            new, xp = self._planned
+            self._planned = None
+            pushed = True
+            self.pushed_steps += 1
+        else:
+            new = old
+            if self.replan_every and self.steps and self.steps % self.replan_every == 0 and w > 1:
+                new = plan_boundaries(self._counts().sum(axis=0), w, self.min_width, old=old, reach=self.reach)
+            xp = exchange_plan(self._counts(), old, new, r, self.reach)
         n_own = e.n_own
         assert n_own == int(self.counts[r].sum())
         m_l, m_r = xp["m_left"], xp["m_right"]
@@ -579,7 +590,8 @@ class SlabSimulator:
             self._m("raw_exchange")
         st = SlabStep(x_begin=new[r], x_end=new[r + 1], ghost=self.ghost, has_left=int(r > 0), has_right=int(r < w - 1),
                       n_own=n_own, m_left=m_l, m_right=m_r, send_left_end=xp["send_left_end"],
-                      send_right_begin=xp["send_right_begin"], pull_left_first=xp["pull_left_first"])
+                      send_right_begin=xp["send_right_begin"],
+                      pull_left_first=SLAB_STATE_PUSHED if pushed else xp["pull_left_first"])
         # 2. keys, one stable sort, layout (the step's one host synchronisation on the compute stream)
         e.begin(st)
         if self.fused:
@@ -605,6 +617,8 @@ class SlabSimulator:
             self._m("halo")
         if self.niter == 0:
             self._gather_counts()
+        if self.fused and w > 1 and self.push_state and hasattr(e, "push_state"):
+            self._plan_next(new)
         e.update_velocity()
         self._m("update_velocity")
         if after_velocity is not None:
@@ -616,6 +630,37 @@ class SlabSimulator:
         e.end()
         self.bounds = new
         self.steps += 1
+
+    # fused raw-state hand-over: on by default with the fused halo (off: pbf_slab_begin pulls, six peer copies per step)
+    push_state = True
+    pushed_steps = 0     # steps whose raw state came by the neighbours' stores (all but the first in fused mode)
+    _planned = None
+
+    def _plan_next(self, cur):
+        """The NEXT step's plan, made before this step's velocity update is enqueued: the per-plane counts of this
+        step's sort are replicated by now (the all-gather was started behind the first lambda pass, a millisecond
+        of device work ago), and the plan is a function of that table alone. Knowing it here lets this step's
+        velocity / XSPH kernels store the raw state of the boundary planes straight into the neighbours' next
+        input arrays (pbf_slab_push_state) — where each range lands follows from the same table: behind the
+        neighbour's own particles, and behind what ITS left neighbour delivers on its right-hand side."""
+        e, r, w = self.e, self.rank, self.world
+        counts = self._counts()
+        nxt = cur
+        if self.replan_every and (self.steps + 1) % self.replan_every == 0:
+            nxt = plan_boundaries(counts.sum(axis=0), w, self.min_width, old=cur, reach=self.reach)
+        xp = exchange_plan(counts, cur, nxt, r, self.reach)
+        n_next = int(counts[r].sum())
+        left_dst = right_dst = 0
+        if r > 0:
+            xl = exchange_plan(counts, cur, nxt, r - 1, self.reach)
+            assert xl["m_right"] == xp["send_left_end"], (xl, xp)
+            left_dst = int(counts[r - 1].sum()) + xl["m_left"]
+        if r < w - 1:
+            xr = exchange_plan(counts, cur, nxt, r + 1, self.reach)
+            assert xr["m_left"] == n_next - xp["send_right_begin"] and xr["pull_left_first"] == xp["send_right_begin"], (xr, xp)
+            right_dst = int(counts[r + 1].sum())
+        e.push_state(xp["send_left_end"] if r > 0 else 0, left_dst, xp["send_right_begin"] if r < w - 1 else n_next, right_dst)
+        self._planned = (nxt, xp)
 
     def _halo(self, what):
         if self.world == 1:

@@ -90,7 +90,8 @@ def _run_ranks(pbf, slab, torch, scene, world, steps, ghost, margin, replan_ever
                 stream.synchronize()
                 sp, sv, si = eng.state()
                 results[rank] = dict(pos=sp.cpu().numpy(), vel=sv.cpu().numpy(), iid=si.cpu().numpy().view(np.uint32),
-                                     bounds=bounds, messages=sim.messages, launches=eng.sim.launch_count())
+                                     bounds=bounds, messages=sim.messages, launches=eng.sim.launch_count(),
+                                     pushed=sim.pushed_steps)
                 hub.barrier.wait(timeout=120)   # nobody frees arrays a neighbour may still be pushing into
                 eng.close()
         except BaseException as ex:   # noqa: BLE001 - reported by the main thread
@@ -128,6 +129,9 @@ def test_slab_ranks_equal_single_gpu_bit_for_bit(pbf, torch, name, world, replan
     assert np.array_equal(pos, ref_pos)
     assert np.array_equal(vel, ref_vel)
     assert all(r["launches"] > 0 for r in results)
+    # fused: from the second step on the raw state of the boundary planes arrives by the neighbours' own stores
+    # (pbf_slab_push_state), through re-plans too; otherwise by the transport
+    assert all(r["pushed"] == (steps - 1 if fused else 0) for r in results)
     if skew:
         b = results[0]["bounds"]
         assert any(row != b[0] for row in b), "the re-plan never moved a boundary"
