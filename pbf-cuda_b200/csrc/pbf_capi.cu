@@ -160,6 +160,10 @@ struct pbf_sim {
         int64_t state_capacity = 0;                                // particles its state arrays hold
         void* ipc_base[9] = {};                                    // opened IPC mappings to close
     } peer[2];
+    // Morton-ordered keys (PBF_OPT_MORTON): spread tables of the current grid dimensions on the device
+    uint32_t* morton_dev = nullptr;
+    int32_t morton_dims[3] = {0, 0, 0};
+    int morton_bits = 0;
     StatePush state_push;            // armed by pbf_slab_push_state for this step's velocity / XSPH kernels
     float* state[4] = {nullptr, nullptr, nullptr, nullptr};        // my registered pos A, pos B, vel A, vel B
     uint32_t* state_iid = nullptr;
@@ -280,7 +284,37 @@ int refresh_consts(pbf_sim* s) {
         g.flags = s->flags_dev;
         s->ghost_left = sl.x_begin - lo;
     }
-    const int64_t ncell = (int64_t)g.nxl * g.dim[1] * g.dim[2];
+    int64_t ncell = (int64_t)g.nxl * g.dim[1] * g.dim[2];
+    g.morton = nullptr;
+    if (s->mode.morton) {
+        // bit-interleaved keys: axis a contributes ceil(log2 dim[a]) bits, dealt round-robin from the lowest bit in the
+        // order z, y, x (z fastest, like the reference's key); the key space — and the cell table — is the power of two
+        if (s->slab_on) return fail(PBF_ERR_INVALID, "PBF_OPT_MORTON: single-GPU steps only (x-planes are not contiguous slot ranges in Morton order)");
+        int bits[3], total = 0;
+        for (int a = 0; a < 3; a++) { bits[a] = key_bits(g.dim[a]); if (g.dim[a] <= 1) bits[a] = 0; total += bits[a]; }
+        if (bits[0] > 10 || bits[1] > 10 || bits[2] > 10 || total > 29) return fail(PBF_ERR_CAPACITY, "PBF_OPT_MORTON: grid %d x %d x %d needs more than 10 bits per axis", g.dim[0], g.dim[1], g.dim[2]);
+        ncell = (int64_t)1 << total;
+        if (memcmp(s->morton_dims, g.dim, sizeof(g.dim)) != 0 || !s->morton_dev) {
+            static uint32_t table[3 * 1024];
+            int place[3][10];
+            int pos = 0;
+            for (int b = 0; b < 10; b++)
+                for (int a = 2; a >= 0; a--)
+                    if (b < bits[a]) place[a][b] = pos++;
+            for (int a = 0; a < 3; a++)
+                for (int v = 0; v < 1024; v++) {
+                    uint32_t k = 0;
+                    for (int b = 0; b < bits[a]; b++) k |= (uint32_t)((v >> b) & 1) << place[a][b];
+                    table[a * 1024 + v] = k;
+                }
+            if (cudaSetDevice(s->device) != cudaSuccess) return fail(PBF_ERR_CUDA, "cudaSetDevice");
+            if (!s->morton_dev && cudaMalloc((void**)&s->morton_dev, sizeof(table)) != cudaSuccess) return fail(PBF_ERR_CUDA, "PBF_OPT_MORTON: no memory for the spread tables");
+            if (cudaMemcpy(s->morton_dev, table, sizeof(table), cudaMemcpyHostToDevice) != cudaSuccess) return fail(PBF_ERR_CUDA, "PBF_OPT_MORTON: table upload failed");
+            memcpy(s->morton_dims, g.dim, sizeof(g.dim));
+        }
+        s->morton_bits = total;
+        g.morton = s->morton_dev;
+    }
     if (ncell > s->cell_capacity || ncell >= ((int64_t)1 << 30) - 1)
         return fail(PBF_ERR_CAPACITY, "box has %lld cells, handle holds %lld", (long long)ncell, (long long)s->cell_capacity);
     g.ncell = (int32_t)ncell;
@@ -420,6 +454,7 @@ void free_all(pbf_sim* s) {
             if (b) cudaIpcCloseMemHandle(b);
     cudaFree(s->sync_words);
     cudaFree(s->halo_done);
+    cudaFree(s->morton_dev);
     cudaFree(s->verify_scratch);
     if (s->verify_stream) cudaStreamDestroy(s->verify_stream);
     if (s->ev_valid) {
@@ -577,6 +612,7 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (const char* rb = getenv("PBF_REBIN")) s->mode.rebin = rb[0] == '1' ? 1 : 0;
     if (const char* sg = getenv("PBF_STAGED")) s->mode.staged = sg[0] == '1' ? 1 : 0;
     if (const char* pr = getenv("PBF_PAIRED")) s->mode.paired = pr[0] == '1' ? 1 : 0;
+    if (const char* mo = getenv("PBF_MORTON")) s->mode.morton = mo[0] == '1' ? 1 : 0;
     if (const char* pd = getenv("PBF_PDL")) s->mode.pdl = pd[0] == '0' ? 0 : 1;
     if (const char* hk = getenv("PBF_HALO_INKERNEL")) s->mode.halo_inkernel = hk[0] == '0' ? 0 : 1;
     if (const char* gr = getenv("PBF_GRAPH")) s->mode.graph = gr[0] == '1' ? 1 : gr[0] == '0' ? 0 : -1;
@@ -693,6 +729,13 @@ int pbf_set_option(pbf_sim* s, int option, int value) {
         case PBF_OPT_PAIRED:
             s->mode.paired = value ? 1 : 0;
             return PBF_OK;
+        case PBF_OPT_MORTON: {
+            const int old = s->mode.morton;
+            s->mode.morton = value ? 1 : 0;
+            int rc = refresh_consts(s);
+            if (rc != PBF_OK) { s->mode.morton = old; refresh_consts(s); }
+            return rc;
+        }
         case PBF_OPT_HALO_INKERNEL:
             s->mode.halo_inkernel = value ? 1 : 0;
             return PBF_OK;
@@ -712,6 +755,7 @@ int pbf_get_option(const pbf_sim* s, int option, int* value) {
         case PBF_OPT_PDL: *value = s->mode.pdl; return PBF_OK;
         case PBF_OPT_STAGED: *value = s->mode.staged; return PBF_OK;
         case PBF_OPT_PAIRED: *value = s->mode.paired; return PBF_OK;
+        case PBF_OPT_MORTON: *value = s->mode.morton; return PBF_OK;
         case PBF_OPT_GRAPH: *value = s->mode.graph; return PBF_OK;
         case PBF_OPT_HALO_INKERNEL: *value = s->mode.halo_inkernel; return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
@@ -1149,7 +1193,7 @@ static int step_graph(pbf_sim* s, float* pos, float* npos, float* vel, float* nv
     StepGraph* lru = nullptr;   // where a new graph goes: a free slot, else the least recently used one
     for (auto& gq : s->graphs) {
         if (gq.exec && gq.n == n && gq.stream == (cudaStream_t)stream && gq.consts_hash == hc &&
-            gq.niter == s->p.niter && gq.team == s->mode.team && gq.rebin == s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired && gq.pdl == s->mode.pdl &&
+            gq.niter == s->p.niter && gq.team == s->mode.team && gq.rebin == s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired + 8 * s->mode.morton && gq.pdl == s->mode.pdl &&
             memcmp(gq.ptr, ptr, sizeof(ptr)) == 0) {
             hit = &gq;
             break;
@@ -1194,7 +1238,7 @@ static int step_graph(pbf_sim* s, float* pos, float* npos, float* vel, float* nv
         }
         memcpy(lru->ptr, ptr, sizeof(ptr));
         lru->n = n; lru->stream = (cudaStream_t)stream; lru->consts_hash = hc;
-        lru->niter = s->p.niter; lru->team = s->mode.team; lru->rebin = s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired; lru->pdl = s->mode.pdl;
+        lru->niter = s->p.niter; lru->team = s->mode.team; lru->rebin = s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired + 8 * s->mode.morton; lru->pdl = s->mode.pdl;
         lru->launches = s->launches - l0;
         lru->sorted_buf = s->sorted_buf; lru->cur = s->cur; lru->iters_done = s->iters_done;
         lru->cull_cur = s->cull.cur; lru->cull_holds = s->cull.holds; lru->v4 = s->v4;

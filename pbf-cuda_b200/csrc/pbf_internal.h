@@ -28,6 +28,10 @@ struct GridConsts {
     // interval (lo > hi) keeps the plain division
     float h_rcp;      // RN(1 / h)
     float hdiv_lo, hdiv_hi;
+    // Morton-ordered keys (PBF_OPT_MORTON, the A/B of DESIGN.md 3.1; single GPU): null = the reference's x-major key.
+    // Else 3 x 1024 words: the bits of a cell coordinate spread to their places in the interleaved key, per axis
+    // ([0..1023] x, [1024..2047] y, [2048..3071] z): key = tx[x] | ty[y] | tz[z]; ncell = the size of that key space.
+    const uint32_t* morton;
 };
 
 // How the caller's particle arrays map to the sort's input order in slab mode (slab.cu).
@@ -245,6 +249,7 @@ struct SweepMode {
                      // (the A/B of DESIGN.md 3.3: measured, not faster — off)
     int paired = 0;  // thread kernels: two consecutive slots per thread, one walk over the union of their candidate runs
                      // (solver.cu gather2): half the cull's loads per test
+    int morton = 0;  // Morton-ordered keys (GridConsts::morton): thread kernels only, 27 one-cell runs instead of 9 runs
     int pdl = 1;     // programmatic dependent launch between the step's kernels (launch.cuh)
     int halo_inkernel = 1;   // fused halo: handshakes inside the pass kernels (HaloSync) instead of two one-thread kernels per refresh
     int graph = -1;  // pbf_step replayed from a CUDA graph: -1 below 256 K particles, 0 never, 1 always (pbf_capi.cu)

@@ -60,7 +60,9 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-template <bool SKIP_SELF, bool STAGED = false, typename Heavy>
+// MORTON (the A/B of DESIGN.md 3.1): keys are bit-interleaved, the three z cells of a column are not neighbours in the
+// sorted order any more — 27 one-cell runs per particle instead of 9 three-cell runs, in the same dx, dy, dz order.
+template <bool SKIP_SELF, bool STAGED = false, bool MORTON = false, typename Heavy>
 __device__ __forceinline__ void gather(const float4 p, const uint32_t self, const float limit,
                                        const float4* __restrict__ x, const CullSoA soa,
                                        const uint2* __restrict__ cell_range, const GridConsts& g,
@@ -108,6 +110,17 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             const int cy = cc.y + dy;
             if (cy < 0 || cy >= g.dim[1]) continue;
             const int cbase = lx * g.dyz + cy * g.dim[2];
+            const uint32_t mxy = MORTON ? (__ldg(g.morton + cx) | __ldg(g.morton + 1024 + cy)) : 0u;
+#pragma unroll 1
+            for (int zi = 0; zi < (MORTON ? 3 : 1); zi++) {
+            uint32_t start, end;
+            if (MORTON) {   // one cell per run
+                const int cz = cc.z + zi - 1;
+                if (cz < 0 || cz >= g.dim[2]) continue;
+                const uint2 r = __ldg(&cell_range[mxy | __ldg(g.morton + 2048 + cz)]);
+                start = r.x;
+                end = r.y;
+            } else {
             // the run = from the first slot of the first non-empty cell of the column's (up to) three to the
             // end of the last non-empty one; empty and out-of-range cells read {0, 0}, so an empty column gives
             // start == end == 0. Straight-line on purpose: as a loop over z (1-3 trips) this was ~80 instructions.
@@ -116,8 +129,9 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             const uint2 r1 = __ldg(&cell_range[cbase + cc.z]);
             const uint2 r2 = has_above ? __ldg(&cell_range[cbase + cc.z + 1]) : zero;
             const bool e0 = r0.y > r0.x, e1 = r1.y > r1.x, e2 = r2.y > r2.x;
-            const uint32_t start = e0 ? r0.x : e1 ? r1.x : r2.x;
-            const uint32_t end = e2 ? r2.y : e1 ? r1.y : r0.y;
+            start = e0 ? r0.x : e1 ? r1.x : r2.x;
+            end = e2 ? r2.y : e1 ? r1.y : r0.y;
+            }
 #pragma unroll 1
             for (uint32_t b = start & ~3u; b < end; b += 32) {   // words start at multiples of four slots
                 const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
@@ -148,6 +162,7 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
                 *tail = make_uint2(b, hits);
                 tail += hits ? GATHER_THREADS : 0;
                 if (tail == words_end) flush();
+            }
             }
         }
     }
@@ -326,7 +341,7 @@ __device__ __forceinline__ bool stage_runs(const float4* __restrict__ x, const C
 // entries are contiguous 8-byte (slot, s) records. A particle with more than PAIR_CAP neighbours
 // is flagged in its count word and handled by the delta-p pass's full gather instead.
 
-template <bool SAVE_PAIRS, bool FAST_SPIKY, bool REBIN, bool STAGED = false>
+template <bool SAVE_PAIRS, bool FAST_SPIKY, bool REBIN, bool STAGED = false, bool MORTON = false>
 __global__ void __launch_bounds__(GATHER_THREADS, STAGED ? 6 : PBF_GATHER_MINBLOCKS)
 lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
               const uint2* __restrict__ cell_range, int64_t first, int64_t n,
@@ -384,7 +399,7 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
     if (STAGED && staged)
         gather<false, true>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, heavy, smem_addr(s_xyz), s_u);
     else
-        gather<false, false>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, heavy);
+        gather<false, false, MORTON>(p, (uint32_t)i, c.h2_cull, x, soa, cell_range, g, s_words + threadIdx.x, heavy);
     if (c.k_boundary != 0.f) rho = __fmaf_rn(c.k_boundary, boundary_density(p.x, p.y, p.z, g), rho);
     const float grad_l2 = __fmaf_rn(giz, giz, __fmaf_rn(giy, giy, __fmaf_rn(gix, gix, gradj_l2)));
     const float lambda = __fdiv_rn(-__fadd_rn(__fdiv_rn(rho, c.pho0), -1.f), __fadd_rn(grad_l2, c.lambda_eps));
@@ -523,7 +538,7 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
 
 // The delta-p pass WITHOUT a neighbour list (the list is optional scratch: PBF_NO_PAIR_REUSE=1, or a handle too
 // large for it): the full two-phase gather for every particle.
-template <int POW, bool REBIN>
+template <int POW, bool REBIN, bool MORTON = false>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restrict__ x_out, const CullOut co,
                const uint2* __restrict__ cell_range, int64_t first, int64_t n, const __grid_constant__ HaloPush hp,
@@ -540,7 +555,7 @@ delta_p_kernel(const float4* __restrict__ xl, const CullSoA soa, float4* __restr
     const int64_t i = first + t;
     const float4 p = xl[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    gather<true>(p, (uint32_t)i, c.h2_cull, xl, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
+    gather<true, false, MORTON>(p, (uint32_t)i, c.h2_cull, xl, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t, float4 q, int) {
         const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
         const float r2 = sumsq(dx, dy, dz);
         const float pw = pow_ncorr<POW>(poly6(r2, c), c);
@@ -587,7 +602,7 @@ update_velocity_kernel(const float4* __restrict__ x, const float* __restrict__ r
     halo_exit(hs, lb);
 }
 
-template <bool REBIN>
+template <bool REBIN, bool MORTON = false>
 __global__ void __launch_bounds__(GATHER_THREADS, PBF_GATHER_MINBLOCKS)
 xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
             const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
@@ -609,7 +624,7 @@ xsph_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __res
     // The particle itself (computeXSPH visits it) contributes 0 / (2 rho_i) = +0 per component, and an
     // accumulator that starts at +0 never becomes -0 (x + y = -0 only for x = y = -0), so adding +0 changes
     // no bit: it is skipped, which keeps three zero dividends off IEEE division's slow path in every warp.
-    gather<true>(p, (uint32_t)i, c.h2, x, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
+    gather<true, false, MORTON>(p, (uint32_t)i, c.h2, x, soa, cell_range, g, s_words + threadIdx.x, [&](uint32_t j, float4 q, int) {
         const float r2 = sumsq(__fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
         const float4 vj = __ldg(&v4[j]);
         const float w = poly6_in(r2, c);
@@ -981,6 +996,15 @@ cudaError_t preload_solver() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda2_kernel<false, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda2_kernel<true, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph2_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, false, false, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, false, false, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<false, true, false, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lambda_kernel<true, true, false, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<0, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<1, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<2, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_kernel<3, false, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_kernel<false, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_ghosts_kernel);
     if (e == cudaSuccess) e = preload_solver_team();
@@ -992,6 +1016,7 @@ static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1)
 // Small scenes take the four-lanes-per-particle kernels of solver_team.cu (latency bound, not throughput bound).
 // The handle's PBF_OPT_TEAM forces the choice (tests run the golden scenes through both, tuning experiments).
 static bool use_team(const SweepMode& mode, int64_t n) {
+    if (mode.morton) return false;   // (the Morton A/B exists for the thread kernels only)
     return mode.team < 0 ? n < TEAM_MAX_PARTICLES : mode.team == 1;
 }
 
@@ -1043,7 +1068,10 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
     halo_sync_blocks(hs, n, GATHER_THREADS);
 #define PBF_LAMBDA_LAUNCH(SAVE, FAST)                                                                                          \
     do {                                                                                                                       \
-        if (mode.paired)                                                                                                       \
+        if (mode.morton)                                                                                                       \
+            PBF_LAUNCH((lambda_kernel<SAVE, FAST, false, false, true>), nb, GATHER_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n, \
+                       pl.js, pl.cnt, hp, hs, g, c);                                                                         \
+        else if (mode.paired)                                                                                                  \
             PBF_LAUNCH((lambda2_kernel<SAVE, FAST>), nb, PAIR_THREADS, LIST_SMEM, st, x, soa, xl, rho, cell_range, first, n,   \
                        pl.js, pl.cnt, hp, hs, g, c);                                                                         \
         else if (mode.staged && !mode.moved)                                                                                        \
@@ -1084,6 +1112,8 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
             if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, cell_range, hp, hs_in, vt, g, c, POW, st); \
             else PBF_LAUNCH((delta_p_replay_kernel<POW>), nb, GATHER_THREADS, 0, st, xl, x_out, co, first, n, pl.js, pl.cnt,  \
                             cell_range, hp, hs, vt, g, c);                                                                   \
+        } else if (mode.morton) {                                                                                             \
+            PBF_LAUNCH((delta_p_kernel<POW, false, true>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, hs, vt, g, c); \
         } else if (mode.rebin && mode.moved) {                                                                                \
             PBF_LAUNCH((delta_p_kernel<POW, true>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, hs, vt, g, c); \
         } else {                                                                                                              \
@@ -1135,7 +1165,9 @@ cudaError_t launch_xsph(const float4* x, CullScratch& cs, int64_t n_slots, const
     }
     HaloSync hs = hs_in;
     halo_sync_blocks(hs, n, GATHER_THREADS);
-    if (mode.paired)
+    if (mode.morton)
+        PBF_LAUNCH((xsph_kernel<false, true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c);
+    else if (mode.paired)
         PBF_LAUNCH((xsph2_kernel), nblocks(n, GATHER_THREADS), PAIR_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c);
     else if (mode.rebin && mode.moved)
         PBF_LAUNCH((xsph_kernel<true>), nblocks(n, GATHER_THREADS), GATHER_THREADS, LIST_SMEM, st, x, soa_of(cs), v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c);

@@ -202,7 +202,7 @@ __device__ __noinline__ float4 delta_p_one(const float4* __restrict__ xl, uint32
             for (int dz = -1; dz <= 1; dz++) {
                 const int cz = cc.z + dz;
                 if (cz < 0 || cz >= g.dim[2]) continue;
-                const uint2 r = __ldg(&cell_range[lx * g.dyz + cy * g.dim[2] + cz]);
+                const uint2 r = __ldg(&cell_range[cell_id(cx, cy, cz, g)]);   // (x-major: lx * dyz + cy * dim z + cz)
                 for (uint32_t j = r.x; j < r.y; j++) {
                     if (j == i) continue;
                     const float4 q = __ldg(&xl[j]);

@@ -457,6 +457,8 @@ class SlabSimulator:
         # fused_halo: the ghost refreshes are peer-memory stores issued by the pass kernels themselves plus a
         # flag handshake (include/pbf.h "Fused halo refresh"); otherwise one send/recv pair per side through comm
         self.fused = bool(fused_halo) and comm.world > 1
+        import os
+        self.push_state = os.environ.get("PBF_SLAB_PUSH", "1") != "0"   # (A/B switch: 0 = pbf_slab_begin pulls)
         self.bounds = None
         self.counts = None
         self.steps = 0
