@@ -437,6 +437,20 @@ constexpr int REPLAY_UNROLL3 = PBF_REPLAY_UNROLL3;
 #ifndef PBF_REPLAY_UNROLL2
 #define PBF_REPLAY_UNROLL2 1
 #endif
+// list records this many TRIPS (of two records) ahead are prefetched into L1: the list streams from HBM, and one trip
+// of look-ahead in registers (nx0 / nx1 below) does not cover that latency — half of the replay's stall samples were
+// waits for a record (profiles/r03_delta_p_ncu_per_instruction.txt). 0: off. Measured (dam_1m, ms per launch, early /
+// compressed state): off 0.1324 / 0.1746, 2 trips 0.1283 / 0.1713, 4 trips 0.1291 / 0.1717, 8 trips 0.1320 / 0.1737,
+// 4 trips into L2 only 0.1288 / 0.1717.
+#ifndef PBF_REPLAY_PREFETCH
+#define PBF_REPLAY_PREFETCH 2
+#endif
+constexpr int REPLAY_PREFETCH = PBF_REPLAY_PREFETCH;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef PBF_REPLAY_PREFETCH_L2
+#define PBF_REPLAY_PREFETCH_L2 0
+#endif
 constexpr bool REPLAY_PACKED = PBF_REPLAY_PACKED != 0;
 constexpr int REPLAY_UNROLL2 = PBF_REPLAY_UNROLL2;
 // (the packed POW = 3 loop keeps two pairs in flight: 48 registers, 10 CTAs per SM — measured against 16 (spills),
@@ -485,6 +499,11 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                 if (k + 2 < cnt) {
                     nx0 = __ldg(&pair_js[pair0 + (size_t)(k + 2) * GATHER_THREADS]);
                     nx1 = __ldg(&pair_js[pair0 + (size_t)(k + 3 < cnt ? k + 3 : k + 2) * GATHER_THREADS]);
+                }
+                if (REPLAY_PREFETCH > 0 && k + 2 * REPLAY_PREFETCH + 2 < cnt) {   // (two rows of the list: one line each per 16 lanes)
+                    const uint2* pf = &pair_js[pair0 + (size_t)(k + 2 * REPLAY_PREFETCH + 2) * GATHER_THREADS];
+                    if (PBF_REPLAY_PREFETCH_L2) { prefetch_l2(pf); prefetch_l2(pf + GATHER_THREADS); }
+                    else { prefetch_l1(pf); prefetch_l1(pf + GATHER_THREADS); }
                 }
                 const float4 q0 = __ldg(&xl[js0.x]), q1 = __ldg(&xl[js1.x]);
                 const f32x2 dx = sub2(px, pack2(q0.x, q1.x)), dy = sub2(py, pack2(q0.y, q1.y)), dz = sub2(pz, pack2(q0.z, q1.z));
