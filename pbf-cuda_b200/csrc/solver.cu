@@ -391,7 +391,7 @@ lambda_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restric
             // only s travels: the replay re-forms r2 from the same positions (the same bits) and
             // evaluates poly6 and the ~45-instruction powf there.
             if (SAVE_PAIRS) {
-                if (n_pairs < PAIR_CAP) pair_js[pair0 + (size_t)n_pairs * GATHER_THREADS] = make_uint2(j, __float_as_uint(s));
+                if (n_pairs < PAIR_CAP) list_store(&pair_js[pair0 + (size_t)n_pairs * GATHER_THREADS], j, __float_as_uint(s));
                 n_pairs++;
             }
         }
@@ -489,16 +489,16 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
             //  is a chain of two long-latency loads otherwise)
             uint2 nx0 = make_uint2(0u, 0u), nx1 = nx0;
             if (cnt > 0) {
-                nx0 = __ldg(&pair_js[pair0]);
-                nx1 = __ldg(&pair_js[pair0 + (size_t)(cnt > 1 ? 1 : 0) * GATHER_THREADS]);
+                nx0 = list_load(&pair_js[pair0]);
+                nx1 = list_load(&pair_js[pair0 + (size_t)(cnt > 1 ? 1 : 0) * GATHER_THREADS]);
             }
 #pragma unroll REPLAY_UNROLL2
             for (uint32_t k = 0; k < cnt; k += 2) {
                 const bool two = k + 1 < cnt;
                 const uint2 js0 = nx0, js1 = nx1;
                 if (k + 2 < cnt) {
-                    nx0 = __ldg(&pair_js[pair0 + (size_t)(k + 2) * GATHER_THREADS]);
-                    nx1 = __ldg(&pair_js[pair0 + (size_t)(k + 3 < cnt ? k + 3 : k + 2) * GATHER_THREADS]);
+                    nx0 = list_load(&pair_js[pair0 + (size_t)(k + 2) * GATHER_THREADS]);
+                    nx1 = list_load(&pair_js[pair0 + (size_t)(k + 3 < cnt ? k + 3 : k + 2) * GATHER_THREADS]);
                 }
                 if (REPLAY_PREFETCH > 0 && k + 2 * REPLAY_PREFETCH + 2 < cnt) {   // (two rows of the list: one line each per 16 lanes)
                     const uint2* pf = &pair_js[pair0 + (size_t)(k + 2 * REPLAY_PREFETCH + 2) * GATHER_THREADS];
@@ -535,7 +535,7 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
 #pragma unroll (POW == 3 ? REPLAY_UNROLL3 : 4)
             for (uint32_t k = 0; k < cnt; k++) {
                 const size_t e = pair0 + (size_t)k * GATHER_THREADS;
-                const uint2 js = __ldg(&pair_js[e]);
+                const uint2 js = list_load(&pair_js[e]);
                 const float4 q = __ldg(&xl[js.x]);
                 const float sj = __uint_as_float(js.y);  // spiky scale of the pair, saved by the lambda pass
                 const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
@@ -850,7 +850,7 @@ struct LambdaAcc {
             giz = __fadd_rn(giz, gz);
             gradj_l2 = __fadd_rn(gradj_l2, sumsq(gx, gy, gz));
             if (SAVE_PAIRS) {
-                if (n_pairs < PAIR_CAP) pair_col[(size_t)n_pairs * GATHER_THREADS] = make_uint2(j, __float_as_uint(s));
+                if (n_pairs < PAIR_CAP) list_store(&pair_col[(size_t)n_pairs * GATHER_THREADS], j, __float_as_uint(s));
                 n_pairs++;
             }
         }
