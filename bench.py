@@ -101,38 +101,58 @@ def hexd(d):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe). The query loop is
+    started when the object is made — before the warm-up steps, nvidia-smi takes ~0.2 s to deliver its first line and
+    a 20-step window lasts 40 ms — and `start()` / `stop()` bracket the timed region: the samples that arrived between
+    them count (plus the first one after `stop()` if the window was shorter than the 50 ms period: the device is still
+    at its load clocks then)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, launch=True):
+        self.index, self.proc, self.lines, self.t0 = index, None, [], None
+        if launch:
+            self._launch()
 
-    def start(self):
+    def _launch(self):
+        if self.proc:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def start(self):
+        self._launch()
+        self.t0 = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = time.time()
+        deadline = t1 + 1.0
+        while not any(t >= t0 for t, _ in self.lines) and time.time() < deadline:
+            time.sleep(0.01)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for t, ln in self.lines if t0 <= t <= t1]
+        if not inside:
+            inside = [ln for t, ln in self.lines if t >= t0][:1]
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -276,7 +296,7 @@ def run_product(args, rank, world, dist):
     run = ProductRun(pbf, torch, local, args.scene)
     sc, n, sim = run.sc, run.n, run.sim
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, launch=(rank == 0))
     launches0 = [0]
 
     def before():
@@ -536,7 +556,7 @@ def slab_leg(args, pbf, slab, torch, dist, rank, world, local, name, scaling, st
         raise SystemExit("slab initialisation lost particles: %d of %d" % (sim.total_particles(), n_total))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, launch=(rank == 0 and full))
     mark = {}
 
     def before():
@@ -725,12 +745,12 @@ def run_product_slab(args, rank, world, dist):
     return out
 
 
-# ncu --set full of the dominant kernels, dam_1m at step ~100 — the state the kernel timers above see
-# (profiles/r01h_solver_ncu_summary.txt): dram__bytes_read.sum + dram__bytes_write.sum per launch, issue slots busy,
-# L1 data-pipe wavefront rate, DRAM throughput. A separate run under the profiler: labelled as such in the line.
-NCU = {"source": "profiles/r01h_solver_ncu_summary.txt (ncu --set full, dam_1m, step 100)",
-       "lambda": {"traffic": 432.8e6, "issue": 0.67, "l1": 0.74, "dram": 0.12},
-       "delta_p": {"traffic": 453.8e6, "issue": 0.76, "l1": None, "dram": 0.27}}
+# ncu --set full of the dominant kernels, dam_1m at step 100 (profiles/r03_solver_ncu_summary.txt, the build of the last
+# session of round 2; means over the four launches of the step): dram__bytes_read.sum + dram__bytes_write.sum per launch,
+# issue slots busy, l1tex throughput, DRAM throughput. A separate run under the profiler: labelled as such in the line.
+NCU = {"source": "profiles/r03_solver_ncu_summary.txt (ncu --set full, dam_1m, step 100)",
+       "lambda": {"traffic": 462.8e6, "issue": 0.70, "l1": 0.77, "dram": 0.12},
+       "delta_p": {"traffic": 493.1e6, "issue": 0.63, "l1": 0.50, "dram": 0.32}}
 
 
 def cpu_baseline(args, sc, n, steps=None):
