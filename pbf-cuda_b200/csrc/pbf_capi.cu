@@ -164,6 +164,8 @@ struct pbf_sim {
     uint32_t* morton_dev = nullptr;
     int32_t morton_dims[3] = {0, 0, 0};
     int morton_bits = 0;
+    float* tail_npos_host = nullptr;   // pbf_step_host: where the final positions go (the last delta-p pass sends them in slices)
+    bool tail_npos_sent = false;
     StatePush state_push;            // armed by pbf_slab_push_state for this step's velocity / XSPH kernels
     float* state[4] = {nullptr, nullptr, nullptr, nullptr};        // my registered pos A, pos B, vel A, vel B
     uint32_t* state_iid = nullptr;
@@ -1084,6 +1086,21 @@ int pbf_stage_delta_p(pbf_sim* s) {
     }
     HaloSync hs;
     make_sync(s, true, true, &hs);
+    if (fused && s->tail_npos_host && s->own_count >= 4 * 131072 && delta_p_sliceable(s->pairs_list, s->mode, s->own_count)) {
+        // pbf_step_host: the pass that produces the final positions runs in four slices of the sorted order, and the
+        // positions of a finished slice go home on the copy stream while the next slice is computed
+        const int64_t nb = (s->own_count + 127) / 128;
+        for (int k = 0; k < 4; k++) {
+            const int64_t b0 = nb * k / 4, b1 = nb * (k + 1) / 4;
+            CUDA_TRY(launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, hs, vt, s->g, s->c, s->mode, s->stream, &s->launches,
+                                    (uint32_t)b0, (uint32_t)(b1 - b0), k == 3));
+            const int64_t a = b0 * 128, b = b1 * 128 < s->own_count ? b1 * 128 : s->own_count;
+            CUDA_TRY(cudaEventRecord(s->host_ev, s->stream));
+            CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
+            CUDA_TRY(cudaMemcpyAsync(s->tail_npos_host + 3 * a, s->npos + 3 * a, (size_t)(b - a) * 12, cudaMemcpyDeviceToHost, s->host_copy));
+        }
+        s->tail_npos_sent = true;
+    } else
     KTIMED(PBF_KERNEL_DELTA_P, launch_delta_p(s->xl, s->cull, s->n_local, s->x[s->cur ^ 1], s->cell_range, s->own_first, s->own_count, s->pairs_list, hp, hs, vt, s->g, s->c, s->mode, s->stream, &s->launches));
     if ((prc = signal_empty_edges(s, hs))) return prc;
     s->cur ^= 1;
@@ -1309,18 +1326,28 @@ int pbf_step_host(pbf_sim* s, float* pos, float* npos, float* vel, float* nvel, 
     if (n > 0) s->reorder_wait = s->host_iid_ev;
     if ((rc = pbf_stage_advect(s))) return rc;
     if ((rc = pbf_stage_build_grid(s))) return rc;
-    for (int i = 0; i < s->p.niter; i++) {
-        s->fuse_velocity = i == s->p.niter - 1;
-        rc = pbf_stage_correct_density(s);
-        s->fuse_velocity = false;
-        if (rc) return rc;
-    }
-    if (s->stage != ST_VELOCITY && (rc = pbf_stage_update_velocity(s))) return rc;
+    // the sorted iid is final as soon as the reorder pass has run: it goes home under the Jacobi iterations (the copy
+    // stream is idle until the positions are final, and everything that leaves after the last delta-p pass — 24 bytes
+    // per particle — is more than the XSPH sweep can hide on PCIe)
     if (n > 0) {
         CUDA_TRY(cudaEventRecord(s->host_ev, st));
         CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
-        CUDA_TRY(cudaMemcpyAsync(npos, s->h_npos, (size_t)n * 12, cudaMemcpyDeviceToHost, s->host_copy));
         CUDA_TRY(cudaMemcpyAsync(iid, s->iid_sorted, (size_t)n * 4, cudaMemcpyDeviceToHost, s->host_copy));
+    }
+    s->tail_npos_sent = false;
+    for (int i = 0; i < s->p.niter; i++) {
+        s->fuse_velocity = i == s->p.niter - 1;
+        s->tail_npos_host = s->fuse_velocity ? npos : nullptr;   // (pbf_stage_delta_p: the last pass in slices, positions home slice by slice)
+        rc = pbf_stage_correct_density(s);
+        s->fuse_velocity = false;
+        s->tail_npos_host = nullptr;
+        if (rc) return rc;
+    }
+    if (s->stage != ST_VELOCITY && (rc = pbf_stage_update_velocity(s))) return rc;
+    if (n > 0 && !s->tail_npos_sent) {
+        CUDA_TRY(cudaEventRecord(s->host_ev, st));
+        CUDA_TRY(cudaStreamWaitEvent(s->host_copy, s->host_ev, 0));
+        CUDA_TRY(cudaMemcpyAsync(npos, s->h_npos, (size_t)n * 12, cudaMemcpyDeviceToHost, s->host_copy));
     }
     // the XSPH sweep in up to four slices of the sorted order: the velocities of a finished slice go home
     // while the next slice is computed (a slice is at least 128 K particles, so small scenes take one launch)

@@ -272,7 +272,9 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
                            int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const HaloSync& hs, const VelTail& vt,
-                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches);
+                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches,
+                           uint32_t block0 = 0, uint32_t nblk = 0, bool last_slice = true);
+bool delta_p_sliceable(const PairList& pl, const SweepMode& mode, int64_t n);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
                                    const HaloSync& hs, const StatePush& sp, const SolverConsts& c, cudaStream_t st, int64_t* launches);

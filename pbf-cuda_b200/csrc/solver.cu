@@ -462,9 +462,11 @@ delta_p_replay_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out,
                       const uint32_t* __restrict__ pair_cnt, const uint2* __restrict__ cell_range,
                       const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
                       const __grid_constant__ VelTail vt, const __grid_constant__ GridConsts g,
-                      const __grid_constant__ SolverConsts c) {
+                      const __grid_constant__ SolverConsts c, const uint32_t block0) {
     pdl_wait();
-    const uint32_t lb = halo_block(hs);
+    // (block0: this launch is a SLICE of the pass, its blocks are block0 .. of the whole — pbf_step_host runs the
+    //  last pass in slices so that the final positions of a finished slice go home while the next one is computed)
+    const uint32_t lb = halo_block(hs) + block0;
     halo_enter(hs, lb);   // (edge blocks: the neighbours' lambdas of this iteration are in the ghost slots of xl)
     const int64_t col = (int64_t)lb * GATHER_THREADS + threadIdx.x;   // list column; its word names the particle
     const uint32_t cw = pair_cnt[col];   // (the lambda pass writes the word of EVERY column of its blocks)
@@ -1063,6 +1065,9 @@ cudaError_t launch_pack_ghosts(const float4* x, CullScratch& cs, int64_t n_slots
 static inline CullSoA soa_of(const CullScratch& cs) { return CullSoA{cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur]}; }
 static inline CullOut out_of(const CullScratch& cs) { return CullOut{cs.xs[cs.cur ^ 1], cs.ys[cs.cur ^ 1], cs.zs[cs.cur ^ 1]}; }
 
+// whether launch_delta_p would take the replay THREAD kernel (the one that can run in slices)
+bool delta_p_sliceable(const PairList& pl, const SweepMode& mode, int64_t n) { return pl.js != nullptr && !use_team(mode, n); }
+
 size_t pair_list_bytes(int64_t max_particles, size_t* js_bytes, size_t* cnt_bytes) {
     const size_t blocks = (size_t)((max_particles + GATHER_THREADS - 1) / GATHER_THREADS);
     *js_bytes = blocks * PAIR_CAP * GATHER_THREADS * sizeof(uint2);
@@ -1115,14 +1120,15 @@ cudaError_t launch_lambda(const float4* x, CullScratch& cs, int64_t n_slots, flo
 // (`cs` holds the positions the lambda pass of this iteration packed: the same ones xl carries)
 cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, float4* x_out, const uint2* cell_range,
                            int64_t first, int64_t n, const PairList& pl, const HaloPush& hp, const HaloSync& hs_in, const VelTail& vt,
-                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches) {
+                           const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches,
+                           uint32_t block0, uint32_t nblk, bool last_slice) {
     if (n <= 0) return cudaSuccess;
     const CullSoA soa = soa_of(cs);   // this iteration's coordinates: what the overflow kernel culls on
     const CullOut co = out_of(cs);    // the other set receives the coordinates of x_out
     // 3: the verified special-case-free powf(w, 4) (n_corr == 4, the default); 2: the library's powf with the
     // exponent folded (same bits; when 3 did not verify or is switched off); 1: powf, any exponent; 0: (w*w)^2
     const int pow_mode = c.n_corr == 4.0f ? (c.exact_pow ? (c.trim_pow ? 3 : 2) : 0) : 1;
-    const unsigned nb = nblocks(n, GATHER_THREADS);
+    const unsigned nb = nblk ? nblk : nblocks(n, GATHER_THREADS);   // (a slice: nblk blocks from block0; replay thread kernel only)
     HaloSync hs = hs_in;
     halo_sync_blocks(hs, n, GATHER_THREADS);
 #define PBF_DP_LAUNCH(POW)                                                                                                    \
@@ -1130,7 +1136,7 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
         if (pl.js) {                                                                                                          \
             if (use_team(mode, n)) launch_delta_p_replay_team(xl, x_out, co, first, n, pl.js, pl.cnt, cell_range, hp, hs_in, vt, g, c, POW, st); \
             else PBF_LAUNCH((delta_p_replay_kernel<POW>), nb, GATHER_THREADS, 0, st, xl, x_out, co, first, n, pl.js, pl.cnt,  \
-                            cell_range, hp, hs, vt, g, c);                                                                   \
+                            cell_range, hp, hs, vt, g, c, block0);                                                           \
         } else if (mode.morton) {                                                                                             \
             PBF_LAUNCH((delta_p_kernel<POW, false, true>), nb, GATHER_THREADS, LIST_SMEM, st, xl, soa, x_out, co, cell_range, first, n, hp, hs, vt, g, c); \
         } else if (mode.rebin && mode.moved) {                                                                                \
@@ -1145,6 +1151,7 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
     else PBF_DP_LAUNCH(0);
 #undef PBF_DP_LAUNCH
     if (launches) (*launches)++;
+    if (!last_slice) return cudaGetLastError();
     // the other set now mirrors x_out — if the pass covered every stored slot (single GPU); in slab mode the ghost
     // slots of x_out are the neighbours' to fill, and the next sweep packs
     if (first == 0 && n == n_slots) {
