@@ -47,7 +47,7 @@ EXPORTS = (
 
 HALO_LAMBDA, HALO_POSITION, HALO_VELOCITY = 0, 1, 2
 SLAB_STATE_PUSHED = -1   # pbf_slab_step.pull_left_first: the neighbours stored the raw state themselves (pbf_slab_push_state)
-OPT_TEAM, OPT_REBIN, OPT_PDL, OPT_GRAPH, OPT_HALO_INKERNEL, OPT_STAGED, OPT_PAIRED, OPT_MORTON = 0, 1, 2, 3, 4, 5, 6, 7
+OPT_TEAM, OPT_REBIN, OPT_PDL, OPT_GRAPH, OPT_HALO_INKERNEL, OPT_STAGED, OPT_PAIRED, OPT_MORTON, OPT_COOP = 0, 1, 2, 3, 4, 5, 6, 7, 8
 SLAB_FLAG_MIGRATION, SLAB_FLAG_GHOST, SLAB_FLAG_TIMEOUT = 1, 2, 4
 
 

@@ -615,6 +615,7 @@ int pbf_create(const pbf_params* params, const float ulim[3], const float llim[3
     if (const char* sg = getenv("PBF_STAGED")) s->mode.staged = sg[0] == '1' ? 1 : 0;
     if (const char* pr = getenv("PBF_PAIRED")) s->mode.paired = pr[0] == '1' ? 1 : 0;
     if (const char* mo = getenv("PBF_MORTON")) s->mode.morton = mo[0] == '1' ? 1 : 0;
+    if (const char* co = getenv("PBF_COOP")) s->mode.coop = co[0] == '1' ? 1 : 0;
     if (const char* pd = getenv("PBF_PDL")) s->mode.pdl = pd[0] == '0' ? 0 : 1;
     if (const char* hk = getenv("PBF_HALO_INKERNEL")) s->mode.halo_inkernel = hk[0] == '0' ? 0 : 1;
     if (const char* gr = getenv("PBF_GRAPH")) s->mode.graph = gr[0] == '1' ? 1 : gr[0] == '0' ? 0 : -1;
@@ -731,6 +732,9 @@ int pbf_set_option(pbf_sim* s, int option, int value) {
         case PBF_OPT_PAIRED:
             s->mode.paired = value ? 1 : 0;
             return PBF_OK;
+        case PBF_OPT_COOP:
+            s->mode.coop = value ? 1 : 0;
+            return PBF_OK;
         case PBF_OPT_MORTON: {
             const int old = s->mode.morton;
             s->mode.morton = value ? 1 : 0;
@@ -758,6 +762,7 @@ int pbf_get_option(const pbf_sim* s, int option, int* value) {
         case PBF_OPT_STAGED: *value = s->mode.staged; return PBF_OK;
         case PBF_OPT_PAIRED: *value = s->mode.paired; return PBF_OK;
         case PBF_OPT_MORTON: *value = s->mode.morton; return PBF_OK;
+        case PBF_OPT_COOP: *value = s->mode.coop; return PBF_OK;
         case PBF_OPT_GRAPH: *value = s->mode.graph; return PBF_OK;
         case PBF_OPT_HALO_INKERNEL: *value = s->mode.halo_inkernel; return PBF_OK;
         default: return fail(PBF_ERR_INVALID, "unknown option %d", option);
@@ -1182,6 +1187,22 @@ static int step_direct(pbf_sim* s, float* pos, float* npos, float* vel, float* n
     if (rc) return rc;
     if ((rc = pbf_stage_advect(s))) return rc;
     if ((rc = pbf_stage_build_grid(s))) return rc;
+    if (s->mode.coop && !s->timing && s->p.niter >= 1 && n > 0 && sweeps_use_team(s->mode, n)) {
+        // PBF_OPT_COOP: every solver pass of the step in one persistent cooperative kernel (north-star item 3)
+        float4* const xx[2] = {s->x[0], s->x[1]};
+        const cudaError_t ce = launch_solve_team_coop(xx, s->cull, s->xl, s->rho, s->cell_range, s->pairs_list, s->pos, s->npos, s->vel, s->nvel,
+                                                      s->iid_sorted, s->iid, n, s->p.niter, s->g, s->c, s->stream, &s->launches);
+        if (ce == cudaSuccess) {
+            s->cur = s->p.niter & 1;
+            s->iters_done = s->p.niter;
+            s->v4 = s->x[s->cur ^ 1];
+            s->pos0_in_npos = false;
+            s->stage = ST_XSPH;
+            return pbf_stage_end(s);
+        }
+        cudaGetLastError();
+        if (ce != cudaErrorNotSupported) return fail(PBF_ERR_CUDA, "cooperative solver kernel: %s", cudaGetErrorString(ce));
+    }
     for (int i = 0; i < s->p.niter; i++) {
         s->fuse_velocity = i == s->p.niter - 1;   // (pbf_stage_delta_p decides; off again right away: the stage
         rc = pbf_stage_correct_density(s);        //  entry points called one by one keep the stages apart)
@@ -1210,7 +1231,7 @@ static int step_graph(pbf_sim* s, float* pos, float* npos, float* vel, float* nv
     StepGraph* lru = nullptr;   // where a new graph goes: a free slot, else the least recently used one
     for (auto& gq : s->graphs) {
         if (gq.exec && gq.n == n && gq.stream == (cudaStream_t)stream && gq.consts_hash == hc &&
-            gq.niter == s->p.niter && gq.team == s->mode.team && gq.rebin == s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired + 8 * s->mode.morton && gq.pdl == s->mode.pdl &&
+            gq.niter == s->p.niter && gq.team == s->mode.team && gq.rebin == s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired + 8 * s->mode.morton + 16 * s->mode.coop && gq.pdl == s->mode.pdl &&
             memcmp(gq.ptr, ptr, sizeof(ptr)) == 0) {
             hit = &gq;
             break;
@@ -1255,7 +1276,7 @@ static int step_graph(pbf_sim* s, float* pos, float* npos, float* vel, float* nv
         }
         memcpy(lru->ptr, ptr, sizeof(ptr));
         lru->n = n; lru->stream = (cudaStream_t)stream; lru->consts_hash = hc;
-        lru->niter = s->p.niter; lru->team = s->mode.team; lru->rebin = s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired + 8 * s->mode.morton; lru->pdl = s->mode.pdl;
+        lru->niter = s->p.niter; lru->team = s->mode.team; lru->rebin = s->mode.rebin + 2 * s->mode.staged + 4 * s->mode.paired + 8 * s->mode.morton + 16 * s->mode.coop; lru->pdl = s->mode.pdl;
         lru->launches = s->launches - l0;
         lru->sorted_buf = s->sorted_buf; lru->cur = s->cur; lru->iters_done = s->iters_done;
         lru->cull_cur = s->cull.cur; lru->cull_holds = s->cull.holds; lru->v4 = s->v4;

@@ -249,6 +249,7 @@ struct SweepMode {
                      // (the A/B of DESIGN.md 3.3: measured, not faster — off)
     int paired = 0;  // thread kernels: two consecutive slots per thread, one walk over the union of their candidate runs
                      // (solver.cu gather2): half the cull's loads per test
+    int coop = 0;    // small scenes: the solver passes of pbf_step as one persistent cooperative kernel (solver_team.cu)
     int morton = 0;  // Morton-ordered keys (GridConsts::morton): thread kernels only, 27 one-cell runs instead of 9 runs
     int pdl = 1;     // programmatic dependent launch between the step's kernels (launch.cuh)
     int halo_inkernel = 1;   // fused halo: handshakes inside the pass kernels (HaloSync) instead of two one-thread kernels per refresh
@@ -275,6 +276,13 @@ cudaError_t launch_delta_p(const float4* xl, CullScratch& cs, int64_t n_slots, f
                            const GridConsts& g, const SolverConsts& c, const SweepMode& mode, cudaStream_t st, int64_t* launches,
                            uint32_t block0 = 0, uint32_t nblk = 0, bool last_slice = true);
 bool delta_p_sliceable(const PairList& pl, const SweepMode& mode, int64_t n);
+bool sweeps_use_team(const SweepMode& mode, int64_t n);   // whether the sweeps of n particles take the four-lane kernels
+// solver_team.cu: niter x (lambda, delta-p with the velocity update on the last) + XSPH of a single-GPU small-scene step
+// as ONE persistent cooperative kernel (PBF_OPT_COOP). cudaErrorNotSupported: not this configuration, launch as usual.
+cudaError_t launch_solve_team_coop(float4* const x[2], CullScratch& cs, float4* xl, float* rho, const uint2* cell_range,
+                                   const PairList& pl, float* pos_out, float* npos_io, float* vel_out, float* nvel_out,
+                                   const uint32_t* iid_sorted, uint32_t* iid_out, int64_t n, int niter,
+                                   const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches);
 cudaError_t launch_update_velocity(const float4* x, const float* rho, float* pos_out, float* npos_io,
                                    float* vel_out, float4* v4, int64_t first, int64_t n, const HaloPush& hp,
                                    const HaloSync& hs, const StatePush& sp, const SolverConsts& c, cudaStream_t st, int64_t* launches);

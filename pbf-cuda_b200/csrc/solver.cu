@@ -1065,6 +1065,7 @@ cudaError_t launch_pack_ghosts(const float4* x, CullScratch& cs, int64_t n_slots
 static inline CullSoA soa_of(const CullScratch& cs) { return CullSoA{cs.xs[cs.cur], cs.ys[cs.cur], cs.zs[cs.cur]}; }
 static inline CullOut out_of(const CullScratch& cs) { return CullOut{cs.xs[cs.cur ^ 1], cs.ys[cs.cur ^ 1], cs.zs[cs.cur ^ 1]}; }
 
+bool sweeps_use_team(const SweepMode& mode, int64_t n) { return use_team(mode, n); }
 // whether launch_delta_p would take the replay THREAD kernel (the one that can run in slices)
 bool delta_p_sliceable(const PairList& pl, const SweepMode& mode, int64_t n) { return pl.js != nullptr && !use_team(mode, n); }
 

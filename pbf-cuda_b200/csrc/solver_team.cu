@@ -15,8 +15,12 @@
 // never becomes -0.
 // More instruction slots per pair than solver.cu (shuffles, the list expansion), so the launchers take these
 // kernels only below TEAM_MAX_PARTICLES, where latency, not throughput, is the bound.
+#include <cooperative_groups.h>
+
 #include "launch.cuh"
 #include "solver_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pbf {
 
@@ -132,17 +136,15 @@ __device__ __forceinline__ void team_gather(const Team& tm, const float4 p, cons
 
 // ---- lambda pass -----------------------------------------------------------------------------------------
 
+// (the bodies of the three team kernels are device functions of a logical block `lb`, so that the persistent cooperative
+//  kernel at the end of this file can run the same code for all passes of a step)
 template <bool SAVE_PAIRS, bool FAST_SPIKY>
-__global__ void __launch_bounds__(TEAM_THREADS, 8)
-lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
+__device__ __forceinline__ void lambda_team_body(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
                    const uint2* __restrict__ cell_range, int64_t first, int64_t n,
                    uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
-                   const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
-                   const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
-    pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
-    extern __shared__ uint32_t s_list[];
+                   const HaloPush& hp, const HaloSync& hs, const GridConsts& g, const SolverConsts& c,
+                   uint32_t* __restrict__ s_list, const uint32_t lb) {
     const Team tm = team_of();
-    const uint32_t lb = halo_block(hs);   // (slab mode: the edge blocks first, see HaloSync)
     const int64_t t = (int64_t)lb * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;   // whole teams leave together
     const int64_t i = first + t;
@@ -196,19 +198,27 @@ lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __re
     }
     halo_exit(hs, lb);
 }
+template <bool SAVE_PAIRS, bool FAST_SPIKY>
+__global__ void __launch_bounds__(TEAM_THREADS, 8)
+lambda_team_kernel(const float4* __restrict__ x, const CullSoA soa, float4* __restrict__ xl, float* __restrict__ rho_out,
+                   const uint2* __restrict__ cell_range, int64_t first, int64_t n,
+                   uint2* __restrict__ pair_js, uint32_t* __restrict__ pair_cnt,
+                   const __grid_constant__ HaloPush hp, const __grid_constant__ HaloSync hs,
+                   const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
+    extern __shared__ uint32_t s_list[];
+    // (slab mode: the edge blocks first, see HaloSync)
+    lambda_team_body<SAVE_PAIRS, FAST_SPIKY>(x, soa, xl, rho_out, cell_range, first, n, pair_js, pair_cnt, hp, hs, g, c, s_list, halo_block(hs));
+}
 
 // ---- delta-p replay ----------------------------------------------------------------------------------------
 
 template <int POW>
-__global__ void __launch_bounds__(TEAM_THREADS, 16)
-delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
+__device__ __forceinline__ void delta_p_replay_team_body(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
                            const uint2* __restrict__ pair_js, const uint32_t* __restrict__ pair_cnt,
-                           const uint2* __restrict__ cell_range, const __grid_constant__ HaloPush hp,
-                           const __grid_constant__ HaloSync hs, const __grid_constant__ VelTail vt,
-                           const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
-    pdl_wait();
+                           const uint2* __restrict__ cell_range, const HaloPush& hp, const HaloSync& hs, const VelTail& vt,
+                           const GridConsts& g, const SolverConsts& c, const uint32_t lb) {
     const Team tm = team_of();
-    const uint32_t lb = halo_block(hs);
     halo_enter(hs, lb);   // (edge blocks: the neighbours' lambdas of this iteration are in the ghost slots of xl)
     const int64_t t = (int64_t)lb * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;
@@ -253,19 +263,25 @@ delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x
     if (vt.v4) velocity_tail(vt, t, i, out);
     halo_exit(hs, lb);
 }
+template <int POW>
+__global__ void __launch_bounds__(TEAM_THREADS, 16)
+delta_p_replay_team_kernel(const float4* __restrict__ xl, float4* __restrict__ x_out, const CullOut co, int64_t first, int64_t n,
+                           const uint2* __restrict__ pair_js, const uint32_t* __restrict__ pair_cnt,
+                           const uint2* __restrict__ cell_range, const __grid_constant__ HaloPush hp,
+                           const __grid_constant__ HaloSync hs, const __grid_constant__ VelTail vt,
+                           const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();
+    delta_p_replay_team_body<POW>(xl, x_out, co, first, n, pair_js, pair_cnt, cell_range, hp, hs, vt, g, c, halo_block(hs));
+}
 
 // ---- XSPH ----------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(TEAM_THREADS, 8)
-xsph_team_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
+__device__ __forceinline__ void xsph_team_body(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
                  const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
                  const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
-                 const __grid_constant__ HaloSync hs, const __grid_constant__ StatePush sp, const __grid_constant__ GridConsts g,
-                 const __grid_constant__ SolverConsts c) {
-    pdl_wait();
-    extern __shared__ uint32_t s_list[];
+                 const HaloSync& hs, const StatePush& sp, const GridConsts& g, const SolverConsts& c,
+                 uint32_t* __restrict__ s_list, const uint32_t lb) {
     const Team tm = team_of();
-    const uint32_t lb = halo_block(hs);
     halo_enter(hs, lb);   // (edge blocks: the neighbours' velocities are in the ghost slots of v4)
     const int64_t t = (int64_t)lb * TEAM_PARTICLES + (threadIdx.x >> 2);
     if (t >= n) return;
@@ -300,6 +316,65 @@ xsph_team_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* 
     iid_out[t] = id;
     push_state_vel(sp, t, ox, oy, oz, id);
 }
+__global__ void __launch_bounds__(TEAM_THREADS, 8)
+xsph_team_kernel(const float4* __restrict__ x, const CullSoA soa, const float4* __restrict__ v4,
+                 const uint2* __restrict__ cell_range, float* __restrict__ nvel_out,
+                 const uint32_t* __restrict__ iid_sorted, uint32_t* __restrict__ iid_out, int64_t first, int64_t n,
+                 const __grid_constant__ HaloSync hs, const __grid_constant__ StatePush sp, const __grid_constant__ GridConsts g,
+                 const __grid_constant__ SolverConsts c) {
+    pdl_wait();
+    extern __shared__ uint32_t s_list[];
+    xsph_team_body(x, soa, v4, cell_range, nvel_out, iid_sorted, iid_out, first, n, hs, sp, g, c, s_list, halo_block(hs));
+}
+
+// ---- the persistent cooperative kernel (north-star item 3, the A/B of DESIGN.md 3.8) -------------------------------
+// All solver passes of a single-GPU small-scene step in ONE launch: niter x (lambda, delta-p) — the last delta-p pass
+// carrying the velocity update — and the XSPH sweep, as loops over logical blocks with a grid-wide barrier between the
+// passes (cooperative groups: every block of the grid is resident). The bodies are the team kernels' own, so the bits
+// are the same; what changes is that kernel boundaries become grid barriers.
+struct CoopArgs {
+    float4* x[2];           // position iterate, ping-pong (x[0] = what the reorder pass built)
+    float* cx[2][3];        // the cull's coordinate arrays, two sets (set 0 mirrors x[0])
+    float4* xl;
+    float* rho;
+    const uint2* cell_range;
+    uint2* pair_js;
+    uint32_t* pair_cnt;
+    float* pos_out;  float* npos_io;  float* vel_out;  float* nvel_out;   // the caller's arrays (VelTail, XSPH)
+    const uint32_t* iid_sorted;  uint32_t* iid_out;
+    int64_t n;
+    int32_t niter;
+};
+template <bool FAST_SPIKY, int POW>
+__global__ void __launch_bounds__(TEAM_THREADS, 7)   // (73 registers: 8 blocks per SM spill; 7 x 148 still hold the 1000 blocks of 32 000 particles)
+solve_team_coop_kernel(const __grid_constant__ CoopArgs a, const __grid_constant__ GridConsts g, const __grid_constant__ SolverConsts c) {
+    pdl_wait();
+    extern __shared__ uint32_t s_list[];
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t nvb = (uint32_t)((a.n + TEAM_PARTICLES - 1) / TEAM_PARTICLES);
+    const HaloPush hp;
+    const HaloSync hs;
+    const StatePush sp;
+    int cur = 0;
+    for (int it = 0; it < a.niter; it++) {
+        const CullSoA soa{a.cx[cur][0], a.cx[cur][1], a.cx[cur][2]};
+        for (uint32_t vb = blockIdx.x; vb < nvb; vb += gridDim.x)
+            lambda_team_body<true, FAST_SPIKY>(a.x[cur], soa, a.xl, a.rho, a.cell_range, 0, a.n, a.pair_js, a.pair_cnt, hp, hs, g, c, s_list, vb);
+        grid.sync();
+        VelTail vt;
+        if (it == a.niter - 1) {   // (pbf_stage_delta_p, fused: the velocities go to the iterate buffer this pass does not read)
+            vt.rho = a.rho; vt.pos_out = a.pos_out; vt.npos_io = a.npos_io; vt.vel_out = a.vel_out; vt.v4 = a.x[cur]; vt.inv_dt = c.inv_dt;
+        }
+        const CullOut co{a.cx[cur ^ 1][0], a.cx[cur ^ 1][1], a.cx[cur ^ 1][2]};
+        for (uint32_t vb = blockIdx.x; vb < nvb; vb += gridDim.x)
+            delta_p_replay_team_body<POW>(a.xl, a.x[cur ^ 1], co, 0, a.n, a.pair_js, a.pair_cnt, a.cell_range, hp, hs, vt, g, c, vb);
+        grid.sync();
+        cur ^= 1;
+    }
+    const CullSoA soa{a.cx[cur][0], a.cx[cur][1], a.cx[cur][2]};
+    for (uint32_t vb = blockIdx.x; vb < nvb; vb += gridDim.x)
+        xsph_team_body(a.x[cur], soa, a.x[cur ^ 1], a.cell_range, a.nvel_out, a.iid_sorted, a.iid_out, 0, a.n, hs, sp, g, c, s_list, vb);
+}
 
 // ---- launchers -----------------------------------------------------------------------------------------------
 
@@ -317,7 +392,48 @@ cudaError_t preload_solver_team() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_team_kernel<2>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, delta_p_replay_team_kernel<3>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, xsph_team_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, solve_team_coop_kernel<true, 3>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, solve_team_coop_kernel<false, 3>);
     return e;
+}
+
+// One cooperative launch for niter x (lambda, delta-p) + XSPH (see solve_team_coop_kernel). Returns cudaErrorNotSupported
+// when the configuration is not the one the kernel is built for (n_corr == 4 with the verified trimmed powf, the
+// neighbour list present, niter >= 1): the caller then takes the ordinary launches.
+cudaError_t launch_solve_team_coop(float4* const x[2], CullScratch& cs, float4* xl, float* rho, const uint2* cell_range,
+                                   const PairList& pl, float* pos_out, float* npos_io, float* vel_out, float* nvel_out,
+                                   const uint32_t* iid_sorted, uint32_t* iid_out, int64_t n, int niter,
+                                   const GridConsts& g, const SolverConsts& c, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || niter < 1 || !pl.js || !(c.n_corr == 4.0f && c.exact_pow && c.trim_pow) || cs.holds != x[0] || cs.cur != 0)
+        return cudaErrorNotSupported;
+    CoopArgs a;
+    a.x[0] = x[0]; a.x[1] = x[1];
+    for (int k = 0; k < 2; k++) { a.cx[k][0] = cs.xs[k]; a.cx[k][1] = cs.ys[k]; a.cx[k][2] = cs.zs[k]; }
+    a.xl = xl; a.rho = rho; a.cell_range = cell_range; a.pair_js = pl.js; a.pair_cnt = pl.cnt;
+    a.pos_out = pos_out; a.npos_io = npos_io; a.vel_out = vel_out; a.nvel_out = nvel_out;
+    a.iid_sorted = iid_sorted; a.iid_out = iid_out; a.n = n; a.niter = niter;
+    static int resident[2] = {0, 0};   // blocks of the kernel the device holds at once (per FAST_SPIKY variant)
+    const int v = c.fast_spiky ? 1 : 0;
+    if (resident[v] == 0) {
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = c.fast_spiky ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_team_coop_kernel<true, 3>, TEAM_THREADS, TEAM_SMEM)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_team_coop_kernel<false, 3>, TEAM_THREADS, TEAM_SMEM);
+        if (e != cudaSuccess || per_sm < 1 || sms < 1) { cudaGetLastError(); return cudaErrorNotSupported; }
+        resident[v] = per_sm * sms;
+    }
+    const unsigned nvb = team_blocks(n);
+    const unsigned grid = nvb < (unsigned)resident[v] ? nvb : (unsigned)resident[v];
+    void* args[3] = {(void*)&a, (void*)&g, (void*)&c};
+    cudaError_t e = c.fast_spiky ? cudaLaunchCooperativeKernel((const void*)solve_team_coop_kernel<true, 3>, dim3(grid), dim3(TEAM_THREADS), args, TEAM_SMEM, st)
+                                 : cudaLaunchCooperativeKernel((const void*)solve_team_coop_kernel<false, 3>, dim3(grid), dim3(TEAM_THREADS), args, TEAM_SMEM, st);
+    if (e != cudaSuccess) return e;
+    if (launches) (*launches)++;
+    // the state the ordinary launches leave behind: the coordinates of the final iterate x[niter & 1] are in set niter & 1
+    cs.cur = niter & 1;
+    cs.holds = x[niter & 1];
+    return cudaSuccess;
 }
 
 void launch_lambda_team(const float4* x, const CullSoA soa, float4* xl, float* rho, const uint2* cell_range, int64_t first,

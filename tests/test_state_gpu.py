@@ -334,6 +334,42 @@ def test_morton_keys_first_step_exact_then_within_tolerance(pbf, torch):
     assert np.abs(mor5[1] - lin5[1]).max() <= 5e-5 * scale
 
 
+def test_cooperative_solver_kernel_gives_the_same_bits(pbf, torch):
+    """PBF_OPT_COOP: every solver pass of a small-scene pbf_step in one persistent cooperative kernel (grid-wide barriers
+    instead of kernel boundaries; the team kernels' own device code) — the same bits as the separate launches, launched
+    directly and replayed from a CUDA graph, with an odd iteration count too, and one launch instead of 2 niter + 1."""
+    pos, vel, iid, ulim, llim = pbf.scene_double_dam_reference()
+    n = len(iid)
+    dev = torch.device("cuda:0")
+
+    def run(coop, graph, niter):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            d = [torch.from_numpy(pos).to(dev), torch.zeros((n, 3), device=dev), torch.from_numpy(vel).to(dev), torch.zeros((n, 3), device=dev)]
+            d_iid = torch.from_numpy(iid.astype(np.int64)).to(dev).to(torch.int32)
+            p = pbf.default_params()
+            p.niter = niter
+            sim = pbf.Simulator(p, ulim, llim, n)
+            sim.set_option(pbf.OPT_COOP, coop)
+            sim.set_option(pbf.OPT_GRAPH, graph)
+            assert sim.get_option(pbf.OPT_COOP) == coop
+            l0 = sim.launch_count()
+            for _ in range(8):
+                sim.step(d[0], d[1], d[2], d[3], d_iid, n, st.cuda_stream)
+                d[0], d[1], d[2], d[3] = d[1], d[0], d[3], d[2]
+            st.synchronize()
+            out = (pbf.state_digest(d[0], d[2], d_iid, n), sim.launch_count() - l0)
+            sim.close()
+        return out
+
+    for niter in (4, 3):
+        plain = run(0, 0, niter)
+        for graph in (0, 1):
+            got = run(1, graph, niter)
+            assert got[0] == plain[0]
+        assert run(1, 0, niter)[1] == plain[1] - 8 * (2 * niter + 1 - 1), "one launch instead of 2 niter + 1 per step"
+
+
 @pytest.mark.parametrize("moving", [0, 1])
 def test_graph_and_pdl_steps_give_the_same_bits(pbf, torch, moving):
     """PBF_OPT_GRAPH / PBF_OPT_PDL (include/pbf.h): a step replayed from a CUDA graph, with or without programmatic

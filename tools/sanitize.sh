@@ -5,7 +5,7 @@ tool=${1:-memcheck}
 mkdir -p gpurun_out
 compute-sanitizer --tool "$tool" --error-exitcode 99 --print-limit 20 \
     python -m pytest tests/test_parity_gpu.py tests/test_state_gpu.py -m gpu -x -q \
-    -k "golden and (cube2k or wall2k or ragged) or cluster or one_cell or empty_and_tiny or rebinned or paired or morton or graph_and_pdl" \
+    -k "golden and (cube2k or wall2k or ragged) or cluster or one_cell or empty_and_tiny or rebinned or paired or morton or cooperative or graph_and_pdl" \
     > "gpurun_out/sanitize_$tool.log" 2>&1
 rc=$?
 grep -E "ERROR SUMMARY|passed|failed|Error" "gpurun_out/sanitize_$tool.log" | tail -5
