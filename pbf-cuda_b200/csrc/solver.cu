@@ -26,6 +26,20 @@
 namespace pbf {
 
 constexpr int CULL_UNROLL = PBF_CULL_UNROLL;
+// PBF_CULL_WIDE: the cull takes EIGHT slots per trip with three 256-bit loads (LDG.E.256, sm_100) instead of four with
+// three 128-bit ones: half the load instructions — and, where the lanes of a warp read the same few lines, half the L1
+// tag requests — per candidate. Words then start at multiples of eight slots.
+#ifndef PBF_CULL_WIDE
+#define PBF_CULL_WIDE 0
+#endif
+constexpr bool CULL_WIDE = PBF_CULL_WIDE != 0;
+struct float8 { float4 lo, hi; };
+__device__ __forceinline__ float8 ldg256(const float* p) {
+    float8 v;
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.lo.z), "=f"(v.lo.w), "=f"(v.hi.x), "=f"(v.hi.y), "=f"(v.hi.z), "=f"(v.hi.w) : "l"(p));
+    return v;
+}
 
 // Two-phase gather of one particle (one thread), the core of all three neighbour sweeps.
 //
@@ -133,11 +147,20 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             end = e2 ? r2.y : e1 ? r1.y : r0.y;
             }
 #pragma unroll 1
-            for (uint32_t b = start & ~3u; b < end; b += 32) {   // words start at multiples of four slots
+            for (uint32_t b = start & ((CULL_WIDE && !STAGED) ? ~7u : ~3u); b < end; b += 32) {   // words start at multiples of four (eight) slots
                 const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
-                const uint32_t groups = (cnt + 3) >> 2;
+                const uint32_t groups = (CULL_WIDE && !STAGED) ? ((cnt + 7) >> 3) << 1 : (cnt + 3) >> 2;   // (in units of four slots)
                 uint32_t hits = 0;
-                if (STAGED) {
+                if (CULL_WIDE && !STAGED) {
+#pragma unroll 1
+                    for (uint32_t gi = 0; gi < groups; gi += 2) {   // eight candidates: 3 loads, 28 packed flops, 8 shifts
+                        const float8 X = ldg256(soa.xs + b + 4 * gi), Y = ldg256(soa.ys + b + 4 * gi), Z = ldg256(soa.zs + b + 4 * gi);
+                        hits = push_hits2(hits, px, py, pz, lim, X.lo.x, X.lo.y, Y.lo.x, Y.lo.y, Z.lo.x, Z.lo.y);
+                        hits = push_hits2(hits, px, py, pz, lim, X.lo.z, X.lo.w, Y.lo.z, Y.lo.w, Z.lo.z, Z.lo.w);
+                        hits = push_hits2(hits, px, py, pz, lim, X.hi.x, X.hi.y, Y.hi.x, Y.hi.y, Z.hi.x, Z.hi.y);
+                        hits = push_hits2(hits, px, py, pz, lim, X.hi.z, X.hi.w, Y.hi.z, Y.hi.w, Z.hi.z, Z.hi.w);
+                    }
+                } else if (STAGED) {
                     const int run = (dx + 1) * 3 + (dy + 1);
                     uint32_t a = st_base + ((uint32_t)run * 3u * STAGE_CAP + (b - st_ubase[run])) * 4u;
 #pragma unroll 1
