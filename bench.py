@@ -167,6 +167,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_cpus(index):
+    """One process per GPU: run this rank on the CPU cores next to its GPU (NVML's affinity mask), BEFORE anything is
+    allocated — pinned host buffers are then first touched on the GPU's NUMA node, and the e2e leg's uploads / downloads
+    do not cross the socket interconnect. Best effort: a box without NVML or with a restricted cpuset is left alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:   # noqa: BLE001
+        return None
+
+
 def workload_name(S, name, sc, n):
     d = S.scene_dims(sc)
     return "%s: %d particles, niter 4, box %dx%dx%d cells, reference default parameters" % (name, n, d[0], d[1], d[2])
@@ -925,6 +938,7 @@ def main():
         out = run_reference(args, rank, world)
     else:
         if world > 1:
+            bind_to_gpu_cpus(int(os.environ.get("LOCAL_RANK", 0)))
             import torch
             import torch.distributed as dist
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
