@@ -421,6 +421,7 @@ def run_product(args, rank, world, dist):
                       "parallelism": "single GPU" if world == 1 else "replicas x%d (one independent scene per GPU)" % world,
                       "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
                       "ms_per_step_back_to_back": round(b2b_ms, 5), "exact_pow": True,
+                      "neighbour_list": dict(zip(("in_use", "bytes"), sim.pair_list())),
                       "ms_per_step_series": [round(x, 2) for x in series],
                       "stage_ms": {k: round(v, 4) for k, v in sacc.items()},
                       "kernel_ms": {k: round(v, 4) for k, v in kacc.items()},

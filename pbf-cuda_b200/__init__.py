@@ -41,7 +41,7 @@ EXPORTS = (
     "pbf_scene_block_slice_host", "pbf_slab_peer_export", "pbf_slab_peer_attach",
     "pbf_slab_halo_sync", "pbf_slab_push_state", "pbf_slab_register_state", "pbf_slab_adopt_state", "pbf_stream_create", "pbf_stream_destroy",
     "pbf_stream_sync", "pbf_copy_d2h_async", "pbf_device_count", "pbf_get_const_div_interval",
-    "pbf_get_fast_spiky", "pbf_get_trim_pow", "pbf_set_option", "pbf_get_option", "pbf_state_digest_device",
+    "pbf_get_fast_spiky", "pbf_get_pair_list", "pbf_get_trim_pow", "pbf_set_option", "pbf_get_option", "pbf_state_digest_device",
     "pbf_state_digest_host", "pbf_state_write", "pbf_state_read_info", "pbf_state_read", "pbf_checkpoint_save", "pbf_checkpoint_load",
 )
 
@@ -120,6 +120,7 @@ _lib.pbf_get_lim.argtypes = [_vp, _f3, _f3]
 _lib.pbf_set_option_exact_pow.argtypes = [_vp, C.c_int]
 _lib.pbf_get_grid_dim.argtypes = [_vp, C.POINTER(C.c_int32)]
 _lib.pbf_get_fast_spiky.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+_lib.pbf_get_pair_list.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
 _lib.pbf_get_trim_pow.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
 _lib.pbf_set_option.argtypes = [_vp, C.c_int, C.c_int]
 _lib.pbf_get_option.argtypes = [_vp, C.c_int, C.POINTER(C.c_int)]
@@ -377,6 +378,13 @@ class Simulator:
         lo, hi = C.c_float(), C.c_float()
         _check(_lib.pbf_get_const_div_interval(self._h, C.byref(lo), C.byref(hi)))
         return float(lo.value), float(hi.value)
+
+    def pair_list(self):
+        """(in use, bytes) of the lambda -> delta-p neighbour list (pbf_get_pair_list): False = the handle was too large
+        for it (or PBF_NO_PAIR_REUSE=1) and the delta-p pass repeats the full gather."""
+        on, nbytes = C.c_int32(0), C.c_uint64(0)
+        _check(_lib.pbf_get_pair_list(self._h, C.byref(on), C.byref(nbytes)))
+        return bool(on.value), int(nbytes.value)
 
     def fast_spiky(self):
         """(in use, mismatches) of the exhaustively verified branch-free spiky scale (pbf_get_fast_spiky)."""

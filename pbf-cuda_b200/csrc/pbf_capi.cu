@@ -800,6 +800,14 @@ int pbf_get_trim_pow(const pbf_sim* s, int32_t* on, uint64_t* mismatches) {
     *mismatches = (uint64_t)s->pow4_mismatches;
     return PBF_OK;
 }
+int pbf_get_pair_list(const pbf_sim* s, int32_t* on, uint64_t* bytes) {
+    if (!s || !on || !bytes) return fail(PBF_ERR_INVALID, "null argument");
+    size_t jb = 0, cb = 0;
+    const size_t need = pair_list_bytes(s->max_particles, &jb, &cb);
+    *on = s->pairs_list.js ? 1 : 0;
+    *bytes = (uint64_t)need;
+    return PBF_OK;
+}
 int pbf_get_fast_spiky(const pbf_sim* s, int32_t* on, uint64_t* mismatches) {
     if (!s || !on || !mismatches) return fail(PBF_ERR_INVALID, "null argument");
     *on = s->spiky_ok;
