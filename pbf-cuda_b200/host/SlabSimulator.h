@@ -185,6 +185,11 @@ private:
         void* alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
         int64_t capacity = 0, n_own = 0;
         pbf_slab_peer_info info;
+        // the NEXT step's plan, made during this step (its boundaries and this rank's exchange), when this step's kernels
+        // were told to deliver the boundary planes' raw state themselves (pbf_slab_push_state)
+        bool planned = false;
+        std::vector<int> next_bounds;
+        ExchangePlan next_xp;
     };
 
     template <class F> bool run_all(F f) {
@@ -309,19 +314,27 @@ private:
             const std::vector<int64_t>& cur = m_counts[t & 1];
             std::vector<int64_t>& nxt = m_counts[(t + 1) & 1];
             nw = old;
-            if (m_replan && t && t % m_replan == 0 && m_world > 1) {
-                std::vector<int64_t> totals(m_planes, 0);
-                for (int x = 0; x < m_planes; x++) for (int q = 0; q < m_world; q++) totals[x] += cur[(size_t)q * m_planes + x];
-                plan_boundaries(totals, m_world, 2 * m_reach, &old, m_reach, &nw);
+            ExchangePlan xp;
+            const bool pushed = k.planned;   // the neighbours' velocity / XSPH kernels delivered the raw state last step
+            if (pushed) {
+                nw = k.next_bounds;
+                xp = k.next_xp;
+                k.planned = false;
+            } else {
+                if (m_replan && t && t % m_replan == 0 && m_world > 1) {
+                    std::vector<int64_t> totals(m_planes, 0);
+                    for (int x = 0; x < m_planes; x++) for (int q = 0; q < m_world; q++) totals[x] += cur[(size_t)q * m_planes + x];
+                    plan_boundaries(totals, m_world, 2 * m_reach, &old, m_reach, &nw);
+                }
+                xp = exchange_plan(cur, m_planes, old, nw, r, m_reach);
             }
-            const ExchangePlan xp = exchange_plan(cur, m_planes, old, nw, r, m_reach);
             if (k.n_own + xp.m_left + xp.m_right > k.capacity) return fail(r, "the rank would hold more particles than its capacity");
             pbf_slab_step st;
             memset(&st, 0, sizeof(st));
             st.x_begin = nw[r]; st.x_end = nw[r + 1]; st.ghost = m_ghost; st.has_left = L; st.has_right = R;
             st.n_own = k.n_own; st.m_left = xp.m_left; st.m_right = xp.m_right;
-            st.send_left_end = xp.send_left_end; st.send_right_begin = xp.send_right_begin; st.pull_left_first = xp.pull_left_first;
-            SLAB_TRY(pbf_slab_begin(k.sim, &st, k.pos, k.npos, k.vel, k.nvel, k.iid, k.stream));   // pulls the raw boundary state
+            st.send_left_end = xp.send_left_end; st.send_right_begin = xp.send_right_begin; st.pull_left_first = pushed ? (int64_t)PBF_SLAB_STATE_PUSHED : xp.pull_left_first;
+            SLAB_TRY(pbf_slab_begin(k.sim, &st, k.pos, k.npos, k.vel, k.nvel, k.iid, k.stream));   // pulls the raw boundary state (or waits for the pushed one)
             SLAB_TRY(pbf_stage_advect(k.sim));
             SLAB_TRY(pbf_stage_build_grid(k.sim));                                               // sort, layout (one host sync)
             pbf_slab_layout lay;
@@ -340,6 +353,27 @@ private:
             if (m_params.niter == 0) {
                 SLAB_TRY(pbf_slab_plane_counts(k.sim, 0, m_planes, &nxt[(size_t)r * m_planes]));
                 if (!m_barrier.wait()) return false;
+            }
+            if (m_world > 1 && m_push) {
+                // the next step's plan is a function of `nxt` alone (replicated since the barrier above): make it now and
+                // let this step's velocity / XSPH kernels store the boundary planes' final state straight into the
+                // neighbours' next input arrays — behind the neighbour's own particles, and on its right-hand side behind
+                // what ITS left neighbour delivers (slab.py SlabSimulator._plan_next is the same code)
+                std::vector<int> nb = nw;
+                if (m_replan && (t + 1) % m_replan == 0) {
+                    std::vector<int64_t> totals(m_planes, 0);
+                    for (int x = 0; x < m_planes; x++) for (int q = 0; q < m_world; q++) totals[x] += nxt[(size_t)q * m_planes + x];
+                    plan_boundaries(totals, m_world, 2 * m_reach, &nw, m_reach, &nb);
+                }
+                auto owned = [&](int q) { int64_t c = 0; for (int x = 0; x < m_planes; x++) c += nxt[(size_t)q * m_planes + x]; return c; };
+                const ExchangePlan nx = exchange_plan(nxt, m_planes, nw, nb, r, m_reach);
+                int64_t left_dst = 0, right_dst = 0;
+                if (L) left_dst = owned(r - 1) + exchange_plan(nxt, m_planes, nw, nb, r - 1, m_reach).m_left;
+                if (R) right_dst = owned(r + 1);
+                SLAB_TRY(pbf_slab_push_state(k.sim, L ? nx.send_left_end : 0, left_dst, R ? nx.send_right_begin : owned(r), right_dst));
+                k.planned = true;
+                k.next_bounds = nb;
+                k.next_xp = nx;
             }
             SLAB_TRY(pbf_stage_update_velocity(k.sim));
             SLAB_TRY(pbf_slab_halo_sync(k.sim));
@@ -384,6 +418,7 @@ private:
     Scene m_scene;
     std::vector<int> m_dev;
     int m_world, m_ghost, m_margin, m_reach, m_replan;
+    bool m_push = getenv("PBF_SLAB_PUSH") == nullptr || getenv("PBF_SLAB_PUSH")[0] != '0';   // (A/B switch, like slab.py)
     int m_dims[3], m_planes;
     std::vector<Rank> m_rank;
     std::vector<int> m_bounds;
