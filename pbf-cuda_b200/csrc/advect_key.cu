@@ -20,14 +20,14 @@
 namespace pbf {
 
 constexpr int AK_THREADS = 256;
-constexpr int AK_PER = 4;                        // particles per thread: 48 B of pos and of vel = three 16-byte loads each
-constexpr int AK_TILE = AK_THREADS * AK_PER;
+constexpr int AK_PER_WIDE = 4;                   // particles per thread: 48 B of pos and of vel = three 16-byte loads each
+constexpr int64_t AK_SMALL_N = 256 * 1024;       // below: one particle per thread (a 32 000-particle scene is 125 blocks, not 32)
 constexpr int AK_BLOCKS_PER_SM = 8;              // persistent grid: a block keeps its digit counts over many tiles
 constexpr int AK_BINS = RADIX + 1;               // (one more bin per pass for the slots past n of the last tile)
 
 // VEC: pos / vel are 16-byte aligned (every cudaMalloc'ed or torch buffer is): a thread's four particles are six
 // 128-bit loads instead of 24 scalar ones.
-template <bool VEC>
+template <bool VEC, int AK_PER>
 __global__ void __launch_bounds__(AK_THREADS)
 advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
                   uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, uint4* __restrict__ cell_clear,
@@ -35,6 +35,7 @@ advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
                   const __grid_constant__ SlabInput si, const __grid_constant__ GridConsts g,
                   const __grid_constant__ SolverConsts c) {
     pdl_wait();   // (launch.cuh: nothing of the previous kernel is touched before this)
+    constexpr int AK_TILE = AK_THREADS * AK_PER;
     __shared__ uint32_t s_hist[MAX_PASSES * AK_BINS];
     for (int k = threadIdx.x; k < npass * AK_BINS; k += AK_THREADS) s_hist[k] = 0;
     __syncthreads();
@@ -52,7 +53,7 @@ advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
         const int64_t base = tile * AK_TILE + (int64_t)threadIdx.x * AK_PER;
         float pv[2][3 * AK_PER];
         const bool full = base + AK_PER <= n;
-        if (VEC && full) {
+        if (VEC && AK_PER == 4 && full) {
             const float4* p4 = reinterpret_cast<const float4*>(pos + 3 * base);
             const float4* v4 = reinterpret_cast<const float4*>(vel + 3 * base);
 #pragma unroll
@@ -83,8 +84,8 @@ advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
                  (cc.x >= si.need_right_from && i < si.send_right_begin)))
                 atomicOr(si.flags, (uint32_t)PBF_SLAB_FLAG_MIGRATION);
         }
-        if (full && !slab) {
-            *reinterpret_cast<uint4*>(keys + base) = make_uint4(key[0], key[1], key[2], key[3]);
+        if (AK_PER == 4 && full && !slab) {
+            *reinterpret_cast<uint4*>(keys + base) = make_uint4(key[0], key[1 % AK_PER], key[2 % AK_PER], key[3 % AK_PER]);
         } else {
 #pragma unroll
             for (int j = 0; j < AK_PER; j++)
@@ -128,8 +129,9 @@ advect_key_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
 cudaError_t preload_advect_key() {
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, advect_key_kernel<true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, advect_key_kernel<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, advect_key_kernel<true, AK_PER_WIDE>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, advect_key_kernel<false, AK_PER_WIDE>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, advect_key_kernel<false, 1>);
     return e;
 }
 
@@ -139,12 +141,15 @@ cudaError_t launch_advect_key(const float* pos, const float* vel, uint32_t* keys
     if (n <= 0) return cudaSuccess;
     static int sms = 0;   // (same for every device of a B200 box; a wrong count only changes the grid size)
     if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess) { cudaGetLastError(); sms = 148; }
-    const int64_t tiles = (n + AK_TILE - 1) / AK_TILE;
+    const int per = n < AK_SMALL_N ? 1 : AK_PER_WIDE;
+    const int64_t tiles = (n + (int64_t)AK_THREADS * per - 1) / ((int64_t)AK_THREADS * per);
     const unsigned blocks = (unsigned)(tiles < (int64_t)sms * AK_BLOCKS_PER_SM ? tiles : (int64_t)sms * AK_BLOCKS_PER_SM);
-    if ((((uintptr_t)pos | (uintptr_t)vel) & 15u) == 0)
-        PBF_LAUNCH((advect_key_kernel<true>), blocks, AK_THREADS, 0, st, pos, vel, keys, hist, reinterpret_cast<uint4*>(cell_clear), n, npass, si, g, c);
+    if (per == 1)
+        PBF_LAUNCH((advect_key_kernel<false, 1>), blocks, AK_THREADS, 0, st, pos, vel, keys, hist, reinterpret_cast<uint4*>(cell_clear), n, npass, si, g, c);
+    else if ((((uintptr_t)pos | (uintptr_t)vel) & 15u) == 0)
+        PBF_LAUNCH((advect_key_kernel<true, AK_PER_WIDE>), blocks, AK_THREADS, 0, st, pos, vel, keys, hist, reinterpret_cast<uint4*>(cell_clear), n, npass, si, g, c);
     else
-        PBF_LAUNCH((advect_key_kernel<false>), blocks, AK_THREADS, 0, st, pos, vel, keys, hist, reinterpret_cast<uint4*>(cell_clear), n, npass, si, g, c);
+        PBF_LAUNCH((advect_key_kernel<false, AK_PER_WIDE>), blocks, AK_THREADS, 0, st, pos, vel, keys, hist, reinterpret_cast<uint4*>(cell_clear), n, npass, si, g, c);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
