@@ -127,65 +127,65 @@ __device__ __forceinline__ void gather(const float4 p, const uint32_t self, cons
             const uint32_t mxy = MORTON ? (__ldg(g.morton + cx) | __ldg(g.morton + 1024 + cy)) : 0u;
 #pragma unroll 1
             for (int zi = 0; zi < (MORTON ? 3 : 1); zi++) {
-            uint32_t start, end;
-            if (MORTON) {   // one cell per run
-                const int cz = cc.z + zi - 1;
-                if (cz < 0 || cz >= g.dim[2]) continue;
-                const uint2 r = __ldg(&cell_range[mxy | __ldg(g.morton + 2048 + cz)]);
-                start = r.x;
-                end = r.y;
-            } else {
-            // the run = from the first slot of the first non-empty cell of the column's (up to) three to the
-            // end of the last non-empty one; empty and out-of-range cells read {0, 0}, so an empty column gives
-            // start == end == 0. Straight-line on purpose: as a loop over z (1-3 trips) this was ~80 instructions.
-            const uint2 zero = make_uint2(0u, 0u);
-            const uint2 r0 = has_below ? __ldg(&cell_range[cbase + cc.z - 1]) : zero;
-            const uint2 r1 = __ldg(&cell_range[cbase + cc.z]);
-            const uint2 r2 = has_above ? __ldg(&cell_range[cbase + cc.z + 1]) : zero;
-            const bool e0 = r0.y > r0.x, e1 = r1.y > r1.x, e2 = r2.y > r2.x;
-            start = e0 ? r0.x : e1 ? r1.x : r2.x;
-            end = e2 ? r2.y : e1 ? r1.y : r0.y;
-            }
-#pragma unroll 1
-            for (uint32_t b = start & ((CULL_WIDE && !STAGED) ? ~7u : ~3u); b < end; b += 32) {   // words start at multiples of four (eight) slots
-                const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
-                const uint32_t groups = (CULL_WIDE && !STAGED) ? ((cnt + 7) >> 3) << 1 : (cnt + 3) >> 2;   // (in units of four slots)
-                uint32_t hits = 0;
-                if (CULL_WIDE && !STAGED) {
-#pragma unroll 1
-                    for (uint32_t gi = 0; gi < groups; gi += 2) {   // eight candidates: 3 loads, 28 packed flops, 8 shifts
-                        const float8 X = ldg256(soa.xs + b + 4 * gi), Y = ldg256(soa.ys + b + 4 * gi), Z = ldg256(soa.zs + b + 4 * gi);
-                        hits = push_hits2(hits, px, py, pz, lim, X.lo.x, X.lo.y, Y.lo.x, Y.lo.y, Z.lo.x, Z.lo.y);
-                        hits = push_hits2(hits, px, py, pz, lim, X.lo.z, X.lo.w, Y.lo.z, Y.lo.w, Z.lo.z, Z.lo.w);
-                        hits = push_hits2(hits, px, py, pz, lim, X.hi.x, X.hi.y, Y.hi.x, Y.hi.y, Z.hi.x, Z.hi.y);
-                        hits = push_hits2(hits, px, py, pz, lim, X.hi.z, X.hi.w, Y.hi.z, Y.hi.w, Z.hi.z, Z.hi.w);
-                    }
-                } else if (STAGED) {
-                    const int run = (dx + 1) * 3 + (dy + 1);
-                    uint32_t a = st_base + ((uint32_t)run * 3u * STAGE_CAP + (b - st_ubase[run])) * 4u;
-#pragma unroll 1
-                    for (uint32_t gi = 0; gi < groups; gi++, a += 16u) {  // the same four candidates out of shared memory
-                        const float4 X = lds128(a), Y = lds128(a + STAGE_CAP * 4u), Z = lds128(a + 2u * STAGE_CAP * 4u);
-                        hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
-                        hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
-                    }
+                uint32_t start, end;
+                if (MORTON) {   // one cell per run
+                    const int cz = cc.z + zi - 1;
+                    if (cz < 0 || cz >= g.dim[2]) continue;
+                    const uint2 r = __ldg(&cell_range[mxy | __ldg(g.morton + 2048 + cz)]);
+                    start = r.x;
+                    end = r.y;
                 } else {
-                    const float4* xp = reinterpret_cast<const float4*>(soa.xs + b);
-                    const float4* yp = reinterpret_cast<const float4*>(soa.ys + b);
-                    const float4* zp = reinterpret_cast<const float4*>(soa.zs + b);
-#pragma unroll CULL_UNROLL
-                    for (uint32_t gi = 0; gi < groups; gi++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
-                        const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
-                        hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
-                        hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
-                    }
+                    // the run = from the first slot of the first non-empty cell of the column's (up to) three to the
+                    // end of the last non-empty one; empty and out-of-range cells read {0, 0}, so an empty column gives
+                    // start == end == 0. Straight-line on purpose: as a loop over z (1-3 trips) this was ~80 instructions.
+                    const uint2 zero = make_uint2(0u, 0u);
+                    const uint2 r0 = has_below ? __ldg(&cell_range[cbase + cc.z - 1]) : zero;
+                    const uint2 r1 = __ldg(&cell_range[cbase + cc.z]);
+                    const uint2 r2 = has_above ? __ldg(&cell_range[cbase + cc.z + 1]) : zero;
+                    const bool e0 = r0.y > r0.x, e1 = r1.y > r1.x, e2 = r2.y > r2.x;
+                    start = e0 ? r0.x : e1 ? r1.x : r2.x;
+                    end = e2 ? r2.y : e1 ? r1.y : r0.y;
                 }
-                // first slot to the top bit; drop the slots before the run and what was read past its end
-                hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt)) & (0xffffffffu >> (b < start ? start - b : 0));
-                *tail = make_uint2(b, hits);
-                tail += hits ? GATHER_THREADS : 0;
-                if (tail == words_end) flush();
-            }
+#pragma unroll 1
+                for (uint32_t b = start & ((CULL_WIDE && !STAGED) ? ~7u : ~3u); b < end; b += 32) {   // words start at multiples of four (eight) slots
+                    const uint32_t cnt = min(end - b, 32u);   // slots of this word up to the end of the run
+                    const uint32_t groups = (CULL_WIDE && !STAGED) ? ((cnt + 7) >> 3) << 1 : (cnt + 3) >> 2;   // (in units of four slots)
+                    uint32_t hits = 0;
+                    if (CULL_WIDE && !STAGED) {
+#pragma unroll 1
+                        for (uint32_t gi = 0; gi < groups; gi += 2) {   // eight candidates: 3 loads, 28 packed flops, 8 shifts
+                            const float8 X = ldg256(soa.xs + b + 4 * gi), Y = ldg256(soa.ys + b + 4 * gi), Z = ldg256(soa.zs + b + 4 * gi);
+                            hits = push_hits2(hits, px, py, pz, lim, X.lo.x, X.lo.y, Y.lo.x, Y.lo.y, Z.lo.x, Z.lo.y);
+                            hits = push_hits2(hits, px, py, pz, lim, X.lo.z, X.lo.w, Y.lo.z, Y.lo.w, Z.lo.z, Z.lo.w);
+                            hits = push_hits2(hits, px, py, pz, lim, X.hi.x, X.hi.y, Y.hi.x, Y.hi.y, Z.hi.x, Z.hi.y);
+                            hits = push_hits2(hits, px, py, pz, lim, X.hi.z, X.hi.w, Y.hi.z, Y.hi.w, Z.hi.z, Z.hi.w);
+                        }
+                    } else if (STAGED) {
+                        const int run = (dx + 1) * 3 + (dy + 1);
+                        uint32_t a = st_base + ((uint32_t)run * 3u * STAGE_CAP + (b - st_ubase[run])) * 4u;
+#pragma unroll 1
+                        for (uint32_t gi = 0; gi < groups; gi++, a += 16u) {  // the same four candidates out of shared memory
+                            const float4 X = lds128(a), Y = lds128(a + STAGE_CAP * 4u), Z = lds128(a + 2u * STAGE_CAP * 4u);
+                            hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
+                            hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
+                        }
+                    } else {
+                        const float4* xp = reinterpret_cast<const float4*>(soa.xs + b);
+                        const float4* yp = reinterpret_cast<const float4*>(soa.ys + b);
+                        const float4* zp = reinterpret_cast<const float4*>(soa.zs + b);
+#pragma unroll CULL_UNROLL
+                        for (uint32_t gi = 0; gi < groups; gi++) {  // four candidates: 3 loads, 14 packed flops, 4 shifts
+                            const float4 X = __ldg(xp + gi), Y = __ldg(yp + gi), Z = __ldg(zp + gi);
+                            hits = push_hits2(hits, px, py, pz, lim, X.x, X.y, Y.x, Y.y, Z.x, Z.y);
+                            hits = push_hits2(hits, px, py, pz, lim, X.z, X.w, Y.z, Y.w, Z.z, Z.w);
+                        }
+                    }
+                    // first slot to the top bit; drop the slots before the run and what was read past its end
+                    hits = (hits << (32 - 4 * groups)) & (0xffffffffu << (32 - cnt)) & (0xffffffffu >> (b < start ? start - b : 0));
+                    *tail = make_uint2(b, hits);
+                    tail += hits ? GATHER_THREADS : 0;
+                    if (tail == words_end) flush();
+                }
             }
         }
     }
